@@ -1,0 +1,232 @@
+/*
+ * ismpc_b200.h -- C ABI of the B200-native batched ISMPC hot path.
+ *
+ * Drop-in boundary for the reference's gait MPC (paths relative to the
+ * reference repository FrancescoScotti/Quadruped_gait_generation_ISMPC):
+ *
+ *   * AMR_code_DART/MPCSolver.hpp:18-22   MPCSolver(ftsp_and_timings), State solve(State, WalkState, ftsp)
+ *       -> ismpc_formc_set_model (constructor work, MPCSolver.cpp:5-200) and
+ *          ismpc_formc_solve_batch (one tick of MPCSolver.cpp:204-501 for n independent instances)
+ *   * trotting/quad_as_bip_bang.m:99-290 == trotting/quad_as_bip_no_plots.m:117-307 ==
+ *     walking/quad_walk_no_plots.m:129-330  (canonical ISMPC with footsteps, the formulation whose
+ *     matrix shapes MPCSolver's constructor allocates, MPCSolver.cpp:34-54)
+ *       -> ismpc_forma_set_model / ismpc_forma_solve_batch / ismpc_forma_rollout
+ *   * AMR_code_DART/utils.cpp:89-90   Eigen::VectorXd solveQP(H, f, A, lbA, ubA)  (the qpOASES seam)
+ *       -> ismpc_qp_solve_batch
+ *
+ * The reference has no FFI: the seam is a C++ class used by one caller
+ * (AMR_code_DART/Controller.cpp:105-106,346-348).  This header is what a cgo/JNI/ctypes or C++
+ * binding for that seam binds; host/MPCSolver.hpp is the batch-of-1 C++ mirror of the class.
+ *
+ * Conventions: plain pointers and sizes, no CUDA/torch types.  `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream).  With ISMPC_MEM_DEVICE every data pointer is a device pointer, the
+ * call only enqueues work on `stream` and returns; with ISMPC_MEM_HOST every data pointer is a host
+ * pointer (pinned for best speed), the call copies in, launches, copies out and synchronises the
+ * stream before returning.  The caller owns all buffers; the handle owns only its workspace.  One
+ * handle per GPU, not shared between threads.  Functions return 0 or a negative ISMPC_ERR_* code;
+ * per-instance problems are reported in out[i].status -- the library never calls exit().
+ * There is no CPU fallback: every entry point fails with ISMPC_ERR_CUDA if no sm_100 device works.
+ */
+#ifndef ISMPC_B200_H
+#define ISMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ismpc_handle ismpc_handle;
+
+enum {
+    ISMPC_OK = 0,
+    ISMPC_ERR_ARG = -1,      /* bad argument (null pointer, n > max_batch, N > max, ...) */
+    ISMPC_ERR_CUDA = -2,     /* CUDA runtime error (see ismpc_last_cuda_error) */
+    ISMPC_ERR_MODEL = -3,    /* model not set / invalid for this call */
+    ISMPC_ERR_ALLOC = -4
+};
+
+enum { ISMPC_MEM_HOST = 0, ISMPC_MEM_DEVICE = 1 };
+
+/* per-instance status bits (out[i].status) */
+enum {
+    ISMPC_ST_OK = 0,
+    ISMPC_ST_Z_FAIL = 1,        /* vertical QP infeasible / iteration cap */
+    ISMPC_ST_X_FAIL = 2,        /* x QP infeasible / iteration cap */
+    ISMPC_ST_Y_FAIL = 4,        /* y QP infeasible / iteration cap */
+    ISMPC_ST_WINDOW = 8,        /* k0+2N exceeds the midpoint sequence: instance left untouched */
+    ISMPC_ST_XY_SKIPPED = 16,   /* lambda_0 <= 2: horizontal QPs skipped, u = 0 (MPCSolver.cpp:322) */
+    ISMPC_ST_NAN_GUARD = 32,    /* vertical state was NaN and was patched (MPCSolver.cpp:277-278) */
+    ISMPC_ST_QP_FAIL = 64       /* form A / generic QP infeasible or iteration cap */
+};
+
+#define ISMPC_MAX_N 512          /* largest horizon / variable count per axis supported by the kernels */
+#define ISMPC_MAX_FSTEPS 8       /* largest number of predicted footsteps F (form A) */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Types shared by both formulations                                                           */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Subset of `State` that solve() reads/writes (AMR_code_DART/types.hpp:7-29; MPCSolver.cpp:251,
+ * 315-317 read comPos/comVel, :275-276,:419-422 write them; zmpPos is carried through untouched). */
+typedef struct { double com_pos[3], com_vel[3], zmp_pos[3]; } ismpc_state_t;
+
+/* `WalkState` (AMR_code_DART/types.hpp:76-81). */
+typedef struct {
+    double sim_time;            /* simulationTime, in control ticks (k0 = (int)(sim_time/(dt/dtc))) */
+    int32_t mpc_iter, control_iter, footstep_counter, support_foot;
+} ismpc_walk_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Formulation C: what MPCSolver::solve builds and solves (3 QPs per tick: z, x, y)            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* The reference's compile-time constants (AMR_code_DART/parameters.cpp:9-45, MPCSolver.cpp:253-255,
+ * :159) that the constructor bakes into the vertical prediction matrices. */
+typedef struct {
+    double dt;                  /* mpcTimeStep            0.01  */
+    double dtc;                 /* controlTimeStep        0.01  */
+    double mass;                /* mass_hrp4              50    */
+    double g;                   /* g                      9.81  */
+    double q_p, q_v, q_u;       /* 1005000, 100, 0.01          */
+    double fz_max;              /* 10000                        */
+    int32_t N;                  /* prediction samples     100   */
+    int32_t reserved;
+} ismpc_formc_model_t;
+
+/* Per-instance values of what are globals in the reference (they vary across a batch). */
+typedef struct {
+    double com_height;          /* comTargetHeight 0.69 -> h_des and eta = sqrt(g/h) */
+    double box_w;               /* footConstraintSquareWidth 0.09 */
+    double box_w_init;          /* full width used while footstep_counter <= 1: 2.0 (MPCSolver.cpp:334-337) */
+    int32_t S, F_ds;            /* single / double support samples: 35, 10 */
+    int32_t plan_first_row;     /* first row of this instance's footstep plan in plan_xyzt */
+    int32_t n_steps;            /* rows of the plan (ftsp_and_timings.rows(), Controller.cpp:89-97: 40) */
+} ismpc_formc_inst_t;
+
+typedef struct {
+    ismpc_state_t next;         /* com_pos/com_vel updated, zmp_pos copied (MPCSolver.cpp:500) */
+    double zmp_in[2];           /* decisionVariables_x(0), _y(0)  (MPCSolver.cpp:402-403) */
+    double fz0;                 /* decisionVariables_z(0) */
+    double lambda0;             /* lambda(0) (MPCSolver.cpp:306) */
+    double kkt_res;             /* max KKT residual over the three QPs (self-check) */
+    int32_t status;             /* ISMPC_ST_* */
+    int32_t iters[3];           /* working-set iterations z, x, y */
+} ismpc_formc_out_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Formulation A: canonical ISMPC with footsteps (1 QP per tick, x and y stacked)              */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    double dt;                  /* mpcTimeStep 0.01          quad_as_bip_bang.m:28 */
+    double g_eta;               /* 9.8 (eta = sqrt(g_eta/height))  quad_as_bip_bang.m:31 */
+    double q_zdot, q_foot;      /* 1, 1e7 (trot) / 1e9 (walk)  quad_as_bip_bang.m:239-240 */
+    double disp_forw, disp_forw_dummy, disp_L;  /* init_quadruped.m:31-36, quad_as_bip_bang.m:11 */
+    int32_t C, P, F;            /* 100, 200, 3               quad_as_bip_bang.m:25-27 */
+    int32_t reserved;
+} ismpc_forma_model_t;
+
+typedef struct {
+    double st[6];               /* x, xd, xz, y, yd, yz      quad_as_bip_bang.m:44-49 */
+    double cur_fs[2];           /* current_xfs, current_yfs */
+    double fs_store[2];         /* xfs_store(fsCounter), yfs_store(fsCounter) (bang.m:195-198) */
+    double height;              /* CoM height -> eta */
+    double wx, wy;              /* ZMP box widths */
+    int32_t j;                  /* 1-based tick (MATLAB loop index) */
+    int32_t fs_counter;         /* 1-based fsCounter */
+    int32_t ds;                 /* dsSamples */
+    int32_t cl_first_ramp;      /* 1: initial centerline (bang.m:74-84); 0: rebuilt (bang.m:547-555) */
+    int32_t timing_first, n_timing;   /* this instance's fs_timing = fs_timing[timing_first .. +n_timing) */
+    int32_t plan_first_row, n_fs;     /* this instance's fs_plan rows (x,y) in fs_plan */
+} ismpc_forma_inst_t;
+
+typedef struct {
+    double st[6];               /* next x, xd, xz, y, yd, yz */
+    double pred_fs[2 * ISMPC_MAX_FSTEPS]; /* predicted_xfs(1..F) then predicted_yfs(1..F) at [F..2F) */
+    double kkt_res;
+    int32_t status, iters;
+} ismpc_forma_out_t;
+
+/* impulsive push (bang.m:104-114): if fs_counter==fs && ct in [ct0,ct1): xd += dt*ax; yd += dt*ay */
+typedef struct { int32_t fs, ct0, ct1, reserved; double ax, ay; } ismpc_push_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Entry points                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+
+const char* ismpc_version(void);
+const char* ismpc_error_string(int code);
+
+/* Create/destroy a handle on CUDA device `device` able to process up to max_batch instances per call. */
+int ismpc_create(ismpc_handle** out, int device, int max_batch);
+int ismpc_destroy(ismpc_handle* h);
+/* Text of the last CUDA error seen by this handle ("" if none). */
+const char* ismpc_last_cuda_error(const ismpc_handle* h);
+/* Number of kernels this handle has launched since creation (for the benchmark's launch count). */
+int64_t ismpc_kernel_launches(const ismpc_handle* h);
+
+/* MPCSolver::MPCSolver (MPCSolver.cpp:5-200): builds on the device the vertical prediction/cost tables
+ * (H_z^-1 and friends) for this model.  Must be called before ismpc_formc_solve_batch. */
+int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* model);
+
+/* One tick of MPCSolver::solve (MPCSolver.cpp:204-501) for n independent instances.
+ * plan_xyzt: plan_rows x 4 doubles row-major (x, y, z, t) -- ftsp_and_timings (Controller.cpp:89-97).
+ * primal_opt (nullable): n x 3N doubles  [f(N) | u_x(N) | u_y(N)] per instance.
+ * active_opt (nullable): n x 3N int8    [S_bar_z rows | x box rows | y box rows], -1 lower / 0 / +1 upper,
+ *                        the convention of QProblem::getWorkingSetConstraints (qpOASES/QProblem.cpp:809-829);
+ *                        equality rows are always active and not reported. */
+int ismpc_formc_solve_batch(ismpc_handle* h, int n,
+                            const ismpc_state_t* state, const ismpc_walk_t* walk,
+                            const ismpc_formc_inst_t* inst,
+                            const double* plan_xyzt, int plan_rows,
+                            ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt,
+                            int mem, void* stream);
+
+/* Closed loop: n_ticks consecutive ticks on the device, state/walk advanced in place exactly as
+ * Controller::update would (Controller.cpp:503-504: ++controlIter, mpcIter; sim_time += 1), no host
+ * round trip between ticks.  push (nullable, n entries): velocity impulse on ticks
+ * [ct0,ct1) counted from the start of the rollout.  traj_opt (nullable): n x n_ticks x 6 doubles
+ * (com_pos, com_vel) after each tick.  status_opt (nullable): n int32, OR of per-tick status. */
+int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks,
+                        ismpc_state_t* state, ismpc_walk_t* walk, const ismpc_formc_inst_t* inst,
+                        const double* plan_xyzt, int plan_rows, const ismpc_push_t* push,
+                        double* traj_opt, int32_t* status_opt, int mem, void* stream);
+
+int ismpc_forma_set_model(ismpc_handle* h, const ismpc_forma_model_t* model);
+
+/* One tick of the MATLAB loop body (build QP-1, solve, integrate) for n independent instances.
+ * fs_timing: int32 table; fs_plan: rows x 2 doubles.
+ * primal_opt (nullable): n x 2(C+F) doubles [zd_x(C) | x_f(F) | zd_y(C) | y_f(F)].
+ * active_opt (nullable): n x 2(C+F) int8 [ZMP_x(C) | ZMP_y(C) | kin_x(F) | kin_y(F)] (the two stability
+ *                        equality rows are always active and not reported). */
+int ismpc_forma_solve_batch(ismpc_handle* h, int n, const ismpc_forma_inst_t* inst,
+                            const int32_t* fs_timing, int timing_len,
+                            const double* fs_plan, int plan_rows,
+                            ismpc_forma_out_t* out, double* primal_opt, int8_t* active_opt,
+                            int mem, void* stream);
+
+/* Closed loop of the MATLAB scripts (bang.m:99-563, QP-1 loop): n_ticks ticks on the device with the
+ * footstep switch, plan shift and centerline rebuild (bang.m:529-563).  inst is advanced in place;
+ * fs_plan is modified in place (per-instance rows are shifted at every switch).
+ * traj_opt (nullable): n x n_ticks x 6 doubles (x, y, xd, yd, xz, yz) after each tick. */
+int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                        const int32_t* fs_timing, int timing_len,
+                        double* fs_plan, int plan_rows, const ismpc_push_t* push,
+                        double* traj_opt, int32_t* status_opt, int mem, void* stream);
+
+/* solveQP(H, f, A, lbA, ubA) (AMR_code_DART/utils.cpp:89-139) for n independent dense QPs of one shape:
+ * min 1/2 x'Hx + g'x  s.t. lbA <= A x <= ubA.  H: n x nV x nV, g: n x nV, A: n x nC x nV (row-major),
+ * lbA/ubA: n x nC.  x: n x nV.  y_opt (nullable): n x nC constraint duals (qpOASES sign);
+ * ws_opt (nullable): n x nC int8 working set; status: n int32 (0 ok, ISMPC_ST_QP_FAIL otherwise);
+ * iters_opt (nullable): n int32. */
+int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC,
+                         const double* H, const double* g, const double* A,
+                         const double* lbA, const double* ubA,
+                         double* x, double* y_opt, int8_t* ws_opt, int32_t* status, int32_t* iters_opt,
+                         int mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISMPC_B200_H */

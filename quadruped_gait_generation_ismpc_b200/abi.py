@@ -1,0 +1,62 @@
+"""numpy mirrors of the POD structs in include/ismpc_b200.h (layout checked by tests/test_abi.py).
+
+Host-side plumbing only: these dtypes describe the byte layout of the batch arrays that cross the
+C ABI.  Field names follow the reference (AMR_code_DART/types.hpp:7-81, parameters.cpp:9-45,
+trotting/quad_as_bip_bang.m:25-58).
+"""
+import numpy as np
+
+MAX_FSTEPS = 8
+
+STATE = np.dtype([("com_pos", "f8", 3), ("com_vel", "f8", 3), ("zmp_pos", "f8", 3)], align=True)
+WALK = np.dtype([("sim_time", "f8"), ("mpc_iter", "i4"), ("control_iter", "i4"),
+                 ("footstep_counter", "i4"), ("support_foot", "i4")], align=True)
+FORMC_MODEL = np.dtype([("dt", "f8"), ("dtc", "f8"), ("mass", "f8"), ("g", "f8"),
+                        ("q_p", "f8"), ("q_v", "f8"), ("q_u", "f8"), ("fz_max", "f8"),
+                        ("N", "i4"), ("reserved", "i4")], align=True)
+FORMC_INST = np.dtype([("com_height", "f8"), ("box_w", "f8"), ("box_w_init", "f8"),
+                       ("S", "i4"), ("F_ds", "i4"), ("plan_first_row", "i4"), ("n_steps", "i4")], align=True)
+FORMC_OUT = np.dtype([("next", STATE), ("zmp_in", "f8", 2), ("fz0", "f8"), ("lambda0", "f8"),
+                      ("kkt_res", "f8"), ("status", "i4"), ("iters", "i4", 3)], align=True)
+FORMA_MODEL = np.dtype([("dt", "f8"), ("g_eta", "f8"), ("q_zdot", "f8"), ("q_foot", "f8"),
+                        ("disp_forw", "f8"), ("disp_forw_dummy", "f8"), ("disp_L", "f8"),
+                        ("C", "i4"), ("P", "i4"), ("F", "i4"), ("reserved", "i4")], align=True)
+FORMA_INST = np.dtype([("st", "f8", 6), ("cur_fs", "f8", 2), ("fs_store", "f8", 2), ("height", "f8"),
+                       ("wx", "f8"), ("wy", "f8"), ("j", "i4"), ("fs_counter", "i4"), ("ds", "i4"),
+                       ("cl_first_ramp", "i4"), ("timing_first", "i4"), ("n_timing", "i4"),
+                       ("plan_first_row", "i4"), ("n_fs", "i4")], align=True)
+FORMA_OUT = np.dtype([("st", "f8", 6), ("pred_fs", "f8", 2 * MAX_FSTEPS), ("kkt_res", "f8"),
+                      ("status", "i4"), ("iters", "i4")], align=True)
+PUSH = np.dtype([("fs", "i4"), ("ct0", "i4"), ("ct1", "i4"), ("reserved", "i4"),
+                 ("ax", "f8"), ("ay", "f8")], align=True)
+
+SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
+         "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
+         "ismpc_forma_out_t": 192, "ismpc_push_t": 32}
+DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
+          "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
+          "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
+          "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH}
+
+# status bits
+ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+def formc_model(dt=0.01, dtc=0.01, mass=50.0, g=9.81, q_p=1005000.0, q_v=100.0, q_u=0.01,
+                fz_max=10000.0, N=100):
+    """Reference constants: AMR_code_DART/parameters.cpp:9-45, MPCSolver.cpp:159,253-255."""
+    m = np.zeros(1, dtype=FORMC_MODEL)
+    m["dt"], m["dtc"], m["mass"], m["g"] = dt, dtc, mass, g
+    m["q_p"], m["q_v"], m["q_u"], m["fz_max"], m["N"] = q_p, q_v, q_u, fz_max, N
+    return m
+
+
+def forma_model(dt=0.01, g_eta=9.8, q_zdot=1.0, q_foot=1e7, disp_forw=0.5, disp_forw_dummy=0.25,
+                disp_L=0.4, C=100, P=200, F=3):
+    """Reference constants: trotting/quad_as_bip_bang.m:11,25-31,239-240; init_quadruped.m:31-36."""
+    m = np.zeros(1, dtype=FORMA_MODEL)
+    m["dt"], m["g_eta"], m["q_zdot"], m["q_foot"] = dt, g_eta, q_zdot, q_foot
+    m["disp_forw"], m["disp_forw_dummy"], m["disp_L"] = disp_forw, disp_forw_dummy, disp_L
+    m["C"], m["P"], m["F"] = C, P, F
+    return m
