@@ -1,0 +1,208 @@
+"""ctypes binding of the C ABI in include/ismpc_b200.h (the CUDA library, built in-tree under lib/).
+
+This is the reference-side binding a Python caller would use; there is NO CPU fallback: if the shared
+library is missing, or no sm_100 device works, every call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libismpc_b200.so")
+EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy", "ismpc_last_cuda_error",
+           "ismpc_kernel_launches", "ismpc_formc_set_model", "ismpc_formc_solve_batch", "ismpc_formc_rollout",
+           "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch"]
+
+_lib = None
+
+
+class IsmpcError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise IsmpcError("nvcc build failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IsmpcError("CUDA library %s is missing: run __graft_entry__.build() (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.ismpc_version.restype = C.c_char_p
+    L.ismpc_error_string.restype = C.c_char_p
+    L.ismpc_error_string.argtypes = [C.c_int]
+    L.ismpc_last_cuda_error.restype = C.c_char_p
+    L.ismpc_last_cuda_error.argtypes = [C.c_void_p]
+    L.ismpc_kernel_launches.restype = C.c_int64
+    L.ismpc_kernel_launches.argtypes = [C.c_void_p]
+    L.ismpc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.ismpc_destroy.argtypes = [C.c_void_p]
+    L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
+    L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_forma_set_model.argtypes = [C.c_void_p, C.c_void_p]
+    L.ismpc_forma_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_forma_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """Pointer of a numpy array (host), an int (device address) or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Handle:
+    """One handle per GPU (include/ismpc_b200.h: ismpc_create / ismpc_destroy)."""
+
+    def __init__(self, device=0, max_batch=65536):
+        self._L = lib()
+        self._h = C.c_void_p()
+        rc = self._L.ismpc_create(C.byref(self._h), device, max_batch)
+        if rc != 0:
+            raise IsmpcError("ismpc_create failed: %s (no sm_100 CUDA device? there is no CPU fallback)"
+                             % self._L.ismpc_error_string(rc).decode())
+        self.max_batch = max_batch
+        self.formc = None
+        self.forma = None
+
+    def close(self):
+        if self._h:
+            self._L.ismpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise IsmpcError("%s: %s [%s]" % (what, self._L.ismpc_error_string(rc).decode(),
+                                             self._L.ismpc_last_cuda_error(self._h).decode()))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.ismpc_kernel_launches(self._h))
+
+    # ---- formulation C -------------------------------------------------------------------------
+    def formc_set_model(self, model):
+        self._check(self._L.ismpc_formc_set_model(self._h, _ptr(model)), "ismpc_formc_set_model")
+        self.formc = model.copy()
+
+    def formc_solve_batch(self, state, walk, inst, plan, want_primal=True, want_active=True):
+        """Host-memory call (numpy arrays in, numpy arrays out)."""
+        n = len(state)
+        N = int(self.formc["N"][0])
+        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        out = np.zeros(n, dtype=abi.FORMC_OUT)
+        primal = np.zeros((n, 3 * N)) if want_primal else None
+        active = np.zeros((n, 3 * N), dtype=np.int8) if want_active else None
+        rc = self._L.ismpc_formc_solve_batch(self._h, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
+                                             plan.shape[0], _ptr(out), _ptr(primal), _ptr(active), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_formc_solve_batch")
+        return dict(out=out, primal=primal, active=active)
+
+    def formc_solve_batch_raw(self, n, state, walk, inst, plan, plan_rows, out, primal=None, active=None,
+                              mem=abi.MEM_DEVICE, stream=None):
+        """Raw call: every argument is a numpy array (host) or an integer address (device)."""
+        rc = self._L.ismpc_formc_solve_batch(self._h, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan), plan_rows,
+                                             _ptr(out), _ptr(primal), _ptr(active), mem,
+                                             C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_formc_solve_batch")
+
+    def formc_rollout(self, state, walk, inst, plan, n_ticks, push=None, want_traj=True):
+        n = len(state)
+        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        state = state.copy(); walk = walk.copy()
+        traj = np.zeros((n, n_ticks, 6)) if want_traj else None
+        status = np.zeros(n, dtype=np.int32)
+        rc = self._L.ismpc_formc_rollout(self._h, n, n_ticks, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
+                                         plan.shape[0], _ptr(push), _ptr(traj), _ptr(status), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_formc_rollout")
+        return dict(state=state, walk=walk, traj=traj, status=status)
+
+    def formc_rollout_raw(self, n, n_ticks, state, walk, inst, plan, plan_rows, push=None, traj=None, status=None,
+                          mem=abi.MEM_DEVICE, stream=None):
+        rc = self._L.ismpc_formc_rollout(self._h, n, n_ticks, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
+                                         plan_rows, _ptr(push), _ptr(traj), _ptr(status), mem,
+                                         C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_formc_rollout")
+
+    # ---- formulation A -------------------------------------------------------------------------
+    def forma_set_model(self, model):
+        self._check(self._L.ismpc_forma_set_model(self._h, _ptr(model)), "ismpc_forma_set_model")
+        self.forma = model.copy()
+
+    def forma_solve_batch(self, inst, fs_timing, fs_plan, want_primal=True, want_active=True):
+        n = len(inst)
+        nV = 2 * (int(self.forma["C"][0]) + int(self.forma["F"][0]))
+        fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
+        fs_plan = np.ascontiguousarray(fs_plan, dtype=np.float64)
+        out = np.zeros(n, dtype=abi.FORMA_OUT)
+        primal = np.zeros((n, nV)) if want_primal else None
+        active = np.zeros((n, nV), dtype=np.int8) if want_active else None
+        rc = self._L.ismpc_forma_solve_batch(self._h, n, _ptr(inst), _ptr(fs_timing), len(fs_timing), _ptr(fs_plan),
+                                             fs_plan.shape[0], _ptr(out), _ptr(primal), _ptr(active), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_forma_solve_batch")
+        return dict(out=out, primal=primal, active=active)
+
+    def forma_solve_batch_raw(self, n, inst, fs_timing, timing_len, fs_plan, plan_rows, out, primal=None, active=None,
+                              mem=abi.MEM_DEVICE, stream=None):
+        rc = self._L.ismpc_forma_solve_batch(self._h, n, _ptr(inst), _ptr(fs_timing), timing_len, _ptr(fs_plan),
+                                             plan_rows, _ptr(out), _ptr(primal), _ptr(active), mem,
+                                             C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_forma_solve_batch")
+
+    def forma_rollout(self, inst, fs_timing, fs_plan, n_ticks, push=None, want_traj=True):
+        n = len(inst)
+        inst = inst.copy()
+        fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
+        fs_plan = np.array(fs_plan, dtype=np.float64)
+        traj = np.zeros((n, n_ticks, 6)) if want_traj else None
+        status = np.zeros(n, dtype=np.int32)
+        rc = self._L.ismpc_forma_rollout(self._h, n, n_ticks, _ptr(inst), _ptr(fs_timing), len(fs_timing),
+                                         _ptr(fs_plan), fs_plan.shape[0], _ptr(push), _ptr(traj), _ptr(status),
+                                         abi.MEM_HOST, None)
+        self._check(rc, "ismpc_forma_rollout")
+        return dict(inst=inst, fs_plan=fs_plan, traj=traj, status=status)
+
+    def forma_rollout_raw(self, n, n_ticks, inst, fs_timing, timing_len, fs_plan, plan_rows, push=None, traj=None,
+                          status=None, mem=abi.MEM_DEVICE, stream=None):
+        rc = self._L.ismpc_forma_rollout(self._h, n, n_ticks, _ptr(inst), _ptr(fs_timing), timing_len, _ptr(fs_plan),
+                                         plan_rows, _ptr(push), _ptr(traj), _ptr(status), mem,
+                                         C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_forma_rollout")
+
+    # ---- generic dense QP (solveQP seam) ----------------------------------------------------------
+    def qp_solve_batch(self, H, g, A, lbA, ubA):
+        H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        lbA = np.ascontiguousarray(lbA, dtype=np.float64); ubA = np.ascontiguousarray(ubA, dtype=np.float64)
+        n, nV = H.shape[0], H.shape[1]
+        nC = A.shape[1]
+        x = np.zeros((n, nV)); y = np.zeros((n, nC)); ws = np.zeros((n, nC), dtype=np.int8)
+        status = np.zeros(n, dtype=np.int32); iters = np.zeros(n, dtype=np.int32)
+        rc = self._L.ismpc_qp_solve_batch(self._h, n, nV, nC, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA),
+                                          _ptr(x), _ptr(y), _ptr(ws), _ptr(status), _ptr(iters), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_qp_solve_batch")
+        return dict(x=x, y=y, ws=ws, status=status, iters=iters)

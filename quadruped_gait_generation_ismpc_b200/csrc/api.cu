@@ -1,0 +1,391 @@
+// api.cu -- the C ABI (include/ismpc_b200.h): handle, staging for host-memory calls, kernel launches.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "formc.cuh"
+#include "forma.cuh"
+#include "launch.h"
+
+using namespace ismpc;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ismpc_handle {
+    int device = 0;
+    int max_batch = 0;
+    int sm_count = 148;
+    long long launches = 0;
+    char err[256] = {0};
+    // form C
+    bool formc_ready = false;
+    ismpc_formc_model_t cm{};
+    DevBuf c_tables, c_work, c_info;
+    // form A
+    bool forma_ready = false;
+    ismpc_forma_model_t am{};
+    // staging (host-memory calls)
+    DevBuf s_state, s_walk, s_cinst, s_cout, s_plan, s_primal, s_active, s_push, s_traj, s_status;
+    DevBuf s_ainst, s_aout, s_timing, a_Lwork;
+    DevBuf q_in, q_out, q_work;
+};
+
+static int fail_cuda(ismpc_handle* h, cudaError_t e, const char* where)
+{
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
+    return ISMPC_ERR_CUDA;
+}
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return fail_cuda(h, e_, #call);         \
+    } while (0)
+
+extern "C" const char* ismpc_version(void) { return "ismpc-b200 0.1 (sm_100a)"; }
+
+extern "C" const char* ismpc_error_string(int code)
+{
+    switch (code) {
+        case ISMPC_OK: return "ok";
+        case ISMPC_ERR_ARG: return "bad argument";
+        case ISMPC_ERR_CUDA: return "CUDA error";
+        case ISMPC_ERR_MODEL: return "model not set or invalid";
+        case ISMPC_ERR_ALLOC: return "allocation failed";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int ismpc_create(ismpc_handle** out, int device, int max_batch)
+{
+    if (!out || max_batch <= 0) return ISMPC_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ISMPC_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ISMPC_ERR_CUDA;
+    if (prop.major < 10) return ISMPC_ERR_CUDA;   // sm_100a code only: no fallback path exists
+    if (cudaSetDevice(device) != cudaSuccess) return ISMPC_ERR_CUDA;
+    ismpc_handle* h = new (std::nothrow) ismpc_handle();
+    if (!h) return ISMPC_ERR_ALLOC;
+    h->device = device; h->max_batch = max_batch; h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_destroy(ismpc_handle* h)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    cudaSetDevice(h->device);
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
+                     &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
+                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->q_in, &h->q_out, &h->q_work};
+    for (DevBuf* b : all) b->release();
+    delete h;
+    return ISMPC_OK;
+}
+
+extern "C" const char* ismpc_last_cuda_error(const ismpc_handle* h) { return h ? h->err : ""; }
+extern "C" int64_t ismpc_kernel_launches(const ismpc_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// Formulation C
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* m)
+{
+    if (!h || !m) return ISMPC_ERR_ARG;
+    if (m->N < 2 || m->N > ISMPC_MAX_N || !(m->dt > 0) || !(m->dtc > 0) || !(m->mass > 0) || !(m->q_u > 0))
+        return ISMPC_ERR_MODEL;
+    CK(cudaSetDevice(h->device));
+    const size_t NN = (size_t)m->N * m->N;
+    if (h->c_tables.ensure(3 * NN * sizeof(double)) || h->c_work.ensure(3 * NN * sizeof(double)) ||
+        h->c_info.ensure(sizeof(int)))
+        return ISMPC_ERR_ALLOC;
+    CK(cudaMemset(h->c_info.p, 0, sizeof(int)));
+    double* T = (double*)h->c_tables.p;
+    int rc = formc_setup_launch(*m, (double*)h->c_work.p, T, T + NN, T + 2 * NN, (int*)h->c_info.p, 0, &h->launches);
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_setup_launch");
+    int info = 0;
+    CK(cudaMemcpy(&info, h->c_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info != 0) return ISMPC_ERR_MODEL;     // H_z not positive definite
+    h->cm = *m;
+    h->formc_ready = true;
+    return ISMPC_OK;
+}
+
+static void formc_fill_args(ismpc_handle* h, FormCArgs& a, int n)
+{
+    const size_t NN = (size_t)h->cm.N * h->cm.N;
+    const double* T = (const double*)h->c_tables.p;
+    a.n = n; a.model = h->cm;
+    a.T.Hinv = T; a.T.G = T + NN; a.T.M = T + 2 * NN;
+}
+
+extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state_t* state, const ismpc_walk_t* walk,
+                                       const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
+                                       ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt, int mem,
+                                       void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!h->formc_ready) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || !state || !walk || !inst || !plan_xyzt || !out || plan_rows <= 0)
+        return ISMPC_ERR_ARG;
+    if (n == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cm.N;
+    FormCArgs a;
+    formc_fill_args(h, a, n);
+    if (mem == ISMPC_MEM_DEVICE) {
+        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt; a.plan_rows = plan_rows;
+        a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
+        int rc = formc_tick_launch(a, n, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t mb = (size_t)h->max_batch;
+    if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
+        h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t)) ||
+        h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double)))
+        return ISMPC_ERR_ALLOC;
+    if (primal_opt && h->s_primal.ensure(mb * 3 * N * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (active_opt && h->s_active.ensure(mb * 3 * N)) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
+    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = (const double*)h->s_plan.p; a.plan_rows = plan_rows;
+    a.out = (ismpc_formc_out_t*)h->s_cout.p;
+    a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
+    a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
+    int rc = formc_tick_launch(a, n, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
+    CK(cudaMemcpyAsync(out, h->s_cout.p, n * sizeof(ismpc_formc_out_t), cudaMemcpyDeviceToHost, st));
+    if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * 3 * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_state_t* state, ismpc_walk_t* walk,
+                                   const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
+                                   const ismpc_push_t* push, double* traj_opt, int32_t* status_opt, int mem,
+                                   void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!h->formc_ready) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || n_ticks < 0 || !state || !walk || !inst || !plan_xyzt || plan_rows <= 0)
+        return ISMPC_ERR_ARG;
+    if (n == 0 || n_ticks == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FormCArgs a;
+    formc_fill_args(h, a, n);
+    a.out = nullptr; a.primal = nullptr; a.active = nullptr; a.plan_rows = plan_rows;
+    if (mem == ISMPC_MEM_DEVICE) {
+        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt;
+        int rc = formc_rollout_launch(a, state, walk, push, n_ticks, traj_opt, status_opt, n, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t mb = (size_t)h->max_batch;
+    if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
+        h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double)))
+        return ISMPC_ERR_ALLOC;
+    if (push && h->s_push.ensure(mb * sizeof(ismpc_push_t))) return ISMPC_ERR_ALLOC;
+    if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (status_opt && h->s_status.ensure(mb * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (push) CK(cudaMemcpyAsync(h->s_push.p, push, n * sizeof(ismpc_push_t), cudaMemcpyHostToDevice, st));
+    a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
+    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = (const double*)h->s_plan.p;
+    int rc = formc_rollout_launch(a, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
+                                  push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
+                                  traj_opt ? (double*)h->s_traj.p : nullptr,
+                                  status_opt ? (int32_t*)h->s_status.p : nullptr, n, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
+    CK(cudaMemcpyAsync(state, h->s_state.p, n * sizeof(ismpc_state_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(walk, h->s_walk.p, n * sizeof(ismpc_walk_t), cudaMemcpyDeviceToHost, st));
+    if (traj_opt) CK(cudaMemcpyAsync(traj_opt, h->s_traj.p, (size_t)n * n_ticks * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status_opt) CK(cudaMemcpyAsync(status_opt, h->s_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Formulation A
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ismpc_forma_set_model(ismpc_handle* h, const ismpc_forma_model_t* m)
+{
+    if (!h || !m) return ISMPC_ERR_ARG;
+    if (m->C < 2 || m->C > ISMPC_MAX_N || m->P < m->C || m->F < 1 || m->F > ISMPC_MAX_FSTEPS || !(m->dt > 0) ||
+        !(m->q_zdot > 0) || !(m->q_foot > 0) || !(m->g_eta > 0))
+        return ISMPC_ERR_MODEL;
+    h->am = *m;
+    h->forma_ready = true;
+    return ISMPC_OK;
+}
+
+static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc_forma_inst_t* inst,
+                        const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
+                        const ismpc_push_t* push, ismpc_forma_out_t* out, double* primal_opt, int8_t* active_opt,
+                        double* traj_opt, int32_t* status_opt, int mem, void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!h->forma_ready) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || !inst || !fs_timing || !fs_plan || timing_len <= 0 || plan_rows <= 0)
+        return ISMPC_ERR_ARG;
+    if (!rollout && !out) return ISMPC_ERR_ARG;
+    if (n == 0 || (rollout && n_ticks <= 0)) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nV = 2 * (h->am.C + h->am.F);
+    FormAArgs a;
+    a.n = n; a.model = h->am; a.timing_len = timing_len; a.plan_rows = plan_rows; a.sm_count = h->sm_count;
+    a.warps_per_cta = 2; a.L_in_smem = 1; a.Lwork = nullptr;
+    {
+        const size_t lw = forma_Lwork_doubles(h->am, n);
+        if (lw) {
+            if (h->a_Lwork.ensure(lw * sizeof(double))) return ISMPC_ERR_ALLOC;
+            a.Lwork = (double*)h->a_Lwork.p;
+        }
+    }
+    if (mem == ISMPC_MEM_DEVICE) {
+        a.inst = inst; a.fs_timing = fs_timing; a.fs_plan = fs_plan; a.out = out; a.primal = primal_opt;
+        a.active = (signed char*)active_opt;
+        int rc = rollout ? forma_rollout_launch(a, inst, fs_plan, push, n_ticks, traj_opt, status_opt, st)
+                         : forma_tick_launch(a, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t mb = (size_t)h->max_batch;
+    if (h->s_ainst.ensure(mb * sizeof(ismpc_forma_inst_t)) || h->s_aout.ensure(mb * sizeof(ismpc_forma_out_t)) ||
+        h->s_timing.ensure((size_t)timing_len * sizeof(int32_t)) || h->s_plan.ensure((size_t)plan_rows * 2 * sizeof(double)))
+        return ISMPC_ERR_ALLOC;
+    if (primal_opt && h->s_primal.ensure(mb * nV * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (active_opt && h->s_active.ensure(mb * nV)) return ISMPC_ERR_ALLOC;
+    if (push && h->s_push.ensure(mb * sizeof(ismpc_push_t))) return ISMPC_ERR_ALLOC;
+    if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (status_opt && h->s_status.ensure(mb * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->s_ainst.p, inst, n * sizeof(ismpc_forma_inst_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_timing.p, fs_timing, (size_t)timing_len * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_plan.p, fs_plan, (size_t)plan_rows * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (push) CK(cudaMemcpyAsync(h->s_push.p, push, n * sizeof(ismpc_push_t), cudaMemcpyHostToDevice, st));
+    a.inst = (const ismpc_forma_inst_t*)h->s_ainst.p; a.fs_timing = (const int32_t*)h->s_timing.p;
+    a.fs_plan = (const double*)h->s_plan.p; a.out = (ismpc_forma_out_t*)h->s_aout.p;
+    a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
+    a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
+    int rc;
+    if (rollout)
+        rc = forma_rollout_launch(a, (ismpc_forma_inst_t*)h->s_ainst.p, (double*)h->s_plan.p,
+                                  push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
+                                  traj_opt ? (double*)h->s_traj.p : nullptr,
+                                  status_opt ? (int32_t*)h->s_status.p : nullptr, st);
+    else
+        rc = forma_tick_launch(a, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
+    if (rollout) {
+        CK(cudaMemcpyAsync(inst, h->s_ainst.p, n * sizeof(ismpc_forma_inst_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(fs_plan, h->s_plan.p, (size_t)plan_rows * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (traj_opt) CK(cudaMemcpyAsync(traj_opt, h->s_traj.p, (size_t)n * n_ticks * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (status_opt) CK(cudaMemcpyAsync(status_opt, h->s_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    } else {
+        CK(cudaMemcpyAsync(out, h->s_aout.p, n * sizeof(ismpc_forma_out_t), cudaMemcpyDeviceToHost, st));
+        if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * nV, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_forma_solve_batch(ismpc_handle* h, int n, const ismpc_forma_inst_t* inst, const int32_t* fs_timing,
+                                       int timing_len, const double* fs_plan, int plan_rows, ismpc_forma_out_t* out,
+                                       double* primal_opt, int8_t* active_opt, int mem, void* stream)
+{
+    return forma_common(h, n, 1, false, const_cast<ismpc_forma_inst_t*>(inst), fs_timing, timing_len,
+                        const_cast<double*>(fs_plan), plan_rows, nullptr, out, primal_opt, active_opt, nullptr,
+                        nullptr, mem, stream);
+}
+
+extern "C" int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                                   const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
+                                   const ismpc_push_t* push, double* traj_opt, int32_t* status_opt, int mem,
+                                   void* stream)
+{
+    return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
+                        nullptr, traj_opt, status_opt, mem, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generic dense QP (solveQP seam)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, const double* H, const double* g,
+                                    const double* A, const double* lbA, const double* ubA, double* x, double* y_opt,
+                                    int8_t* ws_opt, int32_t* status, int32_t* iters_opt, int mem, void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (n < 0 || n > h->max_batch || nV < 1 || nV > ISMPC_MAX_N || nC < 0 || nC > 2 * ISMPC_MAX_N + 8 || !H || !g ||
+        (nC > 0 && (!A || !lbA || !ubA)) || !x || !status)
+        return ISMPC_ERR_ARG;
+    if (n == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->q_work.ensure(qp_dense_work_doubles(n, nV, nC) * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = qp_dense_launch(n, nV, nC, H, g, A, lbA, ubA, x, y_opt, (signed char*)ws_opt, status, iters_opt,
+                                 (double*)h->q_work.p, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "qp_dense_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t szH = (size_t)n * nV * nV, szg = (size_t)n * nV, szA = (size_t)n * nC * nV, szb = (size_t)n * nC;
+    const size_t in_d = szH + szg + szA + 2 * szb;
+    const size_t out_b = (szg + szb) * sizeof(double) + szb + 2 * (size_t)n * sizeof(int32_t) + 64;
+    if (h->q_in.ensure(in_d * sizeof(double)) || h->q_out.ensure(out_b)) return ISMPC_ERR_ALLOC;
+    double* dH = (double*)h->q_in.p; double* dg = dH + szH; double* dA = dg + szg; double* dlb = dA + szA; double* dub = dlb + szb;
+    double* dx = (double*)h->q_out.p; double* dy = dx + szg;
+    int32_t* dst = (int32_t*)(dy + szb); int32_t* dit = dst + n;
+    signed char* dws = (signed char*)(dit + n);
+    CK(cudaMemcpyAsync(dH, H, szH * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg, g, szg * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nC > 0) {
+        CK(cudaMemcpyAsync(dA, A, szA * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dlb, lbA, szb * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dub, ubA, szb * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    int rc = qp_dense_launch(n, nV, nC, dH, dg, dA, dlb, dub, dx, dy, dws, dst, dit, (double*)h->q_work.p, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "qp_dense_launch");
+    CK(cudaMemcpyAsync(x, dx, szg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (y_opt && nC > 0) CK(cudaMemcpyAsync(y_opt, dy, szb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ws_opt && nC > 0) CK(cudaMemcpyAsync(ws_opt, dws, szb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, dst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (iters_opt) CK(cudaMemcpyAsync(iters_opt, dit, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}

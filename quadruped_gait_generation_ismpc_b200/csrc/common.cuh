@@ -1,0 +1,129 @@
+// common.cuh -- warp/CTA primitives shared by the ISMPC kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ISMPC_FULL_MASK 0xffffffffu
+
+namespace ismpc {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ISMPC_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(ISMPC_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(ISMPC_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ISMPC_FULL_MASK, v, o);
+    return v;
+}
+// argmin over the warp: returns the (value,index) with the smallest value; ties -> smallest index.
+__device__ __forceinline__ void warp_argmin(double& v, int& idx)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(ISMPC_FULL_MASK, v, o);
+        int oi = __shfl_xor_sync(ISMPC_FULL_MASK, idx, o);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+// inclusive prefix sum across lanes
+__device__ __forceinline__ double warp_incl_scan(double v)
+{
+    const int l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(ISMPC_FULL_MASK, v, o);
+        if (l >= o) v += t;
+    }
+    return v;
+}
+// inclusive suffix sum across lanes (lane l gets sum over lanes >= l)
+__device__ __forceinline__ double warp_incl_suffix_scan(double v)
+{
+    const int l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_down_sync(ISMPC_FULL_MASK, v, o);
+        if (l + o < 32) v += t;
+    }
+    return v;
+}
+
+// Contiguous chunk [lo,hi) of [0,n) owned by `lane` when n elements are split over 32 lanes.
+__device__ __forceinline__ void lane_chunk(int n, int lane, int& lo, int& hi)
+{
+    int per = (n + 31) >> 5;
+    lo = lane * per; if (lo > n) lo = n;
+    hi = lo + per;   if (hi > n) hi = n;
+}
+
+// In-place inclusive prefix sum of a shared-memory vector by one warp (chunked: serial in-lane + shuffle scan).
+__device__ __forceinline__ void warp_prefix_sum_smem(double* v, int n)
+{
+    int lo, hi; lane_chunk(n, lane_id(), lo, hi);
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) { s += v[i]; v[i] = s; }
+    double incl = warp_incl_scan(s);
+    double off = incl - s;
+    for (int i = lo; i < hi; ++i) v[i] += off;
+    __syncwarp();
+}
+// In-place inclusive suffix sum (v[i] = sum_{k>=i} v[k]).
+__device__ __forceinline__ void warp_suffix_sum_smem(double* v, int n)
+{
+    int lo, hi; lane_chunk(n, lane_id(), lo, hi);
+    double s = 0.0;
+    for (int i = hi - 1; i >= lo; --i) { s += v[i]; v[i] = s; }
+    double incl = warp_incl_suffix_scan(s);
+    double off = incl - s;
+    for (int i = lo; i < hi; ++i) v[i] += off;
+    __syncwarp();
+}
+
+// ---- 1-D TMA (cp.async.bulk) global -> shared with mbarrier completion -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+}  // namespace ismpc

@@ -1,0 +1,456 @@
+// formc.cuh -- formulation C (what MPCSolver::solve builds): device code for the fused tick.
+//
+// Reference map (AMR_code_DART/...):
+//   MPCSolver.cpp:167-180   midpoint sequence            -> midpoint_value()   (computed on the fly, per window)
+//   MPCSolver.cpp:124-160   vertical prediction matrices -> closed forms + the model tables built by
+//                                                           formc_setup kernels (H_z^-1, S H^-1, S H^-1 S')
+//   MPCSolver.cpp:220-278   stage 1 vertical QP          -> vertical_qp()      (dual active set on tables)
+//   MPCSolver.cpp:296-309   stage 2 lambda sequence      -> lambda_and_lip()
+//   MPCSolver.cpp:325-389   stage 3 horizontal QP build  -> stability_row() (O(N) suffix-product scan instead
+//                                                           of the reference's O(N^2) loop), tails
+//   utils.cpp:385-511 / utils.cpp:89-139  solve          -> knapsack_qp()      (exact active-set Newton on the
+//                                                           scalar multiplier: H = I, A = [a'; I])
+//   MPCSolver.cpp:402-422   integrate                    -> formc_tick() epilogue
+#pragma once
+#include "common.cuh"
+#include "das.cuh"
+#include "../../include/ismpc_b200.h"
+
+namespace ismpc {
+
+constexpr int FORMC_THREADS = 128;
+constexpr int FORMC_QMAX = 64;        // max working-set size of the vertical QP (equalities + active rows)
+constexpr int FORMC_PLAN_STAGE = 40;  // plan rows staged in shared memory by one bulk copy
+
+struct FormCTables {      // device pointers, N x N row-major each (built once per model)
+    const double* Hinv;   // H_z^-1
+    const double* G;      // S_bar_z * H_z^-1
+    const double* M;      // S_bar_z * H_z^-1 * S_bar_z'
+};
+
+struct FormCShared {      // per-CTA shared memory carve-up (all pointers into dynamic smem)
+    double *midx, *midy, *midz;            // [2N], [2N], [N]
+    double *Fz, *f, *rv, *zdir, *scr;      // [N] each
+    double *lam, *chv, *shs, *ssh;         // [N] each: lambda, cosh, sinh/s, s*sinh
+    double *avec, *dl;                     // [N] stability row, exp(-dt*eta*i)
+    double *plan;                          // [FORMC_PLAN_STAGE*4]
+    double *red;                           // [16] small scratch / cross-warp results
+    DasWork das;
+    uint64_t* bar;
+};
+
+__host__ __device__ inline size_t formc_smem_bytes(int N)
+{
+    size_t d = (size_t)16 * N + FORMC_PLAN_STAGE * 4 + 16 + (FORMC_QMAX * (FORMC_QMAX + 1)) / 2 + 3 * FORMC_QMAX;
+    size_t b = d * sizeof(double) + FORMC_QMAX * sizeof(int) + FORMC_QMAX + (size_t)N + 16 /*bar*/;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline void formc_carve(unsigned char* base, int N, FormCShared& s)
+{
+    double* d = reinterpret_cast<double*>(base);
+    s.bar = reinterpret_cast<uint64_t*>(d); d += 2;
+    s.plan = d; d += FORMC_PLAN_STAGE * 4;
+    s.midx = d; d += 2 * N; s.midy = d; d += 2 * N; s.midz = d; d += N;
+    s.Fz = d; d += N; s.f = d; d += N; s.rv = d; d += N; s.zdir = d; d += N; s.scr = d; d += N;
+    s.lam = d; d += N; s.chv = d; d += N; s.shs = d; d += N; s.ssh = d; d += N;
+    s.avec = d; d += N; s.dl = d; d += N;
+    s.red = d; d += 16;
+    s.das.L = d; d += (FORMC_QMAX * (FORMC_QMAX + 1)) / 2;
+    s.das.mu = d; d += FORMC_QMAX; s.das.r = d; d += FORMC_QMAX; s.das.y = d; d += FORMC_QMAX;
+    s.das.wid = reinterpret_cast<int*>(d);
+    s.das.wsg = reinterpret_cast<signed char*>(s.das.wid + FORMC_QMAX);
+    s.das.state = s.das.wsg + FORMC_QMAX;
+    s.das.qmax = FORMC_QMAX;
+}
+
+// MPCSolver.cpp:167-180: value of ftsp_midpoint(t, c).  rows: pointer to plan rows (x,y,z,t), first = index
+// of rows[0] in the instance's plan.
+__device__ __forceinline__ double midpoint_value(const double* rows, int first, int n_steps, int S, int F,
+                                                 int t, int c)
+{
+    const int per = S + F;
+    const int i = t / per, r = t - i * per;
+    if (i >= n_steps - 1) return 0.0;                 // last step's rows stay 0 (loop runs to rows()-1)
+    const double a = rows[(i - first) * 4 + c];
+    if (r < S) return a * 1.0;
+    const double b = rows[(i + 1 - first) * 4 + c];
+    return a * 1.0 + (b - a) * ((double)(r - S) / (double)F);
+}
+
+// ---- vertical QP policy for the dual active-set engine -------------------------------------------
+struct VertProb {
+    int N;
+    FormCTables T;
+    double c1;       // dt*dt/mass  (S_bar_z[k][j] = (k-j)*c1, MPCSolver.cpp:149)
+    double fzmax;
+    double* scr;     // [N] shared scratch
+    __device__ int m() const { return N; }
+    __device__ int nvar() const { return N; }
+    __device__ double lo(int) const { return 0.0; }
+    __device__ double hi(int) const { return fzmax; }
+    // rv_k = (S_bar_z x)_k = c1 * sum_{j<k} (k-j) x_j  -> two prefix sums
+    __device__ void eval(const double* x, double* rv) const
+    {
+        const int lane = lane_id();
+        for (int i = lane; i < N; i += 32) scr[i] = x[i];
+        __syncwarp();
+        warp_prefix_sum_smem(scr, N);
+        warp_prefix_sum_smem(scr, N);
+        for (int i = lane; i < N; i += 32) rv[i] = (i == 0) ? 0.0 : c1 * scr[i - 1];
+        __syncwarp();
+    }
+    __device__ double schur(int a, int b) const
+    {
+        if (a < N) return (b < N) ? T.M[(size_t)a * N + b] : T.G[(size_t)a * N + (b - N)];
+        return (b < N) ? T.G[(size_t)b * N + (a - N)] : T.Hinv[(size_t)(a - N) * N + (b - N)];
+    }
+    __device__ const double* col(int id) const { return id < N ? T.G + (size_t)id * N : T.Hinv + (size_t)(id - N) * N; }
+    __device__ void step_dir(int idp, int sgp, const int* wid, const signed char* wsg, const double* r, int q,
+                             double* z) const
+    {
+        const int lane = lane_id();
+        const double* cp = col(idp);
+        for (int i = lane; i < N; i += 32) {
+            double acc = (double)sgp * cp[i];
+            for (int k = 0; k < q; ++k) acc -= (double)wsg[k] * r[k] * col(wid[k])[i];
+            z[i] = acc;
+        }
+        __syncwarp();
+    }
+};
+
+// Exact solve of   min 1/2|u|^2 - mid'u   s.t.  a'u = b,  mid-rho <= u <= mid+rho   by one warp.
+// u_i = mid_i + clip(nu*a_i, -rho, rho); Newton on the piecewise-linear monotone residual in nu, which is
+// the scalar-Schur-complement active-set iteration for this structure (H = I, A = [a'; I]): every pass adds
+// all newly saturated rows at once; |nu| grows monotonically, so it terminates in <= N passes.
+// Returns status (0 ok, 1 infeasible), *nu_out, *iters.
+__device__ inline int knapsack_qp(int N, const double* a, const double* mid, double rho, double b,
+                                  double* nu_out, int* iters_out, double* resid_out)
+{
+    const int lane = lane_id();
+    double am = 0.0, aa = 0.0;
+    for (int i = lane; i < N; i += 32) { am += a[i] * mid[i]; aa += a[i] * a[i]; }
+    am = warp_sum(am); aa = warp_sum(aa);
+    const double r = b - am;
+    const double sg = (r >= 0.0) ? 1.0 : -1.0;
+    const double rabs = fabs(r);
+    int status = 0, iters = 0;
+    double t = 0.0;           // |nu|
+    int nsat_prev = -1;
+    if (aa > 0.0) {
+        t = rabs / aa;
+        for (;;) {
+            double s1 = 0.0, s2 = 0.0; int ns = 0;
+            for (int i = lane; i < N; i += 32) {
+                double ai = fabs(a[i]);
+                if (t * ai > rho) { s1 += ai; ++ns; } else s2 += ai * ai;
+            }
+            s1 = warp_sum(s1); s2 = warp_sum(s2); ns = warp_sum_int(ns);
+            if (ns == nsat_prev) break;
+            nsat_prev = ns; ++iters;
+            double rem = rabs - rho * s1;
+            if (!(s2 > 0.0)) { if (rem > 1e-12 * fmax(1.0, rabs)) status = 1; break; }
+            double tn = rem / s2;
+            if (!(tn >= t)) tn = t;   // monotone guard against round-off
+            t = tn;
+            if (iters > N + 2) break;
+        }
+    } else if (rabs > 1e-12) status = 1;
+    const double nu = sg * t;
+    // equality residual of the final point (self-check)
+    double au = 0.0;
+    for (int i = lane; i < N; i += 32) au += a[i] * (mid[i] + fmin(fmax(nu * a[i], -rho), rho));
+    au = warp_sum(au);
+    *nu_out = nu; *iters_out = iters > 0 ? iters - 1 : 0; *resid_out = fabs(au - b);
+    return status;
+}
+
+struct FormCArgs {
+    int n;
+    ismpc_formc_model_t model;
+    FormCTables T;
+    const ismpc_state_t* state;
+    const ismpc_walk_t* walk;
+    const ismpc_formc_inst_t* inst;
+    const double* plan;
+    int plan_rows;
+    ismpc_formc_out_t* out;
+    double* primal;      // nullable, n x 3N
+    signed char* active; // nullable, n x 3N
+};
+
+// One tick for one instance by one CTA (FORMC_THREADS threads).  `st`/`wk` are the instance's current
+// state/walk (registers, uniform across the CTA); results are written to *o (thread 0) and, if non-null,
+// prim (3N) / act (3N).
+__device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model_t& mdl, const FormCTables& T,
+                                  const ismpc_state_t& st, const ismpc_walk_t& wk, const ismpc_formc_inst_t& in,
+                                  const double* __restrict__ plan_all, ismpc_formc_out_t* o,
+                                  double* prim, signed char* act, uint32_t& bar_parity)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = mdl.N;
+    const double dt = mdl.dt, mass = mdl.mass, g = mdl.g;
+    const double h = in.com_height;
+    const double eta = sqrt(g / h);                       // parameters.cpp:41
+    const int S = in.S, F = in.F_ds, per = S + F;
+    const int k0 = (int)(wk.sim_time / (dt / mdl.dtc));   // MPCSolver.cpp:259,329
+    int status = 0;
+
+    if (k0 < 0 || per <= 0 || (long long)k0 + 2 * N > (long long)in.n_steps * per) {
+        if (tid == 0) {
+            o->next = st; o->zmp_in[0] = o->zmp_in[1] = 0.0; o->fz0 = 0.0; o->lambda0 = 0.0; o->kkt_res = 0.0;
+            o->status = ISMPC_ST_WINDOW; o->iters[0] = o->iters[1] = o->iters[2] = 0;
+        }
+        return;
+    }
+
+    // ---- stage the plan rows the window touches: one 1-D bulk (TMA) copy into shared memory ----------
+    const int first = k0 / per;
+    int last = (k0 + 2 * N - 1) / per + 1;                // inclusive: row i+1 is read for the ramp
+    if (last > in.n_steps - 1) last = in.n_steps - 1;
+    const int nrows = last - first + 1;
+    const double* rows_g = plan_all + ((size_t)in.plan_first_row + first) * 4;
+    const double* rows;
+    if (nrows <= FORMC_PLAN_STAGE) {
+        if (tid == 0) {
+            mbar_expect_tx(sm.bar, (uint32_t)(nrows * 32));
+            tma_load_1d(sm.plan, rows_g, (uint32_t)(nrows * 32), sm.bar);
+        }
+        mbar_wait(sm.bar, bar_parity);
+        bar_parity ^= 1u;
+        rows = sm.plan;
+    } else {
+        rows = rows_g;                                     // very short steps: read through L1/L2 instead
+    }
+    for (int k = tid; k < 2 * N; k += FORMC_THREADS) {
+        sm.midx[k] = midpoint_value(rows, first, in.n_steps, S, F, k0 + k, 0);
+        sm.midy[k] = midpoint_value(rows, first, in.n_steps, S, F, k0 + k, 1);
+        if (k < N) sm.midz[k] = midpoint_value(rows, first, in.n_steps, S, F, k0 + k, 2);
+    }
+    __syncthreads();
+
+    // ================= STAGE 1: vertical QP (MPCSolver.cpp:220-269) =================
+    const double z0 = st.com_pos[2], zd0 = st.com_vel[2];
+    const double c1 = dt * dt / mass;                      // S_bar_z[k][j]   = (k-j)*dt * dt/m
+    const double c1v = dt / mass;                          // S_bar_z_v[k][j] = dt/m          (j<k)
+    // v_k = T_z[k] z + T_g[k] - h - mid_z[k];  w_k = T_zv[k] z + T_gv[k]           (:259)
+    //   T_z[k] = [1, (k+1)dt], T_g[k] = -g dt^2 k(k+1)/2, T_zv[k] = [0,1], T_gv[k] = -g dt k
+    for (int k = tid; k < N; k += FORMC_THREADS) {
+        double tg = -g * (dt * dt) * (0.5 * (double)k * (double)(k + 1));
+        sm.rv[k] = 1.0 * z0 + ((double)(k + 1) * dt) * zd0 + tg - h - sm.midz[k];   // v
+        sm.scr[k] = zd0 - g * dt * (double)k;                                       // w
+    }
+    __syncthreads();
+    // F_j = q_p*c1 * sum_{k>j}(k-j) v_k + q_v*c1v * sum_{k>j} w_k - q_u*m*g
+    if (warp == 0) {
+        warp_suffix_sum_smem(sm.rv, N);    // SI_l = sum_{k>=l} v_k
+        warp_suffix_sum_smem(sm.rv, N);    // sum_{l>=j} SI_l  -> P2_j = that at j+1
+    } else if (warp == 1) {
+        warp_suffix_sum_smem(sm.scr, N);   // sum_{k>=j} w_k
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += FORMC_THREADS) {
+        double p2 = (j + 1 < N) ? sm.rv[j + 1] : 0.0;
+        double pw = (j + 1 < N) ? sm.scr[j + 1] : 0.0;
+        sm.Fz[j] = mdl.q_p * c1 * p2 + mdl.q_v * c1v * pw - mdl.q_u * mass * g;
+    }
+    __syncthreads();
+    // unconstrained minimiser x0 = -H^-1 F  (table mat-vec; Hinv symmetric -> coalesced row reads).
+    // The 4 warps split the j range; each lane owns outputs i = blk*128 + lane + 32e.  Per-warp partial
+    // vectors go to shared memory (zdir/lam/chv/shs are free at this point) and are summed afterwards.
+    {
+        double* part = (warp == 0) ? sm.zdir : (warp == 1) ? sm.lam : (warp == 2) ? sm.chv : sm.shs;
+        const int jlo = (N * warp) / 4, jhi = (N * (warp + 1)) / 4;
+        for (int blk = 0; blk * 128 < N; ++blk) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const int ib = blk * 128 + lane;
+            for (int j = jlo; j < jhi; ++j) {
+                const double fj = sm.Fz[j];
+                const double* hr = T.Hinv + (size_t)j * N + ib;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (ib + 32 * e < N) acc[e] += __ldg(hr + 32 * e) * fj;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (ib + 32 * e < N) part[ib + 32 * e] = acc[e];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += FORMC_THREADS) sm.f[i] = -(sm.zdir[i] + sm.lam[i] + sm.chv[i] + sm.shs[i]);
+    __syncthreads();
+
+    // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
+    int it_z = 0;
+    if (warp == 0) {
+        DasWork w = sm.das;
+        w.q = 0; w.neq = 0;
+        for (int i = lane; i < N; i += 32) w.state[i] = 0;
+        __syncwarp();
+        VertProb vp{N, T, c1, mdl.fz_max, sm.scr};
+        int zfail = 0;
+        if (wk.footstep_counter > 1) {
+            int ne, c_lo;
+            if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }                 // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
+            else { ne = S + F - wk.mpc_iter; c_lo = 0; }                             // Aeq_z(i,i), i < S+F-mpcIter
+            for (int e = 0; e < ne; ++e) {
+                int c = c_lo + e;
+                if (c < 0 || c >= N) continue;
+                int rc = das_add_equality(vp, w, sm.f, sm.zdir, N + c, sm.f[c], 0.0);
+                if (rc < 0) zfail = 1;
+                __syncwarp();
+            }
+            w.neq = w.q;
+        }
+        int rc = das_solve(vp, w, sm.f, sm.rv, sm.zdir, 4 * N + 16, &it_z);
+        if (rc != 0 || zfail) status |= ISMPC_ST_Z_FAIL;
+        // active set of the S_bar_z rows
+        if (act) for (int i = lane; i < N; i += 32) act[i] = w.state[i];
+        // primal residual for the self-check: rows within bounds (rv holds S x of the last eval)
+        double viol = 0.0;
+        for (int i = lane; i < N; i += 32) viol = fmax(viol, fmax(-sm.rv[i], sm.rv[i] - mdl.fz_max));
+        viol = warp_max(viol);
+        if (lane == 0) { sm.red[0] = viol; sm.red[1] = (double)status; sm.red[2] = (double)it_z; }
+    }
+    __syncthreads();
+    double kkt = fmax(0.0, sm.red[0]);
+    status = (int)sm.red[1];
+    it_z = (int)sm.red[2];
+    if (prim) for (int i = tid; i < N; i += FORMC_THREADS) prim[i] = sm.f[i];
+
+    // ================= STAGE 2: lambda sequence (MPCSolver.cpp:296-309) =================
+    // z_pos = S_bar_z f + T_z z + T_g  (two prefix sums of f), lambda_j = (g + (f_j/m - g)) / z_pos_j
+    if (warp == 0) {
+        for (int i = lane; i < N; i += 32) sm.scr[i] = sm.f[i];
+        __syncwarp();
+        warp_prefix_sum_smem(sm.scr, N);
+        warp_prefix_sum_smem(sm.scr, N);
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += FORMC_THREADS) {
+        double sf = (j == 0) ? 0.0 : c1 * sm.scr[j - 1];
+        double tg = -g * (dt * dt) * (0.5 * (double)j * (double)(j + 1));
+        double zp = sf + 1.0 * z0 + ((double)(j + 1) * dt) * zd0 + tg;
+        double zacc = (1.0 / mass) * sm.f[j] - g;
+        double lam = (g + zacc) / zp;
+        sm.lam[j] = lam;
+        if (lam < 2.0) { sm.chv[j] = 1.0; sm.shs[j] = dt; sm.ssh[j] = 0.0; }       // integrator (:353-355)
+        else {
+            double s = sqrt(lam);
+            double ch = cosh(s * dt), sh = sinh(s * dt);
+            sm.chv[j] = ch; sm.shs[j] = sh / s; sm.ssh[j] = s * sh;                 // (:357-360)
+        }
+        sm.dl[j] = exp(-dt * eta * (double)j);                                      // deltas (:183-184)
+    }
+    __syncthreads();
+    const double fz0 = sm.f[0];
+    const double lam0 = sm.lam[0];
+    double nz0 = 1.0 * z0 + dt * zd0, nz1 = zd0 + (dt / mass) * fz0 - dt * g;      // (:274)
+    if (isnan(nz0)) { nz0 = h; status |= ISMPC_ST_NAN_GUARD; }                      // (:277-278)
+    if (isnan(nz1)) { nz1 = 0.0; status |= ISMPC_ST_NAN_GUARD; }
+
+    // ================= STAGE 3: horizontal QPs (MPCSolver.cpp:322-398) =================
+    double ux0 = 0.0, uy0 = 0.0;
+    int it_x = 0, it_y = 0;
+    if (lam0 > 2.0) {
+        // stability row a_i = C_sc * A_{N-1}...A_{i+1} B_i with C_sc = [1, 1/eta] (:351-379): backward
+        // row-vector recurrence c_{i-1} = c_i A_i, a_i = c_i B_i, evaluated as a chunked warp scan.
+        if (warp == 0) {
+            int lo, hi; lane_chunk(N, lane, lo, hi);
+            // local product P = A_{hi-1} ... A_{lo}   (row-vector convention: c_{lo-1} = c_{hi-1} * P)
+            double p00 = 1, p01 = 0, p10 = 0, p11 = 1;
+            for (int i = hi - 1; i >= lo; --i) {
+                double a00 = sm.chv[i], a01 = sm.shs[i], a10 = sm.ssh[i], a11 = sm.chv[i];
+                double n00 = p00 * a00 + p01 * a10, n01 = p00 * a01 + p01 * a11;
+                double n10 = p10 * a00 + p11 * a10, n11 = p10 * a01 + p11 * a11;
+                p00 = n00; p01 = n01; p10 = n10; p11 = n11;
+            }
+            // exclusive suffix scan over lanes: T_L = P_31 * P_30 * ... * P_{L+1}
+            // inclusive first: I_L = P_31 ... P_L  via  I_L = I_{L+o} * (own partial)   (Hillis-Steele, down-shuffles)
+            double i00 = p00, i01 = p01, i10 = p10, i11 = p11;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double q00 = __shfl_down_sync(ISMPC_FULL_MASK, i00, o), q01 = __shfl_down_sync(ISMPC_FULL_MASK, i01, o);
+                double q10 = __shfl_down_sync(ISMPC_FULL_MASK, i10, o), q11 = __shfl_down_sync(ISMPC_FULL_MASK, i11, o);
+                if (lane + o < 32) {
+                    double n00 = q00 * i00 + q01 * i10, n01 = q00 * i01 + q01 * i11;
+                    double n10 = q10 * i00 + q11 * i10, n11 = q10 * i01 + q11 * i11;
+                    i00 = n00; i01 = n01; i10 = n10; i11 = n11;
+                }
+            }
+            // T_L = I_{L+1}; identity for lane 31
+            double t00 = __shfl_down_sync(ISMPC_FULL_MASK, i00, 1), t01 = __shfl_down_sync(ISMPC_FULL_MASK, i01, 1);
+            double t10 = __shfl_down_sync(ISMPC_FULL_MASK, i10, 1), t11 = __shfl_down_sync(ISMPC_FULL_MASK, i11, 1);
+            if (lane == 31) { t00 = 1; t01 = 0; t10 = 0; t11 = 1; }
+            const double cs0 = 1.0, cs1 = 1.0 / eta;                                 // C_sc (:375-377), nominal eta
+            double c0 = cs0 * t00 + cs1 * t10, c1r = cs0 * t01 + cs1 * t11;          // c_{hi-1}
+            for (int i = hi - 1; i >= lo; --i) {
+                // B_i = [1-ch; -s*sh]; integrator branch has B = 0 (ssh = 0 and ch = 1)
+                sm.avec[i] = c0 * (1.0 - sm.chv[i]) + c1r * (-sm.ssh[i]);
+                double n0 = c0 * sm.chv[i] + c1r * sm.ssh[i], n1 = c0 * sm.shs[i] + c1r * sm.chv[i];
+                c0 = n0; c1r = n1;
+            }
+            if (lane == 0) { sm.red[4] = c0; sm.red[5] = c1r; }                      // C_sc * phi_state
+        } else if (warp == 1 || warp == 2) {
+            const double* mq = (warp == 1) ? sm.midx : sm.midy;
+            double t = 0.0;
+            for (int i = lane; i < N; i += 32) t += sm.dl[i] * mq[N + i];            // anticipative tail (:381-383)
+            t = warp_sum(t);
+            if (lane == 0) sm.red[6 + (warp - 1)] = t;
+        }
+        __syncthreads();
+        if (warp < 2) {
+            const int ax = warp;
+            const double* mq = ax == 0 ? sm.midx : sm.midy;
+            const double c = st.com_pos[ax], cd = st.com_vel[ax];
+            const double b = -(sm.red[4] * c + sm.red[5] * cd) + eta * dt * sm.red[6 + ax];
+            const double rho = (wk.footstep_counter > 1) ? in.box_w / 2 : in.box_w_init / 2;   // (:328-338)
+            double nu, resid; int it;
+            int rc = knapsack_qp(N, sm.avec, mq, rho, b, &nu, &it, &resid);
+            for (int i = lane; i < N; i += 32) {
+                double d = nu * sm.avec[i];
+                double u = mq[i] + fmin(fmax(d, -rho), rho);
+                if (prim) prim[(1 + ax) * N + i] = u;
+                if (act) act[(1 + ax) * N + i] = (signed char)((d > rho) ? 1 : ((d < -rho) ? -1 : 0));
+            }
+            if (lane == 0) {
+                double d0 = nu * sm.avec[0];
+                sm.red[8 + ax * 3 + 0] = mq[0] + fmin(fmax(d0, -rho), rho);
+                sm.red[8 + ax * 3 + 1] = (double)(rc ? (ax == 0 ? ISMPC_ST_X_FAIL : ISMPC_ST_Y_FAIL) : 0) + 1024.0 * it;
+                sm.red[8 + ax * 3 + 2] = resid;
+            }
+        }
+        __syncthreads();
+        ux0 = sm.red[8]; uy0 = sm.red[11];
+        int e0 = (int)sm.red[9], e1 = (int)sm.red[12];
+        status |= (e0 & 1023) | (e1 & 1023);
+        it_x = e0 >> 10; it_y = e1 >> 10;
+        kkt = fmax(kkt, fmax(sm.red[10], sm.red[13]));
+    } else {
+        status |= ISMPC_ST_XY_SKIPPED;
+        if (prim) for (int i = tid; i < 2 * N; i += FORMC_THREADS) prim[N + i] = 0.0;
+        if (act) for (int i = tid; i < 2 * N; i += FORMC_THREADS) act[N + i] = 0;
+    }
+
+    // ================= integrate (MPCSolver.cpp:402-422) =================
+    if (tid == 0) {
+        double a00, a01, a10, a11, b0, b1;
+        if (lam0 < 2.0) { a00 = 1.0; a01 = dt; a10 = 0.0; a11 = 1.0; b0 = 0.0; b1 = 0.0; }
+        else {
+            double s = sqrt(lam0);
+            double ch = cosh(s * dt), sh = sinh(s * dt);
+            a00 = ch; a01 = sh / s; a10 = s * sh; a11 = ch; b0 = 1.0 - ch; b1 = -s * sh;
+        }
+        ismpc_formc_out_t r;
+        r.next = st;
+        r.next.com_pos[0] = a00 * st.com_pos[0] + a01 * st.com_vel[0] + b0 * ux0;
+        r.next.com_vel[0] = a10 * st.com_pos[0] + a11 * st.com_vel[0] + b1 * ux0;
+        r.next.com_pos[1] = a00 * st.com_pos[1] + a01 * st.com_vel[1] + b0 * uy0;
+        r.next.com_vel[1] = a10 * st.com_pos[1] + a11 * st.com_vel[1] + b1 * uy0;
+        r.next.com_pos[2] = nz0; r.next.com_vel[2] = nz1;
+        r.zmp_in[0] = ux0; r.zmp_in[1] = uy0; r.fz0 = fz0; r.lambda0 = lam0; r.kkt_res = kkt;
+        r.status = status; r.iters[0] = it_z; r.iters[1] = it_x; r.iters[2] = it_y;
+        *o = r;
+    }
+}
+
+}  // namespace ismpc

@@ -1,0 +1,29 @@
+// launch.h -- host-side launch entry points of the kernel translation units (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/ismpc_b200.h"
+
+namespace ismpc {
+
+struct FormCArgs;
+struct FormCTables;
+struct FormAArgs;
+
+int formc_setup_launch(const ismpc_formc_model_t& m, double* work, double* Hinv, double* G, double* M,
+                       int* d_info, cudaStream_t st, long long* launches);
+int formc_tick_launch(const FormCArgs& a, int grid, cudaStream_t st);
+int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
+                         const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
+                         cudaStream_t st);
+
+size_t forma_Lwork_doubles(const ismpc_forma_model_t& m, int n);
+int forma_tick_launch(const FormAArgs& a, cudaStream_t st);
+int forma_rollout_launch(const FormAArgs& a, ismpc_forma_inst_t* inst_io, double* fs_plan_io,
+                         const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, cudaStream_t st);
+
+int qp_dense_launch(int n, int nV, int nC, const double* H, const double* g, const double* A, const double* lbA,
+                    const double* ubA, double* x, double* y, signed char* ws, int32_t* status, int32_t* iters,
+                    double* work, cudaStream_t st);
+size_t qp_dense_work_doubles(int n, int nV, int nC);
+
+}  // namespace ismpc

@@ -1,0 +1,28 @@
+"""Parity definition shared by the GPU tests.
+
+(i)  primal: max_i |x_gpu - x_ora| / max(1, |x_ora|_inf) <= 1e-6
+(ii) active set: equal on every row that is strongly determined, i.e. excluding rows where the oracle's
+     |multiplier| < 1e-9 and |slack| < 1e-9 do not both clear the threshold (weakly active / degenerate rows);
+     those rows are counted and reported.
+(iii) instances where the oracle's solver returned non-zero are excluded and counted.
+"""
+import numpy as np
+
+PRIMAL_TOL = 1e-6   # BASELINE.json north_star: "within 1e-6 relative on the primal"
+
+
+def primal_rel_err(x_gpu, x_ora):
+    x_gpu = np.asarray(x_gpu, dtype=np.float64); x_ora = np.asarray(x_ora, dtype=np.float64)
+    scale = np.maximum(1.0, np.abs(x_ora).max(axis=-1, keepdims=True))
+    return (np.abs(x_gpu - x_ora) / scale).max(axis=-1)
+
+
+def active_set_mismatch(as_gpu, as_ora, duals_ora, weak_tol=1e-9):
+    """Number of strongly-determined rows that differ per instance, and number of weak rows.
+    A row is weak when the oracle's multiplier is ~0 (it may sit in either working set)."""
+    as_gpu = np.asarray(as_gpu).astype(np.int32); as_ora = np.asarray(as_ora).astype(np.int32)
+    weak = np.abs(duals_ora) < weak_tol
+    diff = (as_gpu != as_ora) & ~weak
+    # a weak row may legitimately be reported active by one side only; but it must not be active on opposite sides
+    opp = (as_gpu * as_ora == -1)
+    return (diff | opp).sum(axis=-1), (weak & (as_gpu != as_ora)).sum(axis=-1)

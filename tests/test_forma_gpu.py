@@ -1,0 +1,135 @@
+"""GPU parity of the formulation-A tick (canonical ISMPC with footsteps) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from quadruped_gait_generation_ismpc_b200 import abi, synth
+from oracle import oracle as O
+from parity import PRIMAL_TOL, primal_rel_err, active_set_mismatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _advance(handle, inst, fs_timing, fs_plan, ticks):
+    """Roll instance i forward ticks[i] ticks on the GPU (grouped by tick count) to get mid-gait states."""
+    inst = inst.copy(); fs_plan = fs_plan.copy()
+    for t in np.unique(ticks):
+        if t == 0:
+            continue
+        sel = np.nonzero(ticks == t)[0]
+        r = handle.forma_rollout(inst[sel], fs_timing, fs_plan, int(t), want_traj=False)
+        assert (r["status"] == 0).all()
+        inst[sel] = r["inst"]
+        for i in sel:   # only these instances' plan rows changed
+            a = inst["plan_first_row"][i]; b = a + inst["n_fs"][i]
+            fs_plan[a:b] = r["fs_plan"][a:b]
+    return inst, fs_plan
+
+
+def _compare(handle, model, inst, fs_timing, fs_plan, nthreads=8):
+    g = handle.forma_solve_batch(inst, fs_timing, fs_plan)
+    o = O.forma_batch(model, inst, fs_timing, fs_plan, nthreads=nthreads)
+    ok = o["ret"] == 0
+    assert ok.mean() > 0.9
+    assert (g["out"]["status"][ok] == 0).all()
+    C, F = int(model["C"][0]), int(model["F"][0])
+    # parity is per axis block [zd(C) | xf(F)]
+    err = primal_rel_err(g["primal"][ok], o["primal"][ok])
+    assert err.max() <= PRIMAL_TOL, "primal rel err %.3e" % err.max()
+    assert np.abs(g["out"]["st"][ok] - o["out"]["st"][ok]).max() <= PRIMAL_TOL
+    assert np.abs(g["out"]["pred_fs"][ok][:, :2 * F] - o["out"]["pred_fs"][ok][:, :2 * F]).max() <= PRIMAL_TOL
+    mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
+    assert mism.sum() == 0, "active set differs on %d rows (%d weak ignored)" % (mism.sum(), weak.sum())
+    assert g["out"]["kkt_res"][ok].max() < 1e-8
+    return g, o
+
+
+def test_start_of_gait_trot(handle):
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    inst, ft, plan = synth.forma_batch(64, gait="trot")
+    _compare(handle, model, inst, ft, plan)
+
+
+def test_mid_gait_trot_config2(handle):
+    """Config 2 (formulation A): trot instances advanced to random gait phases, then one cold tick each."""
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    n = 96
+    inst, ft, plan = synth.forma_batch(n, gait="trot")
+    rng = np.random.default_rng(11)
+    ticks = rng.choice([0, 17, 49, 63, 98, 131, 207, 260], size=n)
+    inst, plan = _advance(handle, inst, ft, plan, ticks)
+    g, o = _compare(handle, model, inst, ft, plan)
+    assert (np.abs(o["active"]).sum(axis=1) > 10).any(), "vacuous: no instance with a sizeable active set"
+
+
+def test_mid_gait_walk_config3(handle):
+    """Config 3: walking gait, Qf = 1e9, varied CoM height / step duration / ds."""
+    model = abi.forma_model(q_foot=1e9)
+    handle.forma_set_model(model)
+    n = 96
+    inst, ft, plan = synth.forma_batch(n, gait="walk", vary=True, ds=30, N_gait=108)
+    rng = np.random.default_rng(12)
+    ticks = rng.choice([0, 25, 61, 117, 180, 240], size=n)
+    inst, plan = _advance(handle, inst, ft, plan, ticks)
+    _compare(handle, model, inst, ft, plan)
+
+
+def test_closed_loop_lockstep_with_push(handle):
+    """Config 5 in small: GPU rollout vs the oracle run tick-by-tick from the GPU's previous state."""
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    inst, ft, plan = synth.forma_batch(4, gait="trot", seed=3)
+    push = synth.push_batch(4, seed=4)
+    push["fs"] = 2
+    T = 130
+    r = handle.forma_rollout(inst, ft, plan, T, push=push)
+    assert (r["status"] == 0).all()
+    cur, pl = inst.copy(), plan.copy()
+    ct = np.zeros(4, dtype=int)
+    for t in range(T):
+        for i in range(4):
+            if cur["fs_counter"][i] == push["fs"][i] and push["ct0"][i] <= ct[i] < push["ct1"][i]:
+                cur["st"][i][1] += 0.01 * push["ax"][i]; cur["st"][i][4] += 0.01 * push["ay"][i]
+        o = O.forma_batch(model, cur, ft, pl)
+        assert (o["ret"] == 0).all()
+        x = np.stack([o["out"]["st"][:, k] for k in (0, 3, 1, 4, 2, 5)], axis=1)
+        assert np.abs(r["traj"][:, t] - x).max() <= 1e-6, "tick %d err %.3e" % (t, np.abs(r["traj"][:, t] - x).max())
+        # continue from the GPU's state so errors do not compound
+        for k, col in enumerate((0, 3, 1, 4, 2, 5)):
+            cur["st"][:, col] = r["traj"][:, t, k]
+        ct += 1
+        for i in range(4):
+            fc = cur["fs_counter"][i]
+            if cur["j"][i] + 1 >= ft[cur["timing_first"][i] + fc]:
+                fc += 1; cur["fs_counter"][i] = fc
+                pred = np.array([o["out"]["pred_fs"][i][0], o["out"]["pred_fs"][i][3]])
+                cur["cur_fs"][i] = pred; cur["fs_store"][i] = pred
+                a = cur["plan_first_row"][i]; b = a + cur["n_fs"][i]
+                pl[a:b] += pred - pl[a + fc - 1]
+                cur["cl_first_ramp"][i] = 0; ct[i] = 0
+        cur["j"] += 1
+    assert np.array_equal(r["inst"]["fs_counter"], cur["fs_counter"])
+    assert np.abs(r["fs_plan"] - pl).max() < 1e-6
+
+
+def test_walking_fixture_closed_loop(handle):
+    """The reference's own recorded output: CoM of walking/quad_walk_no_plots.m, phi=0, 10 cm steps
+    (AMR_code_DART/MATLAB_trajectories/walking/phi0_10cm_50), first 200 ticks, 7 significant digits."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "matlab_fixtures.npz"))
+    com = g["walk_phi0_com"]
+    from quadruped_gait_generation_ismpc_b200 import plans
+    model = abi.forma_model(q_foot=1e9)
+    handle.forma_set_model(model)
+    _, center = plans.walk_plan(phi=0.0)
+    inst = np.zeros(1, dtype=abi.FORMA_INST)
+    ft = np.arange(0, 2321, 50, dtype=np.int32)
+    inst["st"][0] = [0.44, 0, 0.44, 0, 0, 0]; inst["cur_fs"][0] = center[0]; inst["fs_store"][0] = center[0]
+    inst["height"] = 0.56; inst["wx"] = inst["wy"] = 0.02; inst["j"] = 1; inst["fs_counter"] = 1; inst["ds"] = 30
+    inst["cl_first_ramp"] = 1; inst["n_timing"] = len(ft); inst["n_fs"] = center.shape[0]
+    T = com.shape[0] - 1
+    r = handle.forma_rollout(inst, ft, center, T)
+    assert r["status"][0] == 0
+    err = np.abs(r["traj"][0, :T, :2] - com[1:T + 1, :2])
+    assert err.max() < 5e-6, "max err vs MATLAB fixture %.3e" % err.max()   # quadprog tolerance + %e printing

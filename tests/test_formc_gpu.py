@@ -1,0 +1,112 @@
+"""GPU parity of the formulation-C tick (MPCSolver::solve) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from quadruped_gait_generation_ismpc_b200 import abi, synth
+from oracle import oracle as O
+from parity import PRIMAL_TOL, primal_rel_err, active_set_mismatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(handle, model, state, walk, inst, plan, nthreads=8):
+    handle.formc_set_model(model)
+    g = handle.formc_solve_batch(state, walk, inst, plan)
+    o = O.formc_batch(model, state, walk, inst, plan, nthreads=nthreads)
+    N = int(model["N"][0])
+    ok = (o["ret"] == 0).all(axis=1) & (o["out"]["status"] & abi.ST_WINDOW == 0)
+    assert ok.sum() >= 0.8 * len(state), "too many oracle failures: %d of %d" % ((~ok).sum(), len(state))
+    # GPU must flag the instances the oracle found infeasible as failed too (no silent garbage)
+    gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
+    assert not gfail[ok].any(), "GPU failed on instances the oracle solved: %s" % np.nonzero(gfail & ok)[0][:10]
+    err = primal_rel_err(g["primal"][ok].reshape(-1, 3, N), o["primal"][ok].reshape(-1, 3, N))
+    assert err.max() <= PRIMAL_TOL, "primal rel err %.3e" % err.max()
+    for name in ("com_pos", "com_vel"):
+        e = np.abs(g["out"]["next"][name][ok] - o["out"]["next"][name][ok]).max()
+        assert e <= PRIMAL_TOL, "%s err %.3e" % (name, e)
+    assert np.abs(g["out"]["zmp_in"][ok] - o["out"]["zmp_in"][ok]).max() <= PRIMAL_TOL
+    assert (np.abs(g["out"]["fz0"][ok] - o["out"]["fz0"][ok]) / np.maximum(1, np.abs(o["out"]["fz0"][ok]))).max() <= PRIMAL_TOL
+    mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
+    assert mism.sum() == 0, "active set differs on %d rows (%d weak rows ignored)" % (mism.sum(), weak.sum())
+    assert g["out"]["kkt_res"][ok].max() < 1e-8
+    return g, o, ok
+
+
+def test_reference_instance_closed_loop(handle):
+    """Config 1: the DART app's single instance, 60 closed-loop ticks, oracle in lock-step from the GPU state."""
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.reference_formc_instance()
+    handle.formc_set_model(model)
+    for k in range(60):
+        walk["sim_time"] = k; walk["mpc_iter"] = k % 45; walk["control_iter"] = k % 45
+        g = handle.formc_solve_batch(state, walk, inst, plan)
+        o = O.formc_batch(model, state, walk, inst, plan)
+        assert (o["ret"] == 0).all()
+        assert primal_rel_err(g["primal"].reshape(1, 3, 100), o["primal"].reshape(1, 3, 100)).max() <= PRIMAL_TOL
+        mism, _ = active_set_mismatch(g["active"], o["active"], o["duals"])
+        assert mism.sum() == 0
+        state = state.copy(); state[0] = g["out"]["next"][0]
+
+
+def test_config2_batch_1024(handle):
+    """Config 2: 1,024 randomised trot instances, N=100."""
+    state, walk, inst, plan = synth.formc_batch(1024)
+    _compare(handle, abi.formc_model(), state, walk, inst, plan)
+
+
+def test_vertical_inequalities_active(handle):
+    """CoM well above / below the target height so that rows of 0 <= S_bar_z f <= 1e4 become active."""
+    state, walk, inst, plan = synth.formc_batch(256, seed=77, z_spread=0.08)
+    g, o, ok = _compare(handle, abi.formc_model(), state, walk, inst, plan)
+    assert (o["active"][ok][:, :100] != 0).any(), "test is vacuous: no vertical row active"
+
+
+def test_not_running_and_varied_height(handle):
+    """footstepCounter <= 1 (box +-1, no flight-phase rows) mixed in; per-instance CoM height."""
+    state, walk, inst, plan = synth.formc_batch(256, seed=5, vary_height=True, running_frac=0.5)
+    _compare(handle, abi.formc_model(), state, walk, inst, plan)
+
+
+@pytest.mark.parametrize("N", [50, 200, 400])
+def test_horizon_sweep(handle, N):
+    """Config 4: N in {50, 200, 400} (N=100 is covered above)."""
+    n = 64 if N < 400 else 16
+    steps = (2 * N + 900) // 45 + 3
+    state, walk, inst, plan = synth.formc_batch(n, seed=N, N=N, n_steps=steps)
+    _compare(handle, abi.formc_model(N=N), state, walk, inst, plan)
+
+
+def test_window_status_and_empty_batch(handle):
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(4, seed=9)
+    walk["sim_time"][1] = 40 * 45 - 150      # k0 + 2N beyond the midpoint sequence
+    g = handle.formc_solve_batch(state, walk, inst, plan)
+    assert g["out"]["status"][1] == abi.ST_WINDOW
+    assert (g["out"]["status"][[0, 2, 3]] & abi.ST_WINDOW == 0).all()
+    assert np.array_equal(g["out"]["next"]["com_pos"][1], state["com_pos"][1])
+    e = handle.formc_solve_batch(state[:0], walk[:0], inst[:0], plan)
+    assert len(e["out"]) == 0
+
+
+def test_rollout_matches_tick_by_tick(handle):
+    """ismpc_formc_rollout == repeated ismpc_formc_solve_batch with the Controller bookkeeping on the host."""
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(32, seed=21)
+    walk["sim_time"] = np.minimum(walk["sim_time"], 300)
+    T = 40
+    r = handle.formc_rollout(state, walk, inst, plan, T)
+    st, wk = state.copy(), walk.copy()
+    for t in range(T):
+        for i in range(len(st)):
+            fc = wk["footstep_counter"][i]
+            if fc < inst["n_steps"][i] and wk["sim_time"][i] >= plan[inst["plan_first_row"][i] + fc, 3] - 1:
+                wk["control_iter"][i] = 0; wk["mpc_iter"][i] = 0
+                wk["footstep_counter"][i] += 1; wk["support_foot"][i] = 1 - wk["support_foot"][i]
+        g = handle.formc_solve_batch(st, wk, inst, plan, want_primal=False, want_active=False)
+        st = g["out"]["next"].copy()
+        np.testing.assert_allclose(r["traj"][:, t, :3], st["com_pos"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r["traj"][:, t, 3:], st["com_vel"], rtol=0, atol=1e-12)
+        wk["control_iter"] += 1; wk["mpc_iter"] = wk["control_iter"]; wk["sim_time"] += 1
+    assert np.array_equal(r["walk"]["footstep_counter"], wk["footstep_counter"])
