@@ -26,10 +26,11 @@ def reference_formc_instance(n_ticks_time=0.0):
 
 
 def formc_batch(n, seed=SEED0 ^ 2, N=100, n_steps=40, S=35, F_ds=10, vary_height=False, z_spread=0.01,
-                running_frac=1.0):
+                running_frac=1.0, dcm_spread=0.035):
     """n randomised trot instances: step length L~U[0.05,0.25], half-width W~U[0.05,0.12] alternating,
-    heading in {0, pi/4, pi/2}, per-step jitter N(0, 0.01^2), k0~U{0..k0max}, state = mid(k0)+U[-0.02,0.02]^2,
-    velocity U[-0.1,0.1]^2, footstepCounter >= 2."""
+    heading in {0, pi/4, pi/2}, per-step jitter N(0, 0.01^2), k0~U{0..k0max}, velocity U[-0.1,0.1]^2, position
+    such that the divergent component is within dcm_spread of the value the footstep plan can stabilise
+    (a CoM parked over one foot is infeasible for the 9 cm ZMP box), footstepCounter >= 2."""
     rng = np.random.default_rng(seed)
     per = S + F_ds
     state = np.zeros(n, dtype=abi.STATE)
@@ -51,12 +52,26 @@ def formc_batch(n, seed=SEED0 ^ 2, N=100, n_steps=40, S=35, F_ds=10, vary_height
         plan[i * n_steps:(i + 1) * n_steps] = p
         k0 = int(rng.integers(0, min(800, k0max) + 1))
         step = k0 // per; r = k0 % per
-        a = p[step, :2]; b = p[min(step + 1, n_steps - 1), :2]
-        mid = a if r < S else a + (b - a) * ((r - S) / F_ds)
         h = rng.uniform(0.45, 0.75) if vary_height else 0.69
-        state["com_pos"][i] = [mid[0] + rng.uniform(-0.02, 0.02), mid[1] + rng.uniform(-0.02, 0.02),
-                               h + rng.uniform(-z_spread, z_spread)]
-        state["com_vel"][i] = [rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(-0.05, 0.05)]
+        # A state the ISMPC can stabilise: the divergent component xi = c + cd/eta must match the discounted
+        # future ZMP (stability row, MPCSolver.cpp:375-384, evaluated for u = box centres at nominal eta);
+        # it is then perturbed by U[-dcm_spread, dcm_spread] (box capacity is ~0.044 for w = 0.09).
+        eta = np.sqrt(9.81 / h); dt = 0.01
+        t = k0 + np.arange(2 * N)
+        si = t // per; ri = t % per
+        a_ = p[np.minimum(si, n_steps - 1), :2]; b_ = p[np.minimum(si + 1, n_steps - 1), :2]
+        ramp = np.where(ri < S, 0.0, (ri - S) / F_ds)[:, None]
+        midw = a_ + (b_ - a_) * ramp
+        midw[si >= n_steps - 1] = 0.0
+        e1 = np.exp(eta * dt)
+        avec = -np.exp(eta * dt * (N - 1 - np.arange(N))) * (e1 - 1.0)
+        rhs = eta * dt * (np.exp(-eta * dt * np.arange(N)) @ midw[N:]) - avec @ midw[:N]
+        xi0 = rhs / np.exp(eta * dt * N)
+        vel = rng.uniform(-0.1, 0.1, 2)
+        xi = xi0 + rng.uniform(-dcm_spread, dcm_spread, 2)
+        pos = xi - vel / eta
+        state["com_pos"][i] = [pos[0], pos[1], h + rng.uniform(-z_spread, z_spread)]
+        state["com_vel"][i] = [vel[0], vel[1], rng.uniform(-0.05, 0.05)]
         walk["sim_time"][i] = k0
         walk["mpc_iter"][i] = r
         walk["control_iter"][i] = r

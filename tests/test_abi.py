@@ -1,0 +1,73 @@
+"""The C ABI: struct layouts match the numpy mirrors, the library loads and exports every declared symbol,
+and the product fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from quadruped_gait_generation_ismpc_b200 import abi, binding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ismpc_b200.h")
+
+
+def test_struct_layouts_match_header():
+    names = list(abi.DTYPES)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ismpc_b200.h"', 'int main(void){']
+    for nme in names:
+        lines.append('printf("%s %%zu", sizeof(%s));' % (nme, nme))
+        for f in abi.DTYPES[nme].names:
+            lines.append('printf(" %s=%%zu", offsetof(%s, %s));' % (f, nme, f))
+        lines.append('printf("\\n");')
+    lines.append("return 0;}")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c"); exe = os.path.join(d, "t")
+        open(src, "w").write("\n".join(lines))
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = subprocess.check_output([exe], text=True)
+    for line in out.strip().splitlines():
+        tok = line.split()
+        nme, size = tok[0], int(tok[1])
+        dt = abi.DTYPES[nme]
+        assert dt.itemsize == size == abi.SIZES[nme], nme
+        for kv in tok[2:]:
+            f, off = kv.split("=")
+            assert dt.fields[f][1] == int(off), (nme, f)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(binding.LIB_PATH):
+        binding.build()
+    declared = set(re.findall(r"\b(ismpc_[a-z_0-9]+)\s*\(", open(HEADER).read()))
+    assert declared == set(binding.EXPORTS)
+    L = C.CDLL(binding.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), "missing export %s" % s
+    assert b"sm_100a" in binding.lib().ismpc_version()
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(binding.IsmpcError):
+        binding.Handle(device=0, max_batch=8)
+
+
+def test_product_never_touches_the_oracle():
+    """No file of the shipped package or its CUDA sources references the oracle."""
+    pkg = os.path.join(ROOT, "quadruped_gait_generation_ismpc_b200")
+    for dp, _, fs in os.walk(pkg):
+        if os.sep + "lib" in dp:
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                bad = re.search(r"(from|import)\s+oracle|oracle[/\\]|libismpc_oracle|ismpc_oracle\.h", txt)
+                assert bad is None, "%s uses the oracle: %s" % (f, bad.group(0))
+    libs = subprocess.check_output(["ldd", binding.LIB_PATH], text=True) if os.path.exists(binding.LIB_PATH) else ""
+    assert "oracle" not in libs
