@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the batched ISMPC hot path (BASELINE.json metric: batched ISMPC QP solves/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference ...                         # the reference's qpOASES CPU path (oracle/_ref)
+
+A "step" is one tick of MPCSolver::solve (formulation C: vertical QP + x QP + y QP = 3 QP solves per instance)
+over one batch of synthetic instances: BASELINE.json configs[1], 1,024 independent trot instances, N = 100,
+randomised footstep plans, per GPU (weak scaling: every rank owns its own 1,024 instances, no per-tick
+communication, one NCCL gather of the result records after the timed region).
+
+Printed JSON keys beyond the base contract:
+  roofline      dominant kernel (formc_tick_kernel) against the measured HBM copy bandwidth
+  roofline_fp64 same kernel against the measured FP64 FMA peak (the bound that actually applies)
+  cpu_baseline  the reference's qpOASES path (oracle/_ref) timed on this box's host cores, same workload
+  latency       p50/p90 per-tick device latency
+  form_a        the canonical-ISMPC (footstep) formulation on 1,024 mid-gait trot instances, cold start
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 1024          # instances per GPU (configs[1])
+HORIZON = 100
+L2_BYTES = 126 * 1024 * 1024
+# algorithmic HBM bytes per instance-tick of the fused kernel:
+# state 72 + walk 24 + inst 40 + 7 plan rows x 32 (the rows the 2N window touches) + out 128
+B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
+# executed FP64 flops per instance-tick: H^-1 F mat-vec 2N^2 + ~90N for scans/recurrences/Newton
+FLOP_FORMC = 2 * HORIZON * HORIZON + 90 * HORIZON
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_n=None, threads=None):
+    """The reference's CPU implementation of the path: restated builders + the reference's qpOASES with the
+    solveQP call form (oracle/_ref), every host thread, one cold QProblem per solve per thread."""
+    from oracle import oracle as O
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    kind = "ref" if O.have_ref() else "port"
+    threads = threads or O.hw_threads()
+    model = abi.formc_model(N=HORIZON)
+    n = sample_n or BATCH
+    state, walk, inst, plan = synth.formc_batch(n)
+    for _ in range(warmup):
+        O.formc_batch(model, state[:64], walk[:64], inst[:64], plan, nthreads=threads, kind=kind, want_full=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = O.formc_batch(model, state, walk, inst, plan, nthreads=threads, kind=kind, want_full=False)
+    dt = time.perf_counter() - t0
+    qps = 3.0 * n * steps / dt
+    return qps, dt / steps, threads, ("reference" if kind == "ref" else "port"), n, int((r["ret"] != 0).any(axis=1).sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, per_step, threads, kind, n, nfail = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "batched ISMPC QP solves/sec", "value": qps, "unit": "QP solves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "formC_tick_trot_1024xN100", "instances": n, "horizon_N": HORIZON,
+                       "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)"},
+            "cpu_baseline": {"value": qps, "unit": "QP solves/s", "cores": threads, "kind": kind,
+                             "sample": "%d instances x %d steps, all %d host threads, cold qpOASES QProblem per solve"
+                                       % (n, args.steps, threads), "failed_instances": nfail},
+            "e2e": {"value": qps, "unit": "QP solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="instances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-form-a", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from quadruped_gait_generation_ismpc_b200 import abi, binding, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K, W, n = args.steps, max(args.warmup, 3), args.batch
+    h = binding.Handle(device=local, max_batch=max(n, 1024))
+    model = abi.formc_model(N=HORIZON)
+    h.formc_set_model(model)
+
+    # ---- inputs: distinct batches rotating over a footprint larger than L2 -------------------------------
+    seeds = [synth.SEED0 ^ 2 ^ (rank * 7919 + s) for s in range(4)]
+    host_batches = [synth.formc_batch(n, seed=s, N=HORIZON) for s in seeds]
+    per_batch = sum(a.nbytes for a in host_batches[0]) + n * abi.FORMC_OUT.itemsize
+    n_slots = max(8, int(1.5 * L2_BYTES / per_batch) + 1)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    slots = []
+    for s in range(n_slots):
+        st, wk, ins, pl = host_batches[s % len(host_batches)]
+        slots.append(dict(state=to_dev(st), walk=to_dev(wk), inst=to_dev(ins), plan=to_dev(pl), rows=pl.shape[0],
+                          out=torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(k):
+        s = slots[k % n_slots]
+        h.formc_solve_batch_raw(n, s["state"].data_ptr(), s["walk"].data_ptr(), s["inst"].data_ptr(),
+                                s["plan"].data_ptr(), s["rows"], s["out"].data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(W):
+        step(k)
+    barrier()
+    # ---- timed region: K steps, CUDA events on the launching stream ---------------------------------------
+    clocks = ClockSampler(local); clocks.start()
+    l0 = h.kernel_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(K):
+        step(W + k)
+        ev[k + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[K])
+    launches = h.kernel_launches - l0
+    clk = clocks.stop()
+    per_step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    total_ms_max = sharding.max_over_ranks(total_ms, device=dev)
+    value = 3.0 * n * world * K / (total_ms_max * 1e-3)
+
+    # ---- kernel duration in isolation (roofline): events around single launches, inputs rotating ----------
+    kdur = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(min(K, 100)):
+        torch.cuda.synchronize()
+        e0.record(); step(W + K + k); e1.record(); e1.synchronize()
+        kdur.append(e0.elapsed_time(e1))
+    kernel_ms = statistics.median(kdur)
+
+    # ---- e2e: the C ABI with HOST buffers (pinned), copies inside the timed region -------------------------
+    pinned = []
+    for st, wk, ins, pl in host_batches:
+        d = {}
+        for name, a in (("state", st), ("walk", wk), ("inst", ins), ("plan", pl)):
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory()
+            d[name] = t
+        d["out"] = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8).pin_memory()
+        d["rows"] = pl.shape[0]
+        pinned.append(d)
+
+    def e2e_step(k):
+        d = pinned[k % len(pinned)]
+        h.formc_solve_batch_raw(n, d["state"].data_ptr(), d["walk"].data_ptr(), d["inst"].data_ptr(),
+                                d["plan"].data_ptr(), d["rows"], d["out"].data_ptr(), mem=abi.MEM_HOST, stream=stream)
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step(k)
+    barrier()
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e_value = 3.0 * n * world * K / e2e_s
+    h2d = sum(pinned[0][k].numel() for k in ("state", "walk", "inst", "plan")); d2h = pinned[0]["out"].numel()
+    # sanity: the e2e result equals the device-resident result for the same batch
+    chk = np.frombuffer(pinned[(K - 1) % len(pinned)]["out"].numpy().tobytes(), dtype=abi.FORMC_OUT)
+    bad = int(((chk["status"] & 7) != 0).sum())
+
+    # ---- final gather of the result records (the only collective on this path) -----------------------------
+    last = np.frombuffer(slots[(W + K - 1) % n_slots]["out"].cpu().numpy().tobytes(), dtype=abi.FORMC_OUT)
+    full = sharding.gather_records(last.copy(), n * world, device=dev) if world > 1 else last
+
+    line = None
+    if rank == 0:
+        hbm_peak, peak_src = load_peaks()
+        fp64_peak = h.measure_fp64_peak(5)
+        achieved = B_ALG_FORMC * n / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": "batched ISMPC QP solves/sec", "value": value, "unit": "QP solves/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "formC_tick_trot_1024xN100", "instances_per_gpu": n, "horizon_N": HORIZON,
+                           "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)",
+                           "l2": "inputs rotate over %d distinct device batches (%.0f MB > L2 126 MB)"
+                                 % (n_slots, n_slots * per_batch / 1e6)},
+                "e2e": {"value": e2e_value, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad},
+                "gpu_launches": int(launches),
+                "clocks": clk,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "formc_tick_kernel", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_instance_tick": B_ALG_FORMC},
+                "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
+                                  "peak": fp64_peak, "unit": "TFLOP/s",
+                                  "frac": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
+                                  "executed_flop_per_instance_tick": FLOP_FORMC,
+                                  "peak_source": "ismpc_measure_fp64_peak (DFMA micro-benchmark, this run)"},
+                "latency": {"p50_tick_us": statistics.median(per_step_ms) * 1e3,
+                            "p90_tick_us": sorted(per_step_ms)[int(0.9 * (K - 1))] * 1e3,
+                            "isolated_kernel_us": kernel_ms * 1e3},
+                "instance_ticks_per_s": value / 3.0,
+                "gathered_records": int(len(full))}
+
+    # ---- formulation A (canonical ISMPC with footsteps), rank 0 extra measurement -------------------------
+    if rank == 0 and not args.no_form_a:
+        try:
+            line["form_a"] = bench_form_a(h, torch, dev, n, stream)
+        except Exception as e:  # noqa: BLE001
+            line["form_a"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            reps = 3
+            qps, per_step, threads, kind, ns, nfail = cpu_reference_run(reps, 1)
+            line["cpu_baseline"] = {"value": qps, "unit": "QP solves/s", "cores": threads, "kind": kind,
+                                    "sample": "%d instances x %d passes of the same workload, all %d host threads, "
+                                              "cold qpOASES QProblem per solve (utils.cpp:121-130)" % (ns, reps, threads),
+                                    "failed_instances": nfail}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_form_a(h, torch, dev, n, stream, steps=20):
+    """1,024 trot instances of formulation A advanced on the GPU to random gait phases, then timed single cold ticks."""
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    model = abi.forma_model()
+    h.forma_set_model(model)
+    inst, ft, plan = synth.forma_batch(n, gait="trot")
+    rng = np.random.default_rng(5)
+    ticks = rng.choice([3, 17, 36, 49, 63, 98, 131, 160, 207, 260], size=n)
+    order = np.argsort(ticks, kind="stable")
+    for t in np.unique(ticks):
+        sel = np.nonzero(ticks == t)[0]
+        r = h.forma_rollout(inst[sel], ft, plan, int(t), want_traj=False)
+        inst[sel] = r["inst"]
+        for i in sel:
+            a = inst["plan_first_row"][i]; b = a + inst["n_fs"][i]
+            plan[a:b] = r["fs_plan"][a:b]
+    del order
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    d_inst, d_ft, d_plan = to_dev(inst), to_dev(ft), to_dev(plan)
+    d_out = torch.zeros(n * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for k in range(steps + 3):
+        torch.cuda.synchronize()
+        e0.record()
+        h.forma_solve_batch_raw(n, d_inst.data_ptr(), d_ft.data_ptr(), len(ft), d_plan.data_ptr(), plan.shape[0],
+                                d_out.data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+        e1.record(); e1.synchronize()
+        if k >= 3:
+            times.append(e0.elapsed_time(e1))
+    out = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
+    ms = statistics.median(times)
+    return {"workload": "formA_tick_trot_1024xC100F3_midgait_cold", "qp_solves_per_s": n / (ms * 1e-3),
+            "ms_per_tick": ms, "mean_iters_per_qp": float(out["iters"].mean()), "max_iters": int(out["iters"].max()),
+            "failed": int((out["status"] != 0).sum()), "note": "1 QP per instance-tick (x and y stacked, nV=206, nC=208)"}
+
+
+if __name__ == "__main__":
+    main()

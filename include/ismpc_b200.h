@@ -166,6 +166,10 @@ const char* ismpc_last_cuda_error(const ismpc_handle* h);
 /* Number of kernels this handle has launched since creation (for the benchmark's launch count). */
 int64_t ismpc_kernel_launches(const ismpc_handle* h);
 
+/* Measurement utility (not part of the reference seam): register-resident DFMA micro-benchmark, the FP64
+ * roofline denominator that MEASURED_PEAKS.json lacks.  Writes the best of `reps` runs in TFLOP/s. */
+int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops_out);
+
 /* MPCSolver::MPCSolver (MPCSolver.cpp:5-200): builds on the device the vertical prediction/cost tables
  * (H_z^-1 and friends) for this model.  Must be called before ismpc_formc_solve_batch. */
 int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* model);

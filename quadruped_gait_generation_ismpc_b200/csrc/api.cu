@@ -389,3 +389,43 @@ extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, cons
     CK(cudaStreamSynchronize(st));
     return ISMPC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 peak micro-benchmark (roofline denominator)
+// ---------------------------------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;    // never true: keeps the chain alive
+}
+
+extern "C" int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops_out)
+{
+    if (!h || !tflops_out || reps < 1) return ISMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->c_info.ensure(sizeof(double))) return ISMPC_ERR_ALLOC;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 1 << 16, threads = 256, blocks = h->sm_count * 8;
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; ++r) {
+        CK(cudaEventRecord(e0, 0));
+        fp64_peak_kernel<<<blocks, threads>>>((double*)h->c_info.p, iters, 1.0 + r);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    h->launches += reps + 1;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops_out = best;
+    return ISMPC_OK;
+}
