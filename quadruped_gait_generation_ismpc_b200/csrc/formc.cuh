@@ -280,6 +280,59 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     __syncthreads();
 
     // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
+    int ne = 0, c_lo = 0;
+    if (wk.footstep_counter > 1) {
+        if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }     // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
+        else { ne = S + F - wk.mpc_iter; c_lo = 0; }                 // Aeq_z(i,i), i < S+F-mpcIter
+        if (c_lo < 0) { ne += c_lo; c_lo = 0; }
+        if (c_lo + ne > N) ne = N - c_lo;
+        if (ne < 0) ne = 0;
+    }
+    // keep the unconstrained minimiser for the general path
+    for (int i = tid; i < N; i += FORMC_THREADS) sm.Fz[i] = sm.f[i];
+    // ---- fast path: equality-constrained minimiser in closed form (all rows of 0 <= S f <= fz_max inactive) ----
+    //   f = x0 - H^-1[:,K] mu,  (H^-1)_KK mu = x0_K   with K = [c_lo, c_lo+ne) a contiguous column range
+    const bool fast_eq = (ne > 0 && ne <= 32);
+    if (fast_eq) {
+        double* Sk = sm.das.L;                                       // ne x ne, row-major (fits: 32*32 <= packed qmax)
+        for (int e = tid; e < ne * ne; e += FORMC_THREADS) {
+            int r = e / ne, c = e - r * ne;
+            Sk[e] = __ldg(T.Hinv + (size_t)(c_lo + r) * N + c_lo + c);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // Cholesky (left-looking, lane = row), then two triangular solves; ne <= 32
+            for (int j = 0; j < ne; ++j) {
+                double sdot = 0.0;
+                if (lane >= j && lane < ne) {
+                    sdot = Sk[lane * ne + j];
+                    for (int k = 0; k < j; ++k) sdot -= Sk[lane * ne + k] * Sk[j * ne + k];
+                }
+                const double djj = sqrt(__shfl_sync(ISMPC_FULL_MASK, sdot, j));
+                if (lane >= j && lane < ne) Sk[lane * ne + j] = (lane == j) ? djj : sdot / djj;
+                __syncwarp();
+            }
+            double yv = (lane < ne) ? sm.f[c_lo + lane] : 0.0;       // rhs x0_K, forward solve L y = rhs
+            for (int k = 0; k < ne; ++k) {
+                double yk = __shfl_sync(ISMPC_FULL_MASK, yv, k) / Sk[k * ne + k];
+                if (lane == k) yv = yk;
+                if (lane > k && lane < ne) yv -= Sk[lane * ne + k] * yk;
+            }
+            for (int k = ne - 1; k >= 0; --k) {                      // backward solve L' mu = y
+                double mk = __shfl_sync(ISMPC_FULL_MASK, yv, k) / Sk[k * ne + k];
+                if (lane == k) yv = mk;
+                if (lane < k) yv -= Sk[k * ne + lane] * mk;
+            }
+            if (lane < ne) sm.das.mu[lane] = yv;
+        }
+        __syncthreads();
+        for (int i = tid; i < N; i += FORMC_THREADS) {
+            double acc = sm.f[i];
+            for (int k = 0; k < ne; ++k) acc -= __ldg(T.Hinv + (size_t)(c_lo + k) * N + i) * sm.das.mu[k];
+            sm.f[i] = acc;
+        }
+        __syncthreads();
+    }
     int it_z = 0;
     if (warp == 0) {
         DasWork w = sm.das;
@@ -288,21 +341,30 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         __syncwarp();
         VertProb vp{N, T, c1, mdl.fz_max, sm.scr};
         int zfail = 0;
-        if (wk.footstep_counter > 1) {
-            int ne, c_lo;
-            if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }                 // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
-            else { ne = S + F - wk.mpc_iter; c_lo = 0; }                             // Aeq_z(i,i), i < S+F-mpcIter
+        bool done = false;
+        if (fast_eq || ne == 0) {
+            vp.eval(sm.f, sm.rv);
+            double worst = 0.0;
+            for (int i = lane; i < N; i += 32) {
+                double v = sm.rv[i];
+                worst = fmin(worst, fmin(v + 1e-10, (mdl.fz_max - v) + 1e-10 * (1.0 + fabs(mdl.fz_max))));
+            }
+            worst = warp_min(worst);
+            done = !(worst < 0.0);
+        }
+        if (!done) {
+            // general path: dual active set from the unconstrained minimiser (equalities first, never dropped)
+            for (int i = lane; i < N; i += 32) sm.f[i] = sm.Fz[i];
+            __syncwarp();
             for (int e = 0; e < ne; ++e) {
-                int c = c_lo + e;
-                if (c < 0 || c >= N) continue;
-                int rc = das_add_equality(vp, w, sm.f, sm.zdir, N + c, sm.f[c], 0.0);
+                int rc = das_add_equality(vp, w, sm.f, sm.zdir, N + c_lo + e, sm.f[c_lo + e], 0.0);
                 if (rc < 0) zfail = 1;
                 __syncwarp();
             }
             w.neq = w.q;
+            int rc = das_solve(vp, w, sm.f, sm.rv, sm.zdir, 4 * N + 16, &it_z);
+            if (rc != 0 || zfail) status |= ISMPC_ST_Z_FAIL;
         }
-        int rc = das_solve(vp, w, sm.f, sm.rv, sm.zdir, 4 * N + 16, &it_z);
-        if (rc != 0 || zfail) status |= ISMPC_ST_Z_FAIL;
         // active set of the S_bar_z rows
         if (act) for (int i = lane; i < N; i += 32) act[i] = w.state[i];
         // primal residual for the self-check: rows within bounds (rv holds S x of the last eval)

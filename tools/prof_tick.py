@@ -1,0 +1,55 @@
+"""Small driver for ncu: launches a handful of tick kernels on device-resident data.
+usage: python tools/prof_tick.py [formc|forma] [n] [reps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quadruped_gait_generation_ismpc_b200 import abi, binding, synth  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "formc"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+dev = torch.device("cuda", 0)
+h = binding.Handle(0, max_batch=max(n, 1024))
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if which == "formc":
+    h.formc_set_model(abi.formc_model())
+    st, wk, ins, pl = synth.formc_batch(n)
+    d = [to_dev(x) for x in (st, wk, ins, pl)]
+    out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
+    for r in range(reps):
+        e0.record()
+        h.formc_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), pl.shape[0],
+                                out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        e1.record(); e1.synchronize()
+        print("formc tick n=%d: %.1f us" % (n, e0.elapsed_time(e1) * 1e3))
+else:
+    h.forma_set_model(abi.forma_model())
+    inst, ft, plan = synth.forma_batch(n, gait="trot")
+    rng = np.random.default_rng(5)
+    ticks = rng.choice([3, 17, 36, 49, 63, 98, 131, 160, 207, 260], size=n)
+    for t in np.unique(ticks):
+        sel = np.nonzero(ticks == t)[0]
+        r = h.forma_rollout(inst[sel], ft, plan, int(t), want_traj=False)
+        inst[sel] = r["inst"]
+        for i in sel:
+            a = inst["plan_first_row"][i]; b = a + inst["n_fs"][i]
+            plan[a:b] = r["fs_plan"][a:b]
+    d = [to_dev(x) for x in (inst, ft, plan)]
+    out = torch.zeros(n * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
+    for r in range(reps):
+        e0.record()
+        h.forma_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), len(ft), d[2].data_ptr(), plan.shape[0],
+                                out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        e1.record(); e1.synchronize()
+        o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
+        print("forma tick n=%d: %.1f us, mean iters %.1f, failed %d" % (n, e0.elapsed_time(e1) * 1e3, o["iters"].mean(), (o["status"] != 0).sum()))
