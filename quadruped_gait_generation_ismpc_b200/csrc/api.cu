@@ -429,3 +429,11 @@ extern "C" int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops
     *tflops_out = best;
     return ISMPC_OK;
 }
+
+#ifdef ISMPC_PHASE_TIMING
+__device__ long long ismpc::g_phase[64];
+extern "C" int ismpc_debug_read_phases(long long* out64)
+{
+    return (int)cudaMemcpyFromSymbol(out64, ismpc::g_phase, sizeof(long long) * 64);
+}
+#endif

@@ -19,7 +19,7 @@
 namespace ismpc {
 
 constexpr int FORMC_THREADS = 128;
-constexpr int FORMC_QMAX = 64;        // max working-set size of the vertical QP (equalities + active rows)
+constexpr int FORMC_QMAX = 48;        // max working-set size of the vertical QP (equalities + active rows)
 constexpr int FORMC_PLAN_STAGE = 40;  // plan rows staged in shared memory by one bulk copy
 
 struct FormCTables {      // device pointers, N x N row-major each (built once per model)
@@ -180,6 +180,14 @@ struct FormCArgs {
     signed char* active; // nullable, n x 3N
 };
 
+// Debug-only phase timing (make dbg -> lib/libismpc_b200_dbg.so; never in the product library).
+#ifdef ISMPC_PHASE_TIMING
+extern __device__ long long g_phase[64];
+#define ISMPC_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase[k] = clock64(); } while (0)
+#else
+#define ISMPC_PHASE(k) do { } while (0)
+#endif
+
 // One tick for one instance by one CTA (FORMC_THREADS threads).  `st`/`wk` are the instance's current
 // state/walk (registers, uniform across the CTA); results are written to *o (thread 0) and, if non-null,
 // prim (3N) / act (3N).
@@ -229,6 +237,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         if (k < N) sm.midz[k] = midpoint_value(rows, first, in.n_steps, S, F, k0 + k, 2);
     }
     __syncthreads();
+    ISMPC_PHASE(0);
 
     // ================= STAGE 1: vertical QP (MPCSolver.cpp:220-269) =================
     const double z0 = st.com_pos[2], zd0 = st.com_vel[2];
@@ -242,6 +251,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         sm.scr[k] = zd0 - g * dt * (double)k;                                       // w
     }
     __syncthreads();
+    ISMPC_PHASE(1);
     // F_j = q_p*c1 * sum_{k>j}(k-j) v_k + q_v*c1v * sum_{k>j} w_k - q_u*m*g
     if (warp == 0) {
         warp_suffix_sum_smem(sm.rv, N);    // SI_l = sum_{k>=l} v_k
@@ -250,12 +260,14 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         warp_suffix_sum_smem(sm.scr, N);   // sum_{k>=j} w_k
     }
     __syncthreads();
+    ISMPC_PHASE(2);
     for (int j = tid; j < N; j += FORMC_THREADS) {
         double p2 = (j + 1 < N) ? sm.rv[j + 1] : 0.0;
         double pw = (j + 1 < N) ? sm.scr[j + 1] : 0.0;
         sm.Fz[j] = mdl.q_p * c1 * p2 + mdl.q_v * c1v * pw - mdl.q_u * mass * g;
     }
     __syncthreads();
+    ISMPC_PHASE(3);
     // unconstrained minimiser x0 = -H^-1 F  (table mat-vec; Hinv symmetric -> coalesced row reads).
     // The 4 warps split the j range; each lane owns outputs i = blk*128 + lane + 32e.  Per-warp partial
     // vectors go to shared memory (zdir/lam/chv/shs are free at this point) and are summed afterwards.
@@ -276,8 +288,10 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         }
     }
     __syncthreads();
+    ISMPC_PHASE(4);
     for (int i = tid; i < N; i += FORMC_THREADS) sm.f[i] = -(sm.zdir[i] + sm.lam[i] + sm.chv[i] + sm.shs[i]);
     __syncthreads();
+    ISMPC_PHASE(5);
 
     // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
     int ne = 0, c_lo = 0;
@@ -300,38 +314,45 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
             Sk[e] = __ldg(T.Hinv + (size_t)(c_lo + r) * N + c_lo + c);
         }
         __syncthreads();
+        ISMPC_PHASE(6);
         if (warp == 0) {
-            // Cholesky (left-looking, lane = row), then two triangular solves; ne <= 32
+            // LDL' (right-looking, lane = row, one reciprocal per column, no sqrt), then the two
+            // triangular solves with the stored reciprocals; ne <= 32.  Sk[i][j] (j<i) := L_ij, Sk[j][j] := 1/d_j
             for (int j = 0; j < ne; ++j) {
-                double sdot = 0.0;
-                if (lane >= j && lane < ne) {
-                    sdot = Sk[lane * ne + j];
-                    for (int k = 0; k < j; ++k) sdot -= Sk[lane * ne + k] * Sk[j * ne + k];
+                const double rd = 1.0 / Sk[j * ne + j];
+                double lij = 0.0;
+                if (lane > j && lane < ne) lij = Sk[lane * ne + j];          // a_ij (pre-division)
+                __syncwarp();
+                if (lane > j && lane < ne) {
+                    const double l = lij * rd;
+                    for (int c = j + 1; c <= lane; ++c) Sk[lane * ne + c] -= l * Sk[c * ne + j];   // uses a_cj (undivided)
                 }
-                const double djj = sqrt(__shfl_sync(ISMPC_FULL_MASK, sdot, j));
-                if (lane >= j && lane < ne) Sk[lane * ne + j] = (lane == j) ? djj : sdot / djj;
+                __syncwarp();
+                if (lane > j && lane < ne) Sk[lane * ne + j] = lij * rd;
+                if (lane == j) Sk[j * ne + j] = rd;
                 __syncwarp();
             }
-            double yv = (lane < ne) ? sm.f[c_lo + lane] : 0.0;       // rhs x0_K, forward solve L y = rhs
+            double yv = (lane < ne) ? sm.f[c_lo + lane] : 0.0;               // forward: L y = rhs
             for (int k = 0; k < ne; ++k) {
-                double yk = __shfl_sync(ISMPC_FULL_MASK, yv, k) / Sk[k * ne + k];
-                if (lane == k) yv = yk;
+                const double yk = __shfl_sync(ISMPC_FULL_MASK, yv, k);
                 if (lane > k && lane < ne) yv -= Sk[lane * ne + k] * yk;
             }
-            for (int k = ne - 1; k >= 0; --k) {                      // backward solve L' mu = y
-                double mk = __shfl_sync(ISMPC_FULL_MASK, yv, k) / Sk[k * ne + k];
-                if (lane == k) yv = mk;
+            if (lane < ne) yv *= Sk[lane * ne + lane];                        // D^-1
+            for (int k = ne - 1; k >= 0; --k) {                              // backward: L' mu = y
+                const double mk = __shfl_sync(ISMPC_FULL_MASK, yv, k);
                 if (lane < k) yv -= Sk[k * ne + lane] * mk;
             }
             if (lane < ne) sm.das.mu[lane] = yv;
         }
         __syncthreads();
+        ISMPC_PHASE(7);
         for (int i = tid; i < N; i += FORMC_THREADS) {
             double acc = sm.f[i];
             for (int k = 0; k < ne; ++k) acc -= __ldg(T.Hinv + (size_t)(c_lo + k) * N + i) * sm.das.mu[k];
             sm.f[i] = acc;
         }
         __syncthreads();
+        ISMPC_PHASE(8);
     }
     int it_z = 0;
     if (warp == 0) {
@@ -374,6 +395,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         if (lane == 0) { sm.red[0] = viol; sm.red[1] = (double)status; sm.red[2] = (double)it_z; }
     }
     __syncthreads();
+    ISMPC_PHASE(9);
     double kkt = fmax(0.0, sm.red[0]);
     status = (int)sm.red[1];
     it_z = (int)sm.red[2];
@@ -388,6 +410,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         warp_prefix_sum_smem(sm.scr, N);
     }
     __syncthreads();
+    ISMPC_PHASE(10);
     for (int j = tid; j < N; j += FORMC_THREADS) {
         double sf = (j == 0) ? 0.0 : c1 * sm.scr[j - 1];
         double tg = -g * (dt * dt) * (0.5 * (double)j * (double)(j + 1));
@@ -404,6 +427,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         sm.dl[j] = exp(-dt * eta * (double)j);                                      // deltas (:183-184)
     }
     __syncthreads();
+    ISMPC_PHASE(11);
     const double fz0 = sm.f[0];
     const double lam0 = sm.lam[0];
     double nz0 = 1.0 * z0 + dt * zd0, nz1 = zd0 + (dt / mass) * fz0 - dt * g;      // (:274)
@@ -460,6 +484,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
             if (lane == 0) sm.red[6 + (warp - 1)] = t;
         }
         __syncthreads();
+        ISMPC_PHASE(12);
         if (warp < 2) {
             const int ax = warp;
             const double* mq = ax == 0 ? sm.midx : sm.midy;
@@ -482,6 +507,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
             }
         }
         __syncthreads();
+        ISMPC_PHASE(13);
         ux0 = sm.red[8]; uy0 = sm.red[11];
         int e0 = (int)sm.red[9], e1 = (int)sm.red[12];
         status |= (e0 & 1023) | (e1 & 1023);

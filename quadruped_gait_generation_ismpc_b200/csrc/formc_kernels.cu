@@ -114,7 +114,10 @@ int formc_setup_launch(const ismpc_formc_model_t& m, double* work /*3 N^2*/, dou
 // ---------------------------------------------------------------------------------------------------
 // Fused tick: one CTA per instance.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FORMC_THREADS)
+#ifndef FORMC_MIN_CTAS
+#define FORMC_MIN_CTAS 7
+#endif
+__global__ void __launch_bounds__(FORMC_THREADS, FORMC_MIN_CTAS)
 formc_tick_kernel(FormCArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

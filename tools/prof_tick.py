@@ -9,6 +9,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadruped_gait_generation_ismpc_b200 import abi, binding, synth  # noqa: E402
 
+if os.environ.get("ISMPC_DBG"):
+    binding.LIB_PATH = binding.LIB_PATH.replace("libismpc_b200.so", "libismpc_b200_dbg.so")
+
 which = sys.argv[1] if len(sys.argv) > 1 else "formc"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
@@ -53,3 +56,10 @@ else:
         e1.record(); e1.synchronize()
         o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
         print("forma tick n=%d: %.1f us, mean iters %.1f, failed %d" % (n, e0.elapsed_time(e1) * 1e3, o["iters"].mean(), (o["status"] != 0).sum()))
+
+if os.environ.get("ISMPC_DBG"):
+    import ctypes as C
+    ph = (C.c_longlong * 64)()
+    binding.lib().ismpc_debug_read_phases(ph)
+    v = list(ph)[:24]
+    print("phase clocks (CTA 0, deltas in cycles):", [v[i + 1] - v[i] for i in range(len(v) - 1) if v[i + 1] and v[i]])
