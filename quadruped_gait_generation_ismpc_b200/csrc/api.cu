@@ -38,7 +38,7 @@ struct ismpc_handle {
     ismpc_forma_model_t am{};
     // staging (host-memory calls)
     DevBuf s_state, s_walk, s_cinst, s_cout, s_plan, s_primal, s_active, s_push, s_traj, s_status;
-    DevBuf s_ainst, s_aout, s_timing, a_Lwork;
+    DevBuf s_ainst, s_aout, s_timing, a_Lwork, a_queue;
     DevBuf q_in, q_out, q_work;
 };
 
@@ -90,7 +90,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
     cudaSetDevice(h->device);
     DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
-                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->q_in, &h->q_out, &h->q_work};
+                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work};
     for (DevBuf* b : all) b->release();
     delete h;
     return ISMPC_OK;
@@ -263,20 +263,18 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     const int nV = 2 * (h->am.C + h->am.F);
     FormAArgs a;
     a.n = n; a.model = h->am; a.timing_len = timing_len; a.plan_rows = plan_rows; a.sm_count = h->sm_count;
-    a.warps_per_cta = 2; a.L_in_smem = 1; a.Lwork = nullptr;
-    {
-        const size_t lw = forma_Lwork_doubles(h->am, n);
-        if (lw) {
-            if (h->a_Lwork.ensure(lw * sizeof(double))) return ISMPC_ERR_ALLOC;
-            a.Lwork = (double*)h->a_Lwork.p;
-        }
-    }
+    FormALaunchPlan lp;
+    forma_plan(h->am, h->sm_count, 2LL * n, &lp);
+    if (h->a_Lwork.ensure((lp.spill_doubles + 2) * sizeof(double)) || h->a_queue.ensure(sizeof(int))) return ISMPC_ERR_ALLOC;
+    a.Jspill = lp.spill_doubles ? (double*)h->a_Lwork.p : nullptr;
+    a.queue = (int*)h->a_queue.p;
+    a.R = lp.R; a.warps_per_cta = lp.warps_per_cta;
     if (mem == ISMPC_MEM_DEVICE) {
         a.inst = inst; a.fs_timing = fs_timing; a.fs_plan = fs_plan; a.out = out; a.primal = primal_opt;
         a.active = (signed char*)active_opt;
-        int rc = rollout ? forma_rollout_launch(a, inst, fs_plan, push, n_ticks, traj_opt, status_opt, st)
-                         : forma_tick_launch(a, st);
-        h->launches += 1;
+        int rc = rollout ? forma_rollout_launch(a, lp, inst, fs_plan, push, n_ticks, traj_opt, status_opt, st)
+                         : forma_tick_launch(a, lp, st);
+        h->launches += rollout ? 2 : 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
         return ISMPC_OK;
     }
@@ -300,13 +298,13 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
     int rc;
     if (rollout)
-        rc = forma_rollout_launch(a, (ismpc_forma_inst_t*)h->s_ainst.p, (double*)h->s_plan.p,
+        rc = forma_rollout_launch(a, lp, (ismpc_forma_inst_t*)h->s_ainst.p, (double*)h->s_plan.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr,
                                   status_opt ? (int32_t*)h->s_status.p : nullptr, st);
     else
-        rc = forma_tick_launch(a, st);
-    h->launches += 1;
+        rc = forma_tick_launch(a, lp, st);
+    h->launches += rollout ? 2 : 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
     if (rollout) {
         CK(cudaMemcpyAsync(inst, h->s_ainst.p, n * sizeof(ismpc_forma_inst_t), cudaMemcpyDeviceToHost, st));

@@ -7,6 +7,28 @@
 
 namespace ismpc {
 
+// Debug-only cycle counters (make dbg -> lib/libismpc_b200_dbg.so; never in the product library).
+// g_phase[0..31]: form-C tick phase stamps of CTA 0; g_phase[32..63]: accumulated cycles per section of the
+// dual active-set loop over all warps (DasTimer).
+#ifdef ISMPC_PHASE_TIMING
+extern __device__ long long g_phase[64];
+struct DasTimer {
+    long long t;
+    __device__ __forceinline__ void start() { t = clock64(); }
+    __device__ __forceinline__ void lap(int k)
+    {
+        const long long n = clock64();
+        if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_phase[32 + k]), (unsigned long long)(n - t));
+        t = n;
+    }
+};
+#else
+struct DasTimer {
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void lap(int) {}
+};
+#endif
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
@@ -118,11 +140,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
+        "WAIT_LOOP_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}"
+        "@p bra.uni WAIT_DONE_%=;\n\t"
+        "bra.uni WAIT_LOOP_%=;\n\t"
+        "WAIT_DONE_%=:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 

@@ -31,9 +31,10 @@ struct FormAArgs {
     double* primal;        // nullable, n x 2(C+F)
     signed char* active;   // nullable, n x 2(C+F)
     int sm_count;
-    double* Lwork;         // global-memory Cholesky workspace (used when the factor does not fit in smem)
     int warps_per_cta;
-    int L_in_smem;
+    int R;                 // rows of the inverse factor kept in shared memory (das.cuh)
+    double* Jspill;        // global slices for rows >= R: one per resident warp (grid * warps_per_cta)
+    int* queue;            // work queue head (items = (instance, axis) pairs), zeroed before the launch
 };
 
 struct FormAShared {   // per-warp slices
@@ -44,26 +45,31 @@ struct FormAShared {   // per-warp slices
 };
 
 __host__ __device__ inline size_t forma_vec_doubles(int C, int F) { return (size_t)4 * C + 5 * (C + F) + 3 * (C + F + 1); }
-__host__ __device__ inline size_t forma_L_doubles(int C, int F) { size_t q = C + F + 1; return q * (q + 1) / 2; }
+__host__ __device__ inline size_t forma_spill_doubles(int C, int F, int R)
+{
+    const int q = C + F + 1;
+    return R >= q ? 0 : (size_t)(tri(q, 0) - tri(R, 0));
+}
 __host__ __device__ inline size_t forma_byte_tail(int C, int F)
 {
     size_t q = C + F + 1;
     size_t b = q * sizeof(int) + q /*wsg*/ + (C + F) /*state*/ + C /*mp*/;
     return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t forma_warp_smem_bytes(int C, int F, bool L_in_smem)
+__host__ __device__ inline size_t forma_warp_smem_bytes(int C, int F, int R)
 {
-    return (forma_vec_doubles(C, F) + (L_in_smem ? forma_L_doubles(C, F) : 0)) * sizeof(double) + forma_byte_tail(C, F);
+    return (forma_vec_doubles(C, F) + (size_t)tri(R, 0)) * sizeof(double) + forma_byte_tail(C, F);
 }
 
-__device__ inline void forma_carve(unsigned char* base, int C, int F, bool L_in_smem, double* L_global, FormAShared& s)
+__device__ inline void forma_carve(unsigned char* base, int C, int F, int R, double* J_global, FormAShared& s)
 {
     const int n = C + F, q = n + 1;
     double* d = reinterpret_cast<double*>(base);
     s.a = d; d += C; s.PA = d; d += C; s.mw = d; d += C; s.scr = d; d += C;
     s.x = d; d += n; s.z = d; d += n; s.rv = d; d += n; s.lo = d; d += n; s.hi = d; d += n;
     s.das.mu = d; d += q; s.das.r = d; d += q; s.das.y = d; d += q;
-    if (L_in_smem) { s.das.L = d; d += forma_L_doubles(C, F); } else s.das.L = L_global;
+    s.das.Js = d; d += tri(R, 0);
+    s.das.Jg = J_global; s.das.R = R;
     s.das.wid = reinterpret_cast<int*>(d);
     s.das.wsg = reinterpret_cast<signed char*>(s.das.wid + q);
     s.das.state = s.das.wsg + q;
@@ -95,6 +101,7 @@ struct FormAProb {
     __device__ int nvar() const { return C + F; }
     __device__ double lo(int i) const { return lo_[i]; }
     __device__ double hi(int i) const { return hi_[i]; }
+    __device__ void on_step(double) const {}
     // coefficient of footstep variable f (0-based, column f+1 of `mapping`) in ZMP row i
     __device__ double mcoef(int i, int f) const
     {

@@ -1,4 +1,9 @@
 // forma_kernels.cu -- formulation A kernels: single tick and closed-loop rollout, one warp per (instance, axis).
+//
+// Persistent warps: the grid is sized to what is resident (CTAs/SM x SM count); every warp pulls
+// (instance, axis) items from a global queue head, so instances whose QPs need many working-set changes
+// do not hold up a fixed instance<->CTA map (the iteration count per QP varies 5..100+ inside one batch).
+#include <cstdlib>
 #include "forma.cuh"
 #include "launch.h"
 
@@ -10,41 +15,52 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+__device__ __forceinline__ long long forma_next_item(int* queue)
+{
+    int v = 0;
+    if (lane_id() == 0) v = atomicAdd(queue, 1);
+    return (long long)__shfl_sync(ISMPC_FULL_MASK, v, 0);
+}
+
 __global__ void forma_tick_kernel(FormAArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = warp_id(), lane = lane_id();
     const int C = a.model.C, F = a.model.F, n = C + F;
-    const size_t wbytes = forma_warp_smem_bytes(C, F, a.L_in_smem);
-    const long long item = (long long)blockIdx.x * a.warps_per_cta + warp;
-    if (item >= 2LL * a.n) return;
+    const size_t wbytes = forma_warp_smem_bytes(C, F, a.R);
+    const size_t slot = (size_t)blockIdx.x * a.warps_per_cta + warp;
     FormAShared sm;
-    forma_carve(smem_raw + wbytes * warp, C, F, a.L_in_smem,
-                a.Lwork ? a.Lwork + (size_t)item * forma_L_doubles(C, F) : nullptr, sm);
-    const int inst = (int)(item >> 1), axis = (int)(item & 1);
-    const ismpc_forma_inst_t in = a.inst[inst];
-    const double* plan = a.fs_plan + (size_t)in.plan_first_row * 2;
-    const int32_t* ft = a.fs_timing + in.timing_first;
-    double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
-    int iters; double kkt;
-    int status = forma_tick_axis(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
-                                 in.cl_first_ramp, plan, ft, axis, &iters, &kkt);
-    const double eta = sqrt(a.model.g_eta / in.height);
-    const double zd0 = sm.x[0];
-    forma_integrate(eta, a.model.dt, s3, zd0);
-    ismpc_forma_out_t* o = a.out + inst;
-    if (lane < 3) o->st[axis * 3 + lane] = s3[lane];
-    for (int f = lane; f < F; f += 32) o->pred_fs[axis * F + f] = sm.x[C + f];
-    if (lane == 0) {
-        atomicOr(&o->status, status);
-        atomicAdd(&o->iters, iters);
-        atomic_max_nonneg(&o->kkt_res, kkt);
-    }
-    if (a.primal) for (int i = lane; i < n; i += 32) a.primal[(size_t)inst * 2 * n + axis * n + i] = sm.x[i];
-    if (a.active) {
-        signed char* act = a.active + (size_t)inst * 2 * n;
-        for (int i = lane; i < C; i += 32) act[axis * C + i] = sm.das.state[i];
-        for (int f = lane; f < F; f += 32) act[2 * C + axis * F + f] = sm.das.state[C + f];
+    forma_carve(smem_raw + wbytes * warp, C, F, a.R,
+                a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
+    for (;;) {
+        const long long item = forma_next_item(a.queue);
+        if (item >= 2LL * a.n) break;
+        const int inst = (int)(item >> 1), axis = (int)(item & 1);
+        const ismpc_forma_inst_t in = a.inst[inst];
+        const double* plan = a.fs_plan + (size_t)in.plan_first_row * 2;
+        const int32_t* ft = a.fs_timing + in.timing_first;
+        double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
+        int iters; double kkt;
+        int status = forma_tick_axis(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
+                                     in.cl_first_ramp, plan, ft, axis, &iters, &kkt);
+        const double eta = sqrt(a.model.g_eta / in.height);
+        const double zd0 = sm.x[0];
+        forma_integrate(eta, a.model.dt, s3, zd0);
+        ismpc_forma_out_t* o = a.out + inst;
+        if (lane < 3) o->st[axis * 3 + lane] = s3[lane];
+        for (int f = lane; f < F; f += 32) o->pred_fs[axis * F + f] = sm.x[C + f];
+        if (lane == 0) {
+            atomicOr(&o->status, status);
+            atomicAdd(&o->iters, iters);
+            atomic_max_nonneg(&o->kkt_res, kkt);
+        }
+        if (a.primal) for (int i = lane; i < n; i += 32) a.primal[(size_t)inst * 2 * n + axis * n + i] = sm.x[i];
+        if (a.active) {
+            signed char* act = a.active + (size_t)inst * 2 * n;
+            for (int i = lane; i < C; i += 32) act[axis * C + i] = sm.das.state[i];
+            for (int f = lane; f < F; f += 32) act[2 * C + axis * F + f] = sm.das.state[C + f];
+        }
+        __syncwarp();
     }
 }
 
@@ -64,105 +80,135 @@ __global__ void forma_rollout_kernel(FormARolloutArgs ra)
     const FormAArgs& a = ra.base;
     const int warp = warp_id(), lane = lane_id();
     const int C = a.model.C, F = a.model.F;
-    const size_t wbytes = forma_warp_smem_bytes(C, F, a.L_in_smem);
-    const long long item = (long long)blockIdx.x * a.warps_per_cta + warp;
-    if (item >= 2LL * a.n) return;
+    const size_t wbytes = forma_warp_smem_bytes(C, F, a.R);
+    const size_t slot = (size_t)blockIdx.x * a.warps_per_cta + warp;
     FormAShared sm;
-    forma_carve(smem_raw + wbytes * warp, C, F, a.L_in_smem,
-                a.Lwork ? a.Lwork + (size_t)item * forma_L_doubles(C, F) : nullptr, sm);
-    const int inst = (int)(item >> 1), axis = (int)(item & 1);
-    const ismpc_forma_inst_t in = ra.inst_io[inst];
-    double* plan = ra.plan_io + (size_t)in.plan_first_row * 2;
-    const int32_t* ft = a.fs_timing + in.timing_first;
-    const double eta = sqrt(a.model.g_eta / in.height);
-    double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
-    double cur = in.cur_fs[axis], store = in.fs_store[axis];
-    int j = in.j, fsc = in.fs_counter, first_ramp = in.cl_first_ramp, ct = 0, acc = 0;
-    ismpc_push_t pu; pu.fs = -1; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
-    if (ra.push) pu = ra.push[inst];
-    for (int tick = 0; tick < ra.n_ticks; ++tick) {
-        if (fsc == pu.fs && ct >= pu.ct0 && ct < pu.ct1) s3[1] += a.model.dt * (axis == 0 ? pu.ax : pu.ay); // bang.m:104-114
-        int iters; double kkt;
-        acc |= forma_tick_axis(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis, &iters, &kkt);
-        const double zd0 = sm.x[0], pred = sm.x[C];
-        __syncwarp();
-        forma_integrate(eta, a.model.dt, s3, zd0);
-        if (ra.traj && lane < 3)
-            ra.traj[((size_t)inst * ra.n_ticks + tick) * 6 + 2 * lane + axis] = s3[lane];   // x,y,xd,yd,xz,yz
-        ct += 1;
-        if (fsc + 1 <= in.n_timing && j + 1 >= ft[fsc]) {                                  // bang.m:529
-            fsc += 1; cur = pred; store = pred;
-            if (fsc >= 2 && fsc <= in.n_fs) {                                              // bang.m:539-556
-                const double d = pred - plan[(fsc - 1) * 2 + axis];
-                __syncwarp();
-                for (int r = lane; r < in.n_fs; r += 32) plan[r * 2 + axis] += d;
-                first_ramp = 0;
-                __syncwarp();
+    forma_carve(smem_raw + wbytes * warp, C, F, a.R,
+                a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
+    for (;;) {
+        const long long item = forma_next_item(a.queue);
+        if (item >= 2LL * a.n) break;
+        const int inst = (int)(item >> 1), axis = (int)(item & 1);
+        const ismpc_forma_inst_t in = ra.inst_io[inst];
+        double* plan = ra.plan_io + (size_t)in.plan_first_row * 2;
+        const int32_t* ft = a.fs_timing + in.timing_first;
+        const double eta = sqrt(a.model.g_eta / in.height);
+        double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
+        double cur = in.cur_fs[axis], store = in.fs_store[axis];
+        int j = in.j, fsc = in.fs_counter, first_ramp = in.cl_first_ramp, ct = 0, acc = 0;
+        ismpc_push_t pu; pu.fs = -1; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
+        if (ra.push) pu = ra.push[inst];
+        for (int tick = 0; tick < ra.n_ticks; ++tick) {
+            if (fsc == pu.fs && ct >= pu.ct0 && ct < pu.ct1) s3[1] += a.model.dt * (axis == 0 ? pu.ax : pu.ay); // bang.m:104-114
+            int iters; double kkt;
+            acc |= forma_tick_axis(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis, &iters, &kkt);
+            const double zd0 = sm.x[0], pred = sm.x[C];
+            __syncwarp();
+            forma_integrate(eta, a.model.dt, s3, zd0);
+            if (ra.traj && lane < 3)
+                ra.traj[((size_t)inst * ra.n_ticks + tick) * 6 + 2 * lane + axis] = s3[lane];   // x,y,xd,yd,xz,yz
+            ct += 1;
+            if (fsc + 1 <= in.n_timing && j + 1 >= ft[fsc]) {                                  // bang.m:529
+                fsc += 1; cur = pred; store = pred;
+                if (fsc >= 2 && fsc <= in.n_fs) {                                              // bang.m:539-556
+                    const double d = pred - plan[(fsc - 1) * 2 + axis];
+                    __syncwarp();
+                    for (int r = lane; r < in.n_fs; r += 32) plan[r * 2 + axis] += d;
+                    first_ramp = 0;
+                    __syncwarp();
+                }
+                ct = 0;
             }
-            ct = 0;
+            j += 1;
+        }
+        // The other axis' warp reads inst_io[inst] when it picks the item up, possibly after this write: only the
+        // fields of THIS axis are written here, and j / fs_counter / cl_first_ramp (common to both axes) go to
+        // the `next` copy that the epilogue kernel folds back -- see forma_rollout_fold.
+        ismpc_forma_inst_t* io = ra.inst_io + inst;
+        if (lane < 3) io->st[axis * 3 + lane] = s3[lane];
+        if (lane == 0) {
+            io->cur_fs[axis] = cur; io->fs_store[axis] = store;
+            if (ra.status) atomicOr(&ra.status[inst], acc);
+        }
+        __syncwarp();
+    }
+}
+
+// Advance the fields both axes share (j, fs_counter, cl_first_ramp) after every warp of the rollout is done.
+// They evolve identically on both axes and depend only on the timing table, so they are recomputed here.
+__global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_io, const int32_t* fs_timing)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ismpc_forma_inst_t* io = inst_io + i;
+    const int32_t* ft = fs_timing + io->timing_first;
+    int j = io->j, fsc = io->fs_counter, first_ramp = io->cl_first_ramp;
+    for (int tick = 0; tick < n_ticks; ++tick) {
+        if (fsc + 1 <= io->n_timing && j + 1 >= ft[fsc]) {
+            fsc += 1;
+            if (fsc >= 2 && fsc <= io->n_fs) first_ramp = 0;
         }
         j += 1;
     }
-    ismpc_forma_inst_t* io = ra.inst_io + inst;
-    if (lane < 3) io->st[axis * 3 + lane] = s3[lane];
-    if (lane == 0) {
-        io->cur_fs[axis] = cur; io->fs_store[axis] = store;
-        if (axis == 0) { io->j = j; io->fs_counter = fsc; io->cl_first_ramp = first_ramp; }
-        if (ra.status) atomicOr(&ra.status[inst], acc);
-    }
+    io->j = j; io->fs_counter = fsc; io->cl_first_ramp = first_ramp;
 }
 
-static int forma_configure(FormAArgs& a, size_t* smem_out, int* grid_out, bool rollout)
+static int env_int(const char* name, int dflt)
 {
-    const int C = a.model.C, F = a.model.F;
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Shared-memory / residency plan for a model: R rows of the inverse factor in shared memory, the rest spilled.
+void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p)
+{
+    const int C = m.C, F = m.F, q = C + F + 1;
     const size_t lim = 227 * 1024;
-    size_t per_in = forma_warp_smem_bytes(C, F, true);
-    if (per_in <= lim) {
-        a.L_in_smem = 1;
-        int wpc = (int)(lim / per_in);
-        if (wpc > 2) wpc = 2;          // two warps (x and y of one instance) per CTA keeps CTAs small and numerous
-        a.warps_per_cta = wpc;
-        *smem_out = per_in * wpc;
-    } else {
-        a.L_in_smem = 0;
-        a.warps_per_cta = 2;
-        *smem_out = forma_warp_smem_bytes(C, F, false) * 2;
-    }
-    const long long items = 2LL * a.n;
-    *grid_out = (int)((items + a.warps_per_cta - 1) / a.warps_per_cta);
-    cudaError_t e = rollout
-        ? cudaFuncSetAttribute(forma_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem_out)
-        : cudaFuncSetAttribute(forma_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem_out);
-    return (int)e;
+    int R = env_int("ISMPC_FORMA_R", 48);
+    if (R > q) R = q;
+    if (R < 1) R = 1;
+    int wpc = env_int("ISMPC_FORMA_WPC", 4);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 16) wpc = 16;
+    while (wpc > 1 && forma_warp_smem_bytes(C, F, R) * wpc > lim) --wpc;
+    while (R > 1 && forma_warp_smem_bytes(C, F, R) * wpc > lim) --R;
+    p->R = R; p->warps_per_cta = wpc;
+    p->smem = forma_warp_smem_bytes(C, F, R) * wpc;
+    int per_sm = (int)((lim + 1024) / (p->smem + 1024));      // 1 KB per-CTA reservation
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * wpc > 48) per_sm = 48 / wpc > 0 ? 48 / wpc : 1;
+    long long ctas = (items + wpc - 1) / wpc;
+    long long resident = (long long)per_sm * sm_count;
+    p->grid = (int)(ctas < resident ? ctas : resident);
+    if (p->grid < 1) p->grid = 1;
+    p->spill_doubles = forma_spill_doubles(C, F, R) * (size_t)p->grid * wpc;
 }
 
-size_t forma_Lwork_doubles(const ismpc_forma_model_t& m, int n)
-{
-    if (forma_warp_smem_bytes(m.C, m.F, true) <= (size_t)227 * 1024) return 0;
-    return (size_t)2 * n * forma_L_doubles(m.C, m.F);
-}
-
-int forma_tick_launch(const FormAArgs& a_in, cudaStream_t st)
+int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStream_t st)
 {
     FormAArgs a = a_in;
-    size_t smem; int grid;
-    int rc = forma_configure(a, &smem, &grid, false);
-    if (rc) return rc;
+    a.R = p.R; a.warps_per_cta = p.warps_per_cta;
+    cudaError_t e = cudaFuncSetAttribute(forma_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     cudaMemsetAsync(a.out, 0, (size_t)a.n * sizeof(ismpc_forma_out_t), st);
-    forma_tick_kernel<<<grid, 32 * a.warps_per_cta, smem, st>>>(a);
+    forma_tick_kernel<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
-int forma_rollout_launch(const FormAArgs& a_in, ismpc_forma_inst_t* inst_io, double* fs_plan_io,
-                         const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, cudaStream_t st)
+int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_forma_inst_t* inst_io,
+                         double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status,
+                         cudaStream_t st)
 {
     FormAArgs a = a_in;
-    size_t smem; int grid;
-    int rc = forma_configure(a, &smem, &grid, true);
-    if (rc) return rc;
+    a.R = p.R; a.warps_per_cta = p.warps_per_cta;
+    cudaError_t e = cudaFuncSetAttribute(forma_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
     FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, status};
-    forma_rollout_kernel<<<grid, 32 * a.warps_per_cta, smem, st>>>(ra);
+    forma_rollout_kernel<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
+    forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing);
     return (int)cudaGetLastError();
 }
 

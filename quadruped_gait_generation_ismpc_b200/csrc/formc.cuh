@@ -56,7 +56,8 @@ __device__ inline void formc_carve(unsigned char* base, int N, FormCShared& s)
     s.lam = d; d += N; s.chv = d; d += N; s.shs = d; d += N; s.ssh = d; d += N;
     s.avec = d; d += N; s.dl = d; d += N;
     s.red = d; d += 16;
-    s.das.L = d; d += (FORMC_QMAX * (FORMC_QMAX + 1)) / 2;
+    s.das.Js = d; d += (FORMC_QMAX * (FORMC_QMAX + 1)) / 2;
+    s.das.Jg = nullptr; s.das.R = FORMC_QMAX;
     s.das.mu = d; d += FORMC_QMAX; s.das.r = d; d += FORMC_QMAX; s.das.y = d; d += FORMC_QMAX;
     s.das.wid = reinterpret_cast<int*>(d);
     s.das.wsg = reinterpret_cast<signed char*>(s.das.wid + FORMC_QMAX);
@@ -89,6 +90,7 @@ struct VertProb {
     __device__ int nvar() const { return N; }
     __device__ double lo(int) const { return 0.0; }
     __device__ double hi(int) const { return fzmax; }
+    __device__ void on_step(double) const {}
     // rv_k = (S_bar_z x)_k = c1 * sum_{j<k} (k-j) x_j  -> two prefix sums
     __device__ void eval(const double* x, double* rv) const
     {
@@ -182,7 +184,6 @@ struct FormCArgs {
 
 // Debug-only phase timing (make dbg -> lib/libismpc_b200_dbg.so; never in the product library).
 #ifdef ISMPC_PHASE_TIMING
-extern __device__ long long g_phase[64];
 #define ISMPC_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase[k] = clock64(); } while (0)
 #else
 #define ISMPC_PHASE(k) do { } while (0)
@@ -308,7 +309,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     //   f = x0 - H^-1[:,K] mu,  (H^-1)_KK mu = x0_K   with K = [c_lo, c_lo+ne) a contiguous column range
     const bool fast_eq = (ne > 0 && ne <= 32);
     if (fast_eq) {
-        double* Sk = sm.das.L;                                       // ne x ne, row-major (fits: 32*32 <= packed qmax)
+        double* Sk = sm.das.Js;                                      // ne x ne, row-major (fits: 32*32 <= packed qmax)
         for (int e = tid; e < ne * ne; e += FORMC_THREADS) {
             int r = e / ne, c = e - r * ne;
             Sk[e] = __ldg(T.Hinv + (size_t)(c_lo + r) * N + c_lo + c);

@@ -55,7 +55,10 @@ else:
                                 out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
         e1.record(); e1.synchronize()
         o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
-        print("forma tick n=%d: %.1f us, mean iters %.1f, failed %d" % (n, e0.elapsed_time(e1) * 1e3, o["iters"].mean(), (o["status"] != 0).sum()))
+        it = np.sort(o["iters"])
+        print("forma tick n=%d: %.1f us, iters mean %.1f p50 %d p90 %d p99 %d max %d, failed %d"
+              % (n, e0.elapsed_time(e1) * 1e3, it.mean(), it[len(it) // 2], it[int(len(it) * 0.9)], it[int(len(it) * 0.99)],
+                 it[-1], (o["status"] != 0).sum()))
 
 if os.environ.get("ISMPC_DBG"):
     import ctypes as C
@@ -63,3 +66,9 @@ if os.environ.get("ISMPC_DBG"):
     binding.lib().ismpc_debug_read_phases(ph)
     v = list(ph)[:24]
     print("phase clocks (CTA 0, deltas in cycles):", [v[i + 1] - v[i] for i in range(len(v) - 1) if v[i + 1] and v[i]])
+    names = ["eval", "viol_scan", "schur_col", "apply_J", "apply_Jt", "ratio", "step_dir", "x_mu_update", "append", "drop"]
+    acc = list(ph)[32:32 + len(names)]
+    tot = float(sum(acc)) or 1.0
+    print("das sections (cycles summed over all warps and launches):")
+    for nm, a in zip(names, acc):
+        print("  %-12s %14d  %5.1f%%" % (nm, a, 100.0 * a / tot))
