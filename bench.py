@@ -348,7 +348,7 @@ def bench_form_a(h, torch, dev, n, stream, steps=20):
     ms = statistics.median(times)
     return {"workload": "formA_tick_trot_1024xC100F3_midgait_cold", "qp_solves_per_s": n / (ms * 1e-3),
             "ms_per_tick": ms, "mean_iters_per_qp": float(out["iters"].mean()), "max_iters": int(out["iters"].max()),
-            "failed": int((out["status"] != 0).sum()), "note": "1 QP per instance-tick (x and y stacked, nV=206, nC=208)"}
+            "failed": int((out["status"] & abi.ST_FAIL_MASK != 0).sum()), "gi_fallback": int((out["status"] & abi.ST_GI_FALLBACK != 0).sum()), "note": "1 QP per instance-tick (x and y stacked, nV=206, nC=208)"}
 
 
 if __name__ == "__main__":

@@ -57,7 +57,9 @@ enum {
     ISMPC_ST_WINDOW = 8,        /* k0+2N exceeds the midpoint sequence: instance left untouched */
     ISMPC_ST_XY_SKIPPED = 16,   /* lambda_0 <= 2: horizontal QPs skipped, u = 0 (MPCSolver.cpp:322) */
     ISMPC_ST_NAN_GUARD = 32,    /* vertical state was NaN and was patched (MPCSolver.cpp:277-278) */
-    ISMPC_ST_QP_FAIL = 64       /* form A / generic QP infeasible or iteration cap */
+    ISMPC_ST_QP_FAIL = 64,      /* form A / generic QP infeasible or iteration cap */
+    ISMPC_ST_GI_FALLBACK = 128  /* informational (form A): the structured primal-dual active-set solve did not settle;
+                                   the result comes from the dual active-set fallback and is equally exact */
 };
 
 #define ISMPC_MAX_N 512          /* largest horizon / variable count per axis supported by the kernels */

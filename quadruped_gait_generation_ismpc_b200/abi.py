@@ -40,6 +40,8 @@ DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": F
 
 # status bits
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
+ST_GI_FALLBACK = 128    # informational: form-A result came from the dual active-set fallback
+ST_FAIL_MASK = ST_Z_FAIL | ST_X_FAIL | ST_Y_FAIL | ST_WINDOW | ST_QP_FAIL
 MEM_HOST, MEM_DEVICE = 0, 1
 
 

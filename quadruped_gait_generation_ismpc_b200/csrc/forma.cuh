@@ -35,6 +35,8 @@ struct FormAArgs {
     int R;                 // rows of the inverse factor kept in shared memory (das.cuh)
     double* Jspill;        // global slices for rows >= R: one per resident warp (grid * warps_per_cta)
     int* queue;            // work queue head (items = (instance, axis) pairs), zeroed before the launch
+    int use_pdas;          // structured primal-dual active-set fast path enabled
+    int warm_start;        // rollout: start each tick from the previous tick's working set shifted by one
 };
 
 struct FormAShared {   // per-warp slices
@@ -60,6 +62,8 @@ __host__ __device__ inline size_t forma_warp_smem_bytes(int C, int F, int R)
 {
     return (forma_vec_doubles(C, F) + (size_t)tri(R, 0)) * sizeof(double) + forma_byte_tail(C, F);
 }
+
+__host__ __device__ inline size_t forma_cta_smem_header(int C) { return (((size_t)C + 1) * sizeof(double) + 15) & ~(size_t)15; }
 
 __device__ inline void forma_carve(unsigned char* base, int C, int F, int R, double* J_global, FormAShared& s)
 {
@@ -187,13 +191,318 @@ struct FormAProb {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Structured primal-dual active-set solve (the fast path of bang.m:256 `quadprog`).
+//
+// With p_i = dt*cumsum(zd)_i the Hessian of the ZMP block is tridiagonal, so for a GIVEN working set W the
+// equality-constrained optimum is closed form: between consecutive active ZMP rows kp < k the suffix sum of the
+// multipliers is a constant c, zd_j = (nu a_j + c)/Qz, and row k minus row kp gives
+//     c = [ (Qz/dt)(beta_k - beta_kp + (m_k - m_kp).xf) - nu (PA_k - PA_kp) ] / (k - kp),
+// affine in u = (nu, xf).  Substituting into the stability row and the footstep stationarity leaves a symmetric
+// (1 + F + #active kinematic rows)-dimensional system K u = rhs whose entries are 2 + 2F + F(F+1)/2 sums over the
+// active rows -- O(C/32) per lane instead of an O(q^2) factor update.  Multipliers follow from
+// y_k = (c_seg(k) - c_seg(k+1))/dt.  The working set is then re-guessed wholesale (primal-dual active set /
+// semismooth Newton: inactive rows that are violated enter, active rows whose multiplier has the wrong sign
+// leave) until it is stable; a stable set satisfies the KKT conditions exactly, and the QP is strictly convex,
+// so the result is THE minimiser -- the same point qpOASES' homotopy reaches.  The method has no global
+// convergence guarantee: on an iteration cap or a singular K the caller falls back to the dual active set
+// (das.cuh), which has one.  All positions are shifted by `shift` (the current footstep) so that the sums do
+// not cancel catastrophically far from the origin.
+// Returns 0 converged, 1 iteration cap, 2 singular system.  On 0: sm.x holds [zd; xf], sm.rv the row values,
+// sm.das.state the working set.
+// ---------------------------------------------------------------------------------------------------------
+// Sum every entry of acc over the warp; every lane ends up with every total.  Butterfly with a halving payload
+// (16 + 8 + 4 + 2 + 1 exchanges for up to 16 values instead of 5 per value), then a broadcast through `scratch`.
+template <int NS>
+__device__ __forceinline__ void warp_sum_multi16(double (&acc)[NS], double* scratch)
+{
+    static_assert(NS <= 16, "payload is padded to 16");
+    const int lane = lane_id();
+    double v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = e < NS ? acc[e] : 0.0;
+#pragma unroll
+    for (int half = 8, o = 16; half >= 1; half >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double mine = up ? v[half + k] : v[k];
+            const double theirs = up ? v[k] : v[half + k];
+            v[k] = mine + __shfl_xor_sync(ISMPC_FULL_MASK, theirs, o);
+        }
+    }
+    v[0] += __shfl_xor_sync(ISMPC_FULL_MASK, v[0], 1);
+    // lane L now holds the total of entry ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)
+    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    __syncwarp();
+    if ((lane & 1) == 0) scratch[idx] = v[0];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < NS; ++e) acc[e] = scratch[e];
+    __syncwarp();
+}
+
+// Generic (any F, any number of active kinematic rows) small dense solve: Gauss-Jordan with partial pivoting by
+// the warp on the augmented matrix K (dim x (dim+1), row-major) in shared memory.  Returns false if singular.
+__device__ inline bool warp_gauss_jordan(double* K, int dim)
+{
+    const int lane = lane_id();
+    const int LD = dim + 1;
+    for (int p = 0; p < dim; ++p) {
+        double v = 1.0; int pr = 0x7fffffff;
+        if (p + lane < dim) { v = -fabs(K[(p + lane) * LD + p]); pr = p + lane; }
+        warp_argmin(v, pr);
+        if (!(-v > 1e-200)) return false;
+        if (pr != p) for (int c = p + lane; c <= dim; c += 32) { const double t = K[p * LD + c]; K[p * LD + c] = K[pr * LD + c]; K[pr * LD + c] = t; }
+        __syncwarp();
+        const double pinv = 1.0 / K[p * LD + p];
+        const int ncol = dim - p;
+        for (int e = lane; e < (dim - 1) * ncol; e += 32) {
+            int r = e / ncol; const int c = p + 1 + (e - r * ncol);
+            if (r >= p) ++r;
+            K[r * LD + c] -= K[r * LD + p] * pinv * K[p * LD + c];
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// On entry sm.lo / sm.hi hold the bounds in SHIFTED coordinates (ZMP rows: + shift*sum_f m_if; first kinematic
+// row: - shift), planf the footstep targets minus shift; sm.das.state the starting working set.
+// rg[g] = 1/g for g = 1..C.  On return 0: sm.x = [zd; xf] (xf absolute), sm.rv row values (shifted),
+// sm.das.state the optimal working set.
+template <int FT>
+__device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
+                                 const double* planf, const double* rg, int maxit, int* iters_out)
+{
+    constexpr int NS = 2 + 2 * FT + FT * (FT + 1) / 2;
+    const int lane = lane_id();
+    const int C = pb.C, F = pb.F;
+    const double dt = pb.dt, inv_dt = 1.0 / dt, Qz = 1.0 / pb.qz_inv, Qf = 1.0 / pb.qf_inv;
+    const double qz_dt = Qz * inv_dt, qz_dt2 = qz_dt * inv_dt, dt_qz = dt * pb.qz_inv;
+    signed char* st = sm.das.state;          // [C+F] working set (-1 lower, +1 upper)
+    int* nxt = sm.das.wid;                   // [C] scratch: first active row >= i, then the staged new state
+    double* cseg = pb.scr;                   // [C]
+    double* K = sm.das.Js;                   // scratch: reduction broadcast / augmented system of the generic solve
+    int r0, r1; lane_chunk(C, lane, r0, r1);
+    auto beta = [&](int k) -> double { return st[k] < 0 ? pb.lo_[k] : pb.hi_[k]; };
+    double pl[FT];
+#pragma unroll
+    for (int f = 0; f < FT; ++f) pl[f] = f < F ? planf[f] : 0.0;
+    int it = 0, rc = 1;
+    for (; it < maxit; ++it) {
+        // ---- predecessor / successor active rows of this lane's chunk (ballot + one shuffle each) ----
+        int la = -1, fa = C, nk = 0;
+        for (int i = r0; i < r1; ++i) if (st[i]) { la = i; if (fa == C) fa = i; }
+        for (int f = 0; f < F; ++f) nk += st[C + f] != 0;
+        const unsigned has = __ballot_sync(ISMPC_FULL_MASK, la >= 0);
+        const unsigned below = has & ((1u << lane) - 1u);
+        const unsigned above = lane == 31 ? 0u : has & ~((2u << lane) - 1u);
+        const int src_p = below ? 31 - __clz(below) : 0, src_n = above ? __ffs(above) - 1 : 0;
+        const int kp_t = __shfl_sync(ISMPC_FULL_MASK, la, src_p), kn_t = __shfl_sync(ISMPC_FULL_MASK, fa, src_n);
+        const int kp0 = below ? kp_t : -1, kn0 = above ? kn_t : C;
+        // ---- pass A: sums over the active rows ----
+        double acc[NS];
+#pragma unroll
+        for (int e = 0; e < NS; ++e) acc[e] = 0.0;
+        {
+            int kp = kp0;
+            double bp = 0.0, PAp = 0.0, mpv[FT];
+#pragma unroll
+            for (int f = 0; f < FT; ++f) mpv[f] = 0.0;
+            if (kp >= 0) {
+                bp = beta(kp); PAp = pb.PA[kp];
+#pragma unroll
+                for (int f = 0; f < FT; ++f) mpv[f] = f < F ? pb.mcoef(kp, f) : 0.0;
+            }
+            for (int i = r0; i < r1; ++i) {
+                if (!st[i]) continue;
+                const double bk = beta(i), PAk = pb.PA[i];
+                const double w = rg[i - kp], d = PAk - PAp, b = bk - bp;
+                const double wd = w * d;
+                double e[FT];
+#pragma unroll
+                for (int f = 0; f < FT; ++f) { const double mk = f < F ? pb.mcoef(i, f) : 0.0; e[f] = mk - mpv[f]; mpv[f] = mk; }
+                acc[0] += wd * d; acc[1] += wd * b;
+                int idx = 2 + 2 * FT;
+#pragma unroll
+                for (int f = 0; f < FT; ++f) {
+                    const double we = w * e[f];
+                    acc[2 + f] += d * we; acc[2 + FT + f] += we * b;
+#pragma unroll
+                    for (int g = 0; g <= f; ++g) { acc[idx] += we * e[g]; ++idx; }
+                }
+                kp = i; bp = bk; PAp = PAk;
+            }
+        }
+        double nu, xf[FT], kap = 0.0;
+        bool fast = false;
+        if constexpr (FT <= 3) fast = nk == 0;
+        if constexpr (FT <= 3) if (fast) {
+            // ---- common case: 4 x 4 saddle system solved in registers by every lane (no kinematic row active) ----
+            warp_sum_multi16<NS>(acc, K);
+            const double k00 = -(pb.saa - acc[0]) * pb.qz_inv, rr0 = -beq + acc[1] * inv_dt;
+            double v[3], rf[3], M[3][3];
+            int idx = 2 + 2 * FT;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                v[f] = f < FT ? -acc[2 + (f < FT ? f : 0)] * inv_dt : 0.0;
+                rf[f] = f < FT ? Qf * pl[f < FT ? f : 0] - qz_dt2 * acc[2 + FT + (f < FT ? f : 0)] : 0.0;
+#pragma unroll
+                for (int g = 0; g <= f; ++g) {
+                    double m = f == g ? Qf : 0.0;
+                    if (f < FT) { m += qz_dt2 * acc[idx < NS ? idx : 0]; ++idx; }
+                    M[f][g] = m; M[g][f] = m;
+                }
+            }
+            // M = L D L'
+            const double d0 = M[0][0], i0 = 1.0 / d0;
+            const double l10 = M[1][0] * i0, l20 = M[2][0] * i0;
+            const double d1 = M[1][1] - l10 * l10 * d0, i1 = 1.0 / d1;
+            const double l21 = (M[2][1] - l20 * l10 * d0) * i1;
+            const double d2 = M[2][2] - l20 * l20 * d0 - l21 * l21 * d1, i2 = 1.0 / d2;
+            auto msolve = [&](const double (&b)[3], double (&z)[3]) {
+                const double y0 = b[0], y1 = b[1] - l10 * y0, y2 = b[2] - l20 * y0 - l21 * y1;
+                z[2] = y2 * i2; z[1] = y1 * i1 - l21 * z[2]; z[0] = y0 * i0 - l10 * z[1] - l20 * z[2];
+            };
+            double zr[3], zv[3];
+            msolve(rf, zr); msolve(v, zv);
+            const double S = k00 - (v[0] * zv[0] + v[1] * zv[1] + v[2] * zv[2]);
+            if (!(d0 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0) || !(fabs(S) > 1e-200)) { rc = 2; break; }
+            nu = (rr0 - (v[0] * zr[0] + v[1] * zr[1] + v[2] * zr[2])) / S;
+#pragma unroll
+            for (int f = 0; f < FT; ++f) xf[f] = f < 3 ? zr[f < 3 ? f : 0] - zv[f < 3 ? f : 0] * nu : 0.0;
+        }
+        if (!fast) {
+            // ---- general case: K u = rhs, u = (nu, xf', kappa_active), Gauss-Jordan in shared memory ----
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int e = 0; e < NS; ++e) acc[e] += __shfl_xor_sync(ISMPC_FULL_MASK, acc[e], o);
+            }
+            const int dim = 1 + F + nk, LD = dim + 1;
+            if (lane == 0) {
+                for (int e = 0; e < dim * LD; ++e) K[e] = 0.0;
+                K[0] = -(pb.saa - acc[0]) * pb.qz_inv;
+                K[dim] = -beq + acc[1] * inv_dt;
+                int idx = 2 + 2 * FT;
+#pragma unroll
+                for (int f = 0; f < FT; ++f) {
+                    if (f < F) {
+                        K[1 + f] = -acc[2 + f] * inv_dt; K[(1 + f) * LD] = -acc[2 + f] * inv_dt;
+                        K[(1 + f) * LD + dim] = Qf * pl[f] - qz_dt2 * acc[2 + FT + f];
+                    }
+#pragma unroll
+                    for (int g = 0; g <= f; ++g) {
+                        if (f < F) {
+                            const double m = qz_dt2 * acc[idx] + (f == g ? Qf : 0.0);
+                            K[(1 + f) * LD + 1 + g] = m; K[(1 + g) * LD + 1 + f] = m;
+                        }
+                        ++idx;
+                    }
+                }
+                int col = 1 + F;
+                for (int f = 0; f < F; ++f) {
+                    if (!st[C + f]) continue;
+                    K[(1 + f) * LD + col] -= 1.0; K[col * LD + 1 + f] -= 1.0;
+                    if (f > 0) { K[f * LD + col] += 1.0; K[col * LD + f] += 1.0; }
+                    K[col * LD + dim] = -(st[C + f] < 0 ? pb.lo_[C + f] : pb.hi_[C + f]);
+                    ++col;
+                }
+            }
+            __syncwarp();
+            if (!warp_gauss_jordan(K, dim)) { rc = 2; break; }
+            nu = K[dim] / K[0];
+#pragma unroll
+            for (int f = 0; f < FT; ++f) xf[f] = f < F ? K[(1 + f) * LD + dim] / K[(1 + f) * LD + 1 + f] : 0.0;
+            int col = 1 + F;
+            for (int f = 0; f < F; ++f) if (st[C + f]) { if (f == lane) kap = K[col * LD + dim] / K[col * LD + col]; ++col; }
+            __syncwarp();
+        }
+        auto mx = [&](int i) -> double {                     // m_i . xf'
+            const int p = pb.mp[i]; const double w = pb.mw[i];
+            double s = 0.0;
+#pragma unroll
+            for (int f = 0; f < FT; ++f) s += ((p == f + 1 ? w : 0.0) + (p == f ? 1.0 - w : 0.0)) * xf[f];
+            return s;
+        };
+        // ---- pass B: successor rows, segment constants, zd, row values ----
+        { int kn = kn0; for (int i = r1 - 1; i >= r0; --i) { if (st[i]) kn = i; nxt[i] = kn; } }
+        {
+            int kp = kp0;
+            double bp = 0.0, PAp = 0.0, mxp = 0.0;
+            if (kp >= 0) { bp = beta(kp); PAp = pb.PA[kp]; mxp = mx(kp); }
+            int kn_c = -1; double c = 0.0;
+            for (int i = r0; i < r1; ++i) {
+                const int kn = nxt[i];
+                if (kn != kn_c) {
+                    kn_c = kn;
+                    c = kn < C ? (qz_dt * ((beta(kn) - bp) + (mx(kn) - mxp)) - nu * (pb.PA[kn] - PAp)) * rg[kn - kp] : 0.0;
+                }
+                cseg[i] = c;
+                sm.x[i] = (nu * pb.a[i] + c) * pb.qz_inv;
+                if (st[i]) {
+                    bp = beta(i); PAp = pb.PA[i]; mxp = mx(i); kp = i;
+                    sm.rv[i] = bp;
+                    kn_c = -1;                                // the next row starts a new segment
+                } else {
+                    sm.rv[i] = bp + dt_qz * (nu * (pb.PA[i] - PAp) + c * (double)(i - kp)) - (mx(i) - mxp);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- re-guess the working set ----
+        int changed = 0;
+        for (int i = r0; i < r1; ++i) {
+            const int s0 = st[i];
+            int s1 = 0;
+            if (s0 == 0) {
+                const double lo = pb.lo_[i], hi = pb.hi_[i], r = sm.rv[i];
+                if (lo - r > 1e-10 * (1.0 + fabs(lo))) s1 = -1;
+                else if (r - hi > 1e-10 * (1.0 + fabs(hi))) s1 = +1;
+            } else {
+                const double y = cseg[i] - (i + 1 < C ? cseg[i + 1] : 0.0);     // dt * multiplier
+                if (s0 < 0 ? y > 0.0 : y < 0.0) s1 = s0;
+            }
+            changed |= s1 != s0;
+            nxt[i] = s1;                                      // staged: cseg[i+1] of a neighbour lane may still be read
+        }
+        if (lane < F) {
+            const int f = lane, s0 = st[C + f];
+            double xm1 = 0.0, xme = 0.0;
+#pragma unroll
+            for (int g = 0; g < FT; ++g) { if (g == f - 1) xm1 = xf[g]; if (g == f) xme = xf[g]; }
+            const double r = xme - xm1;
+            const double lo = pb.lo_[C + f], hi = pb.hi_[C + f];
+            int s1 = 0;
+            if (s0 == 0) {
+                if (lo - r > 1e-10 * (1.0 + fabs(lo))) s1 = -1;
+                else if (r - hi > 1e-10 * (1.0 + fabs(hi))) s1 = +1;
+            } else if (s0 < 0 ? kap > 0.0 : kap < 0.0) s1 = s0;
+            changed |= s1 != s0;
+            sm.rv[C + f] = r;
+            sm.x[C + f] = xme + shift;
+            st[C + f] = (signed char)s1;
+        }
+        __syncwarp();
+        for (int i = r0; i < r1; ++i) st[i] = (signed char)nxt[i];
+        changed = __any_sync(ISMPC_FULL_MASK, changed);
+        __syncwarp();
+        if (!changed) { rc = 0; ++it; break; }
+    }
+    *iters_out = it;
+    return rc;
+}
+
 // One tick for one (instance, axis) by one warp.  Returns status bits; writes x (primal) in sm.x.
 // in: the instance (by reference; read only), plan: this instance's fs_plan rows, ft: its fs_timing.
+// warm != 0: sm.das.state holds a working-set guess (previous tick's set shifted by one tick).
+template <int FT>
 __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_model_t& mdl,
                                       const ismpc_forma_inst_t& in, const double* st3 /*x,xd,xz of this axis*/,
                                       double cur, double fs_store, int j, int fs_counter, int first_ramp,
-                                      const double* plan, const int32_t* ft, int axis,
-                                      int* iters_out, double* kkt_out)
+                                      const double* plan, const int32_t* ft, int axis, int warm, int use_pdas,
+                                      const double* rg, int* iters_out, double* kkt_out)
 {
     const int lane = lane_id();
     const int C = mdl.C, P = mdl.P, F = mdl.F, n = C + F;
@@ -247,34 +556,91 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     ant = warp_sum(ant);
     ant += exp(-eta * dt * (double)P) * (forma_centerline(plan, n_fs, axis, step, ds, first_ramp, P) - fs_store);
     const double beq = st3[0] + st3[1] / eta - st3[2] - ant;       // bang.m:209-210
-    // ---- unconstrained minimiser: zd = 0, xf = plan(fsCounter+1 .. fsCounter+F) (bang.m:244-245) ----
-    for (int i = lane; i < C; i += 32) sm.x[i] = 0.0;
+    // ---- footstep targets plan(fsCounter+1 .. fsCounter+F) (bang.m:244-245), kept in the tail of sm.z ----
     for (int f = lane; f < F; f += 32) {
         int row = fs_counter + 1 + f; if (row > n_fs) row = n_fs;
-        sm.x[C + f] = plan[(row - 1) * 2 + axis];
+        sm.z[C + f] = plan[(row - 1) * 2 + axis];
     }
-    for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+    if (!warm) for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
     __syncwarp();
     FormAProb pb{C, F, dt, 1.0 / mdl.q_zdot, 1.0 / mdl.q_foot, saa, sm.a, sm.PA, sm.mw, sm.lo, sm.hi, sm.mp, sm.scr};
-    DasWork w = sm.das;
-    w.q = 0; w.neq = 0;
-    int status = 0;
-    int rc = das_add_equality(pb, w, sm.x, sm.z, n, 0.0, beq);
-    if (rc < 0) status |= ISMPC_ST_QP_FAIL;
-    w.neq = w.q;
-    int iters = 0;
-    rc = das_solve(pb, w, sm.x, sm.rv, sm.z, 6 * n + 50, &iters);
-    if (rc != 0) status |= ISMPC_ST_QP_FAIL;
-    // self-check: equality residual and worst bound violation
-    double eqv = 0.0;
-    for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
-    eqv = warp_sum(eqv);
-    double viol = 0.0;
-    for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
-    viol = warp_max(viol);
+    int status = 0, iters = 0;
+    bool solved = false;
+    double eqv = 0.0, viol = 0.0;
+    if (use_pdas) {
+        // shifted coordinates: positions relative to the current footstep (see forma_pdas)
+        for (int i = lane; i < C; i += 32) {
+            const int p = sm.mp[i]; const double w = sm.mw[i];
+            const double ms = cur * ((p >= 1 ? w : 0.0) + (p + 1 <= F ? 1.0 - w : 0.0));
+            sm.lo[i] += ms; sm.hi[i] += ms;
+        }
+        if (lane == 0) { sm.lo[C] -= cur; sm.hi[C] -= cur; }
+        for (int f = lane; f < F; f += 32) sm.z[f] = sm.z[C + f] - cur;
+        __syncwarp();
+        int rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, 48, &iters);
+        if (rc != 0 && warm) {                                      // a stale guess can stall: retry from the empty set
+            for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+            __syncwarp();
+            int it2 = 0;
+            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, 48, &it2);
+            iters += it2;
+        }
+        if (rc == 0) {
+            for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
+            eqv = warp_sum(eqv);
+            for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
+            viol = warp_max(viol);
+            solved = fabs(eqv - beq) <= 1e-8 * fmax(1.0, fabs(beq)) && viol <= 1e-8;
+        }
+        if (!solved) {                                              // back to absolute coordinates for the fallback
+            __syncwarp();
+            for (int i = lane; i < C; i += 32) {
+                const int p = sm.mp[i]; const double w = sm.mw[i];
+                const double ms = cur * ((p >= 1 ? w : 0.0) + (p + 1 <= F ? 1.0 - w : 0.0));
+                sm.lo[i] -= ms; sm.hi[i] -= ms;
+            }
+            if (lane == 0) { sm.lo[C] += cur; sm.hi[C] += cur; }
+            __syncwarp();
+        }
+    }
+    if (!solved) {
+        // ---- fallback: dual active set from the unconstrained minimiser zd = 0, xf = plan ----
+        for (int i = lane; i < C; i += 32) sm.x[i] = 0.0;
+        for (int f = lane; f < F; f += 32) sm.x[C + f] = sm.z[C + f];
+        for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+        __syncwarp();
+        if (use_pdas) status |= ISMPC_ST_GI_FALLBACK;
+        DasWork w = sm.das;
+        w.q = 0; w.neq = 0;
+        int rc = das_add_equality(pb, w, sm.x, sm.z, n, 0.0, beq);
+        if (rc < 0) status |= ISMPC_ST_QP_FAIL;
+        w.neq = w.q;
+        int it2 = 0;
+        rc = das_solve(pb, w, sm.x, sm.rv, sm.z, 6 * n + 50, &it2);
+        iters += it2;
+        if (rc != 0) status |= ISMPC_ST_QP_FAIL;
+        // self-check: equality residual and worst bound violation
+        eqv = 0.0; viol = 0.0;
+        for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
+        eqv = warp_sum(eqv);
+        for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
+        viol = warp_max(viol);
+    }
     *iters_out = iters;
     *kkt_out = fmax(fabs(eqv - beq), fmax(viol, 0.0));
     return status;
+}
+
+// Warm start for the next tick of a closed loop: ZMP row i of the next QP is row i+1 of this one.
+__device__ inline void forma_shift_working_set(signed char* st, int C, int F, bool reset_kin)
+{
+    const int lane = lane_id();
+    int r0, r1; lane_chunk(C, lane, r0, r1);
+    const signed char nb = (r1 < C) ? st[r1] : (signed char)0;
+    __syncwarp();
+    for (int i = r0; i < r1; ++i) st[i] = (i + 1 < r1) ? st[i + 1] : nb;
+    if (reset_kin && lane < F) st[C + lane] = 0;
+    __syncwarp();
 }
 
 // bang.m:55-58,265-290: [c; cd; z]+ = A_upd [c; cd; z] + B_upd * zd(1)

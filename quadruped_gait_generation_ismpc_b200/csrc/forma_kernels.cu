@@ -9,6 +9,8 @@
 
 namespace ismpc {
 
+constexpr int FORMA_MAX_THREADS = 128;   // 4 warps = 4 (instance, axis) items in flight per CTA
+
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
 {
     // non-negative doubles order like their bit patterns
@@ -22,15 +24,19 @@ __device__ __forceinline__ long long forma_next_item(int* queue)
     return (long long)__shfl_sync(ISMPC_FULL_MASK, v, 0);
 }
 
-__global__ void forma_tick_kernel(FormAArgs a)
+template <int FT>
+__global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick_kernel(FormAArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = warp_id(), lane = lane_id();
     const int C = a.model.C, F = a.model.F, n = C + F;
     const size_t wbytes = forma_warp_smem_bytes(C, F, a.R);
     const size_t slot = (size_t)blockIdx.x * a.warps_per_cta + warp;
+    double* rg = reinterpret_cast<double*>(smem_raw);             // rg[g] = 1/g, shared by the CTA's warps
+    for (int g = threadIdx.x; g <= C; g += blockDim.x) rg[g] = g ? 1.0 / (double)g : 0.0;
+    __syncthreads();
     FormAShared sm;
-    forma_carve(smem_raw + wbytes * warp, C, F, a.R,
+    forma_carve(smem_raw + forma_cta_smem_header(C) + wbytes * warp, C, F, a.R,
                 a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
     for (;;) {
         const long long item = forma_next_item(a.queue);
@@ -41,8 +47,8 @@ __global__ void forma_tick_kernel(FormAArgs a)
         const int32_t* ft = a.fs_timing + in.timing_first;
         double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
         int iters; double kkt;
-        int status = forma_tick_axis(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
-                                     in.cl_first_ramp, plan, ft, axis, &iters, &kkt);
+        int status = forma_tick_axis<FT>(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
+                                         in.cl_first_ramp, plan, ft, axis, 0, a.use_pdas, rg, &iters, &kkt);
         const double eta = sqrt(a.model.g_eta / in.height);
         const double zd0 = sm.x[0];
         forma_integrate(eta, a.model.dt, s3, zd0);
@@ -74,7 +80,8 @@ struct FormARolloutArgs {
     int32_t* status;
 };
 
-__global__ void forma_rollout_kernel(FormARolloutArgs ra)
+template <int FT>
+__global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_rollout_kernel(FormARolloutArgs ra)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FormAArgs& a = ra.base;
@@ -82,8 +89,11 @@ __global__ void forma_rollout_kernel(FormARolloutArgs ra)
     const int C = a.model.C, F = a.model.F;
     const size_t wbytes = forma_warp_smem_bytes(C, F, a.R);
     const size_t slot = (size_t)blockIdx.x * a.warps_per_cta + warp;
+    double* rg = reinterpret_cast<double*>(smem_raw);             // rg[g] = 1/g, shared by the CTA's warps
+    for (int g = threadIdx.x; g <= C; g += blockDim.x) rg[g] = g ? 1.0 / (double)g : 0.0;
+    __syncthreads();
     FormAShared sm;
-    forma_carve(smem_raw + wbytes * warp, C, F, a.R,
+    forma_carve(smem_raw + forma_cta_smem_header(C) + wbytes * warp, C, F, a.R,
                 a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
     for (;;) {
         const long long item = forma_next_item(a.queue);
@@ -101,14 +111,17 @@ __global__ void forma_rollout_kernel(FormARolloutArgs ra)
         for (int tick = 0; tick < ra.n_ticks; ++tick) {
             if (fsc == pu.fs && ct >= pu.ct0 && ct < pu.ct1) s3[1] += a.model.dt * (axis == 0 ? pu.ax : pu.ay); // bang.m:104-114
             int iters; double kkt;
-            acc |= forma_tick_axis(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis, &iters, &kkt);
+            acc |= forma_tick_axis<FT>(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis,
+                                       a.warm_start && tick > 0, a.use_pdas, rg, &iters, &kkt);
             const double zd0 = sm.x[0], pred = sm.x[C];
             __syncwarp();
             forma_integrate(eta, a.model.dt, s3, zd0);
             if (ra.traj && lane < 3)
                 ra.traj[((size_t)inst * ra.n_ticks + tick) * 6 + 2 * lane + axis] = s3[lane];   // x,y,xd,yd,xz,yz
             ct += 1;
+            bool switched = false;
             if (fsc + 1 <= in.n_timing && j + 1 >= ft[fsc]) {                                  // bang.m:529
+                switched = true;
                 fsc += 1; cur = pred; store = pred;
                 if (fsc >= 2 && fsc <= in.n_fs) {                                              // bang.m:539-556
                     const double d = pred - plan[(fsc - 1) * 2 + axis];
@@ -120,6 +133,7 @@ __global__ void forma_rollout_kernel(FormARolloutArgs ra)
                 ct = 0;
             }
             j += 1;
+            if (a.warm_start) forma_shift_working_set(sm.das.state, C, F, switched);
         }
         // The other axis' warp reads inst_io[inst] when it picks the item up, possibly after this write: only the
         // fields of THIS axis are written here, and j / fs_counter / cl_first_ramp (common to both axes) go to
@@ -164,16 +178,17 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, For
 {
     const int C = m.C, F = m.F, q = C + F + 1;
     const size_t lim = 227 * 1024;
-    int R = env_int("ISMPC_FORMA_R", 48);
+    int R = env_int("ISMPC_FORMA_R", 32);
     if (R > q) R = q;
     if (R < 1) R = 1;
     int wpc = env_int("ISMPC_FORMA_WPC", 4);
     if (wpc < 1) wpc = 1;
-    if (wpc > 16) wpc = 16;
-    while (wpc > 1 && forma_warp_smem_bytes(C, F, R) * wpc > lim) --wpc;
-    while (R > 1 && forma_warp_smem_bytes(C, F, R) * wpc > lim) --R;
+    if (wpc > FORMA_MAX_THREADS / 32) wpc = FORMA_MAX_THREADS / 32;
+    const size_t hdr = forma_cta_smem_header(C);
+    while (wpc > 1 && forma_warp_smem_bytes(C, F, R) * wpc + hdr > lim) --wpc;
+    while (R > 1 && forma_warp_smem_bytes(C, F, R) * wpc + hdr > lim) --R;
     p->R = R; p->warps_per_cta = wpc;
-    p->smem = forma_warp_smem_bytes(C, F, R) * wpc;
+    p->smem = forma_warp_smem_bytes(C, F, R) * wpc + hdr;
     int per_sm = (int)((lim + 1024) / (p->smem + 1024));      // 1 KB per-CTA reservation
     if (per_sm < 1) per_sm = 1;
     if (per_sm * wpc > 48) per_sm = 48 / wpc > 0 ? 48 / wpc : 1;
@@ -182,17 +197,20 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, For
     p->grid = (int)(ctas < resident ? ctas : resident);
     if (p->grid < 1) p->grid = 1;
     p->spill_doubles = forma_spill_doubles(C, F, R) * (size_t)p->grid * wpc;
+    p->use_pdas = env_int("ISMPC_FORMA_PDAS", 1) && (size_t)tri(R, 0) >= (size_t)(1 + 2 * F) * (2 + 2 * F);
+    p->warm_start = env_int("ISMPC_FORMA_WARM", 1);
 }
 
 int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStream_t st)
 {
     FormAArgs a = a_in;
-    a.R = p.R; a.warps_per_cta = p.warps_per_cta;
-    cudaError_t e = cudaFuncSetAttribute(forma_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = 0;
+    auto kern = a.model.F <= 3 ? forma_tick_kernel<3> : forma_tick_kernel<ISMPC_MAX_FSTEPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     cudaMemsetAsync(a.out, 0, (size_t)a.n * sizeof(ismpc_forma_out_t), st);
-    forma_tick_kernel<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(a);
+    kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -201,13 +219,14 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
                          cudaStream_t st)
 {
     FormAArgs a = a_in;
-    a.R = p.R; a.warps_per_cta = p.warps_per_cta;
-    cudaError_t e = cudaFuncSetAttribute(forma_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = p.warm_start;
+    auto kern = a.model.F <= 3 ? forma_rollout_kernel<3> : forma_rollout_kernel<ISMPC_MAX_FSTEPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
     FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, status};
-    forma_rollout_kernel<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
+    kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
     forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing);
     return (int)cudaGetLastError();
 }

@@ -16,7 +16,7 @@ int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk
                          const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
                          cudaStream_t st);
 
-struct FormALaunchPlan { int R, warps_per_cta, grid; size_t smem, spill_doubles; };
+struct FormALaunchPlan { int R, warps_per_cta, grid, use_pdas, warm_start; size_t smem, spill_doubles; };
 void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p);
 int forma_tick_launch(const FormAArgs& a, const FormALaunchPlan& p, cudaStream_t st);
 int forma_rollout_launch(const FormAArgs& a, const FormALaunchPlan& p, ismpc_forma_inst_t* inst_io,

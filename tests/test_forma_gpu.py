@@ -17,7 +17,7 @@ def _advance(handle, inst, fs_timing, fs_plan, ticks):
             continue
         sel = np.nonzero(ticks == t)[0]
         r = handle.forma_rollout(inst[sel], fs_timing, fs_plan, int(t), want_traj=False)
-        assert (r["status"] == 0).all()
+        assert (r["status"] & abi.ST_FAIL_MASK == 0).all()
         inst[sel] = r["inst"]
         for i in sel:   # only these instances' plan rows changed
             a = inst["plan_first_row"][i]; b = a + inst["n_fs"][i]
@@ -30,7 +30,7 @@ def _compare(handle, model, inst, fs_timing, fs_plan, nthreads=8):
     o = O.forma_batch(model, inst, fs_timing, fs_plan, nthreads=nthreads)
     ok = o["ret"] == 0
     assert ok.mean() > 0.9
-    assert (g["out"]["status"][ok] == 0).all()
+    assert (g["out"]["status"][ok] & abi.ST_FAIL_MASK == 0).all()
     C, F = int(model["C"][0]), int(model["F"][0])
     # parity is per axis block [zd(C) | xf(F)]
     err = primal_rel_err(g["primal"][ok], o["primal"][ok])
@@ -84,7 +84,7 @@ def test_closed_loop_lockstep_with_push(handle):
     push["fs"] = 2
     T = 130
     r = handle.forma_rollout(inst, ft, plan, T, push=push)
-    assert (r["status"] == 0).all()
+    assert (r["status"] & abi.ST_FAIL_MASK == 0).all()
     cur, pl = inst.copy(), plan.copy()
     ct = np.zeros(4, dtype=int)
     for t in range(T):
@@ -130,6 +130,56 @@ def test_walking_fixture_closed_loop(handle):
     inst["cl_first_ramp"] = 1; inst["n_timing"] = len(ft); inst["n_fs"] = center.shape[0]
     T = com.shape[0] - 1
     r = handle.forma_rollout(inst, ft, center, T)
-    assert r["status"][0] == 0
+    assert r["status"][0] & abi.ST_FAIL_MASK == 0
     err = np.abs(r["traj"][0, :T, :2] - com[1:T + 1, :2])
     assert err.max() < 5e-6, "max err vs MATLAB fixture %.3e" % err.max()   # quadprog tolerance + %e printing
+
+
+def test_kinematic_rows_active(handle):
+    """Footstep displacement bounds tight enough that kinematic rows enter the working set (bang.m:163-190)."""
+    model = abi.forma_model(disp_forw=0.06, disp_forw_dummy=0.03, disp_L=0.05)
+    handle.forma_set_model(model)
+    n = 64
+    inst, ft, plan = synth.forma_batch(n, gait="trot", seed=31)
+    rng = np.random.default_rng(13)
+    ticks = rng.choice([0, 17, 49, 63, 98, 131], size=n)
+    inst, plan = _advance(handle, inst, ft, plan, ticks)
+    g, o = _compare(handle, model, inst, ft, plan)
+    C = int(model["C"][0])
+    assert (o["active"][o["ret"] == 0][:, 2 * C:] != 0).any(), "vacuous: no kinematic row active"
+
+
+def test_structured_solver_equals_dual_active_set(handle, monkeypatch):
+    """The primal-dual active-set fast path and the dual active-set fallback are two exact methods: same answers."""
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    n = 128
+    inst, ft, plan = synth.forma_batch(n, gait="trot", seed=41)
+    rng = np.random.default_rng(14)
+    ticks = rng.choice([0, 9, 33, 49, 50, 77, 99, 100, 150, 222], size=n)
+    inst, plan = _advance(handle, inst, ft, plan, ticks)
+    a = handle.forma_solve_batch(inst, ft, plan)
+    monkeypatch.setenv("ISMPC_FORMA_PDAS", "0")
+    b = handle.forma_solve_batch(inst, ft, plan)
+    monkeypatch.delenv("ISMPC_FORMA_PDAS")
+    assert (b["out"]["status"] & abi.ST_GI_FALLBACK == 0).all()
+    assert (a["out"]["status"] & abi.ST_FAIL_MASK == 0).all() and (b["out"]["status"] & abi.ST_FAIL_MASK == 0).all()
+    assert (a["out"]["status"] & abi.ST_GI_FALLBACK != 0).mean() < 0.05, "fast path falls back too often"
+    assert primal_rel_err(a["primal"], b["primal"]).max() <= 1e-7
+    assert np.abs(a["out"]["st"] - b["out"]["st"]).max() <= 1e-8
+
+
+def test_warm_started_rollout_equals_cold(handle, monkeypatch):
+    """Closed loop with the working set carried from tick to tick == every tick solved from the empty set."""
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    inst, ft, plan = synth.forma_batch(16, gait="trot", seed=51)
+    push = synth.push_batch(16, seed=52)
+    push["fs"] = 2
+    w = handle.forma_rollout(inst, ft, plan, 160, push=push)
+    monkeypatch.setenv("ISMPC_FORMA_WARM", "0")
+    c = handle.forma_rollout(inst, ft, plan, 160, push=push)
+    monkeypatch.delenv("ISMPC_FORMA_WARM")
+    assert (w["status"] & abi.ST_FAIL_MASK == 0).all() and (c["status"] & abi.ST_FAIL_MASK == 0).all()
+    assert np.abs(w["traj"] - c["traj"]).max() <= 1e-7
+    assert np.array_equal(w["inst"]["fs_counter"], c["inst"]["fs_counter"])

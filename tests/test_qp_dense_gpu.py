@@ -98,7 +98,6 @@ def test_forma_stacked_as_dense(handle):
     """Formulation A exactly as MPCSolver's constructor shapes it: nV = 2(C+F) = 206, nC = 208, equalities first."""
     am = abi.forma_model()
     inst, ft, plan = synth.forma_batch(6, gait="trot", seed=8)
-    r = handle  # noqa: F841
     handle.forma_set_model(am)
     adv = handle.forma_rollout(inst, ft, plan, 63, want_traj=False)
     inst, plan = adv["inst"], adv["fs_plan"]

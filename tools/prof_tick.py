@@ -58,7 +58,7 @@ else:
         it = np.sort(o["iters"])
         print("forma tick n=%d: %.1f us, iters mean %.1f p50 %d p90 %d p99 %d max %d, failed %d"
               % (n, e0.elapsed_time(e1) * 1e3, it.mean(), it[len(it) // 2], it[int(len(it) * 0.9)], it[int(len(it) * 0.99)],
-                 it[-1], (o["status"] != 0).sum()))
+                 it[-1], (o["status"] & abi.ST_FAIL_MASK != 0).sum()), "fallback", (o["status"] & abi.ST_GI_FALLBACK != 0).sum())
 
 if os.environ.get("ISMPC_DBG"):
     import ctypes as C
