@@ -164,7 +164,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     K, W, n = args.steps, max(args.warmup, 3), args.batch
-    h = binding.Handle(device=local, max_batch=max(n, 1024))
+    h = binding.Handle(device=local, max_batch=max(n, 8192))
     model = abi.formc_model(N=HORIZON)
     h.formc_set_model(model)
 
@@ -294,6 +294,11 @@ def main():
             line["form_a"] = bench_form_a(h, torch, dev, n, stream)
         except Exception as e:  # noqa: BLE001
             line["form_a"] = {"error": repr(e)}
+        try:
+            h.formc_set_model(model)
+            line["closed_loop_form_c"] = bench_formc_rollout(h, torch, dev, stream)
+        except Exception as e:  # noqa: BLE001
+            line["closed_loop_form_c"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             reps = 3
@@ -311,15 +316,11 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_form_a(h, torch, dev, n, stream, steps=20):
-    """1,024 trot instances of formulation A advanced on the GPU to random gait phases, then timed single cold ticks."""
-    from quadruped_gait_generation_ismpc_b200 import abi, synth
-    model = abi.forma_model()
-    h.forma_set_model(model)
-    inst, ft, plan = synth.forma_batch(n, gait="trot")
-    rng = np.random.default_rng(5)
+def _midgait(h, inst, ft, plan, seed=5):
+    """Advance formulation-A instances on the GPU to random gait phases (in place on copies)."""
+    n = len(inst)
+    rng = np.random.default_rng(seed)
     ticks = rng.choice([3, 17, 36, 49, 63, 98, 131, 160, 207, 260], size=n)
-    order = np.argsort(ticks, kind="stable")
     for t in np.unique(ticks):
         sel = np.nonzero(ticks == t)[0]
         r = h.forma_rollout(inst[sel], ft, plan, int(t), want_traj=False)
@@ -327,28 +328,103 @@ def bench_form_a(h, torch, dev, n, stream, steps=20):
         for i in sel:
             a = inst["plan_first_row"][i]; b = a + inst["n_fs"][i]
             plan[a:b] = r["fs_plan"][a:b]
-    del order
+    return inst, plan
+
+
+def bench_form_a(h, torch, dev, n, stream, steps=20):
+    """Formulation A (canonical ISMPC with footsteps, 1 QP of nV=206/nC=208 per instance-tick):
+    cold single ticks on mid-gait trot (configs[1]) and walking (configs[2], per-GPU share) batches, and the
+    closed loop with pushes, warm-started (configs[4])."""
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
 
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
 
-    d_inst, d_ft, d_plan = to_dev(inst), to_dev(ft), to_dev(plan)
-    d_out = torch.zeros(n * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
+    def tick_bench(model, inst, ft, plan, label):
+        m = len(inst)
+        h.forma_set_model(model)
+        inst, plan = _midgait(h, inst, ft, plan)
+        d_inst, d_ft, d_plan = to_dev(inst), to_dev(ft), to_dev(plan)
+        d_out = torch.zeros(m * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for k in range(steps + 3):
+            torch.cuda.synchronize()
+            e0.record()
+            h.forma_solve_batch_raw(m, d_inst.data_ptr(), d_ft.data_ptr(), len(ft), d_plan.data_ptr(), plan.shape[0],
+                                    d_out.data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+            e1.record(); e1.synchronize()
+            if k >= 3:
+                times.append(e0.elapsed_time(e1))
+        out = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
+        ms = statistics.median(times)
+        return {"workload": label, "qp_solves_per_s": m / (ms * 1e-3), "ms_per_tick": ms,
+                "mean_iters_per_qp": float(out["iters"].mean()), "max_iters": int(out["iters"].max()),
+                "failed": int((out["status"] & abi.ST_FAIL_MASK != 0).sum()),
+                "dual_active_set_fallbacks": int((out["status"] & abi.ST_GI_FALLBACK != 0).sum())}
+
+    res = {"note": "1 QP per instance-tick (x and y stacked: nV=206, nC=208); cold = empty working set"}
+    inst, ft, plan = synth.forma_batch(n, gait="trot")
+    res["tick_cold_trot"] = tick_bench(abi.forma_model(), inst, ft, plan, "formA_tick_trot_%dxC100F3_midgait_cold" % n)
+    nw = 8192
+    inst, ft, plan = synth.forma_batch(nw, gait="walk", vary=True, ds=30, N_gait=108)
+    res["tick_cold_walk"] = tick_bench(abi.forma_model(q_foot=1e9), inst, ft, plan,
+                                       "formA_tick_walk_%dxC100F3_midgait_cold (configs[2] per-GPU share)" % nw)
+    # closed loop: 1,000 instances x 250 ticks with pushes, state resident on the device, warm-started
+    nr, T = 1000, 250
+    h.forma_set_model(abi.forma_model())
+    inst, ft, plan = synth.forma_batch(nr, gait="trot", seed=synth.SEED0 ^ 9)
+    push = synth.push_batch(nr)
+    d_ft = to_dev(ft)
+    d_status = torch.zeros(nr, dtype=torch.int32, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
-    for k in range(steps + 3):
+    for k in range(3):
+        d_inst, d_plan, d_push = to_dev(inst), to_dev(plan), to_dev(push)
         torch.cuda.synchronize()
         e0.record()
-        h.forma_solve_batch_raw(n, d_inst.data_ptr(), d_ft.data_ptr(), len(ft), d_plan.data_ptr(), plan.shape[0],
-                                d_out.data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+        h.forma_rollout_raw(nr, T, d_inst.data_ptr(), d_ft.data_ptr(), len(ft), d_plan.data_ptr(), plan.shape[0],
+                            push=d_push.data_ptr(), status=d_status.data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
         e1.record(); e1.synchronize()
-        if k >= 3:
-            times.append(e0.elapsed_time(e1))
-    out = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
-    ms = statistics.median(times)
-    return {"workload": "formA_tick_trot_1024xC100F3_midgait_cold", "qp_solves_per_s": n / (ms * 1e-3),
-            "ms_per_tick": ms, "mean_iters_per_qp": float(out["iters"].mean()), "max_iters": int(out["iters"].max()),
-            "failed": int((out["status"] & abi.ST_FAIL_MASK != 0).sum()), "gi_fallback": int((out["status"] & abi.ST_GI_FALLBACK != 0).sum()), "note": "1 QP per instance-tick (x and y stacked, nV=206, nC=208)"}
+        times.append(e0.elapsed_time(e1))
+    ms = min(times)
+    stt = d_status.cpu().numpy()
+    res["rollout_warm_trot"] = {"workload": "formA_rollout_trot_%dx%dticks_push (configs[4] shape)" % (nr, T),
+                                "instance_ticks_per_s": nr * T / (ms * 1e-3), "ms_total": ms,
+                                "failed": int((stt & abi.ST_FAIL_MASK != 0).sum()),
+                                "dual_active_set_fallbacks": int((stt & abi.ST_GI_FALLBACK != 0).sum())}
+    return res
+
+
+def bench_formc_rollout(h, torch, dev, stream):
+    """configs[4] on formulation C: 1,000 instances x 1,000 closed-loop ticks (3 QPs each) with pushes, on the device."""
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    nr, T = 1000, 1000
+    steps_plan = (T + 2 * HORIZON + 900) // 45 + 3
+    state, walk, inst, plan = synth.formc_batch(nr, seed=synth.SEED0 ^ 11, n_steps=steps_plan, k0_cap=100)
+    push = synth.push_batch(nr, formc=True)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    d_inst, d_plan, d_push = to_dev(inst), to_dev(plan), to_dev(push)
+    d_status = torch.zeros(nr, dtype=torch.int32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for k in range(3):
+        d_state, d_walk = to_dev(state), to_dev(walk)
+        torch.cuda.synchronize()
+        e0.record()
+        h.formc_rollout_raw(nr, T, d_state.data_ptr(), d_walk.data_ptr(), d_inst.data_ptr(), d_plan.data_ptr(),
+                            plan.shape[0], push=d_push.data_ptr(), status=d_status.data_ptr(), mem=abi.MEM_DEVICE,
+                            stream=stream)
+        e1.record(); e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = min(times)
+    stt = d_status.cpu().numpy()
+    return {"workload": "formC_rollout_trot_%dx%dticks_push (configs[4])" % (nr, T),
+            "instance_ticks_per_s": nr * T / (ms * 1e-3), "qp_solves_per_s": 3.0 * nr * T / (ms * 1e-3), "ms_total": ms,
+            "instances_with_a_failed_tick": int((stt & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) .astype(bool).sum())}
 
 
 if __name__ == "__main__":

@@ -271,6 +271,9 @@ __device__ inline bool warp_gauss_jordan(double* K, int dim)
 // row: - shift), planf the footstep targets minus shift; sm.das.state the starting working set.
 // rg[g] = 1/g for g = 1..C.  On return 0: sm.x = [zd; xf] (xf absolute), sm.rv row values (shifted),
 // sm.das.state the optimal working set.
+constexpr int PDAS_DAMP_AFTER = 12;
+constexpr int PDAS_MAX_ITERS = 80;
+
 template <int FT>
 __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
                                  const double* planf, const double* rg, int maxit, int* iters_out)
@@ -452,7 +455,10 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
         }
         __syncwarp();
         // ---- re-guess the working set ----
-        int changed = 0;
+        // Rows whose multiplier has the wrong sign leave.  From iteration PDAS_DAMP_AFTER on, only those at an end of
+        // a run of equally-signed active rows leave (if there is one): an over-long run can flip the sign of nu,
+        // which would release the whole run at once and make the iteration cycle.
+        int changed = 0, wrong_end = 0;
         for (int i = r0; i < r1; ++i) {
             const int s0 = st[i];
             int s1 = 0;
@@ -463,9 +469,22 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
             } else {
                 const double y = cseg[i] - (i + 1 < C ? cseg[i + 1] : 0.0);     // dt * multiplier
                 if (s0 < 0 ? y > 0.0 : y < 0.0) s1 = s0;
+                else {
+                    const int sl = i > 0 ? st[i - 1] : 0, sr = i + 1 < C ? st[i + 1] : 0;
+                    s1 = (sl != s0 || sr != s0) ? 0 : 2;          // 2: wrong sign, interior of a run
+                    wrong_end |= s1 == 0;
+                }
             }
-            changed |= s1 != s0;
             nxt[i] = s1;                                      // staged: cseg[i+1] of a neighbour lane may still be read
+        }
+        {
+            const bool damp = it >= PDAS_DAMP_AFTER && __any_sync(ISMPC_FULL_MASK, wrong_end);
+            for (int i = r0; i < r1; ++i) {
+                int s1 = nxt[i];
+                if (s1 == 2) s1 = damp ? st[i] : 0;
+                changed |= s1 != st[i];
+                nxt[i] = s1;
+            }
         }
         if (lane < F) {
             const int f = lane, s0 = st[C + f];
@@ -577,12 +596,12 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
         if (lane == 0) { sm.lo[C] -= cur; sm.hi[C] -= cur; }
         for (int f = lane; f < F; f += 32) sm.z[f] = sm.z[C + f] - cur;
         __syncwarp();
-        int rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, 48, &iters);
+        int rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &iters);
         if (rc != 0 && warm) {                                      // a stale guess can stall: retry from the empty set
             for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
             __syncwarp();
             int it2 = 0;
-            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, 48, &it2);
+            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
             iters += it2;
         }
         if (rc == 0) {

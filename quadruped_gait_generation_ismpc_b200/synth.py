@@ -26,7 +26,7 @@ def reference_formc_instance(n_ticks_time=0.0):
 
 
 def formc_batch(n, seed=SEED0 ^ 2, N=100, n_steps=40, S=35, F_ds=10, vary_height=False, z_spread=0.01,
-                running_frac=1.0, dcm_spread=0.035):
+                running_frac=1.0, dcm_spread=0.035, k0_cap=800):
     """n randomised trot instances: step length L~U[0.05,0.25], half-width W~U[0.05,0.12] alternating,
     heading in {0, pi/4, pi/2}, per-step jitter N(0, 0.01^2), k0~U{0..k0max}, velocity U[-0.1,0.1]^2, position
     such that the divergent component is within dcm_spread of the value the footstep plan can stabilise
@@ -50,7 +50,7 @@ def formc_batch(n, seed=SEED0 ^ 2, N=100, n_steps=40, S=35, F_ds=10, vary_height
             p[k, 1] = s * fx + c * fy + rng.normal(0, 0.01)
             p[k, 3] = per * k
         plan[i * n_steps:(i + 1) * n_steps] = p
-        k0 = int(rng.integers(0, min(800, k0max) + 1))
+        k0 = int(rng.integers(0, min(k0_cap, k0max) + 1))
         step = k0 // per; r = k0 % per
         h = rng.uniform(0.45, 0.75) if vary_height else 0.69
         # A state the ISMPC can stabilise: the divergent component xi = c + cd/eta must match the discounted
