@@ -168,6 +168,11 @@ const char* ismpc_last_cuda_error(const ismpc_handle* h);
 /* Number of kernels this handle has launched since creation (for the benchmark's launch count). */
 int64_t ismpc_kernel_launches(const ismpc_handle* h);
 
+/* Tuning knobs that do not change results.  "formc_cluster_size": CTAs per instance of the formulation-C tick
+ * (1 = CTA-per-QP, 2/4/8 = thread-block-cluster-per-QP, 0 = automatic: clusters from N = 200 on while the whole
+ * batch stays resident -- the latency regime). */
+int ismpc_set_option(ismpc_handle* h, const char* name, int value);
+
 /* Measurement utility (not part of the reference seam): register-resident DFMA micro-benchmark, the FP64
  * roofline denominator that MEASURED_PEAKS.json lacks.  Writes the best of `reps` runs in TFLOP/s. */
 int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops_out);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libismpc_b200.so")
 EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy", "ismpc_last_cuda_error",
            "ismpc_kernel_launches", "ismpc_formc_set_model", "ismpc_formc_solve_batch", "ismpc_formc_rollout",
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
-           "ismpc_measure_fp64_peak"]
+           "ismpc_measure_fp64_peak", "ismpc_set_option"]
 
 _lib = None
 
@@ -52,6 +52,7 @@ def lib():
     L.ismpc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
     L.ismpc_destroy.argtypes = [C.c_void_p]
     L.ismpc_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.ismpc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
@@ -101,6 +102,9 @@ class Handle:
         if rc != 0:
             raise IsmpcError("%s: %s [%s]" % (what, self._L.ismpc_error_string(rc).decode(),
                                              self._L.ismpc_last_cuda_error(self._h).decode()))
+
+    def set_option(self, name, value):
+        self._check(self._L.ismpc_set_option(self._h, name.encode(), int(value)), "ismpc_set_option(%s)" % name)
 
     def measure_fp64_peak(self, reps=5):
         v = C.c_double(0.0)

@@ -29,6 +29,8 @@ struct ismpc_handle {
     int sm_count = 148;
     long long launches = 0;
     char err[256] = {0};
+    int opt_formc_cluster = 0;     // 0 = automatic
+    int c_ctas_per_sm = 1;
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
@@ -96,6 +98,17 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
     return ISMPC_OK;
 }
 
+extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
+{
+    if (!h || !name) return ISMPC_ERR_ARG;
+    if (strcmp(name, "formc_cluster_size") == 0) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return ISMPC_ERR_ARG;
+        h->opt_formc_cluster = value;
+        return ISMPC_OK;
+    }
+    return ISMPC_ERR_ARG;
+}
+
 extern "C" const char* ismpc_last_cuda_error(const ismpc_handle* h) { return h ? h->err : ""; }
 extern "C" int64_t ismpc_kernel_launches(const ismpc_handle* h) { return h ? h->launches : 0; }
 
@@ -120,8 +133,22 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
     CK(cudaMemcpy(&info, h->c_info.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) return ISMPC_ERR_MODEL;     // H_z not positive definite
     h->cm = *m;
+    h->c_ctas_per_sm = formc_cluster_ctas_per_sm(m->N);
     h->formc_ready = true;
     return ISMPC_OK;
+}
+
+// Cluster-per-QP is the latency mode (measured, profiles/r1_horizon_sweep.json): splitting the O(N^2) mat-vec
+// over 4 CTAs pays from N = 200 on, as long as all clusters of the batch are resident at once; a batch that
+// fills the GPU anyway is faster with one CTA per QP (the O(N) stages are replicated in every CTA of a cluster).
+static int formc_cluster_size(const ismpc_handle* h, int n)
+{
+    if (h->opt_formc_cluster > 0) return h->opt_formc_cluster;
+    if (h->cm.N < 200) return 1;
+    const long long resident = (long long)h->c_ctas_per_sm * h->sm_count;
+    if (4LL * n <= resident) return 4;
+    if (2LL * n <= resident) return 2;
+    return 1;
 }
 
 static void formc_fill_args(ismpc_handle* h, FormCArgs& a, int n)
@@ -150,7 +177,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     if (mem == ISMPC_MEM_DEVICE) {
         a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt; a.plan_rows = plan_rows;
         a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
-        int rc = formc_tick_launch(a, n, st);
+        int rc = formc_tick_launch(a, n, formc_cluster_size(h, n), st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
         return ISMPC_OK;
@@ -172,7 +199,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     a.out = (ismpc_formc_out_t*)h->s_cout.p;
     a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
     a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
-    int rc = formc_tick_launch(a, n, st);
+    int rc = formc_tick_launch(a, n, formc_cluster_size(h, n), st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
     CK(cudaMemcpyAsync(out, h->s_cout.p, n * sizeof(ismpc_formc_out_t), cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,7 @@
 //   MPCSolver.cpp:402-422   integrate                    -> formc_tick() epilogue
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include "das.cuh"
 #include "../../include/ismpc_b200.h"
 
@@ -192,6 +193,12 @@ struct FormCArgs {
 // One tick for one instance by one CTA (FORMC_THREADS threads).  `st`/`wk` are the instance's current
 // state/walk (registers, uniform across the CTA); results are written to *o (thread 0) and, if non-null,
 // prim (3N) / act (3N).
+// CLUSTER: the instance is owned by a thread-block cluster (long horizons).  The one O(N^2) stage -- the table
+// mat-vec x0 = -H_z^-1 F_z, N^2 FMAs and N^2 doubles out of L2 -- is split by output rows over the CTAs of the
+// cluster; every CTA then stores its slice of x0 into the shared memory of all its peers (distributed shared
+// memory) and, after one cluster barrier, all CTAs carry on redundantly with the O(N) stages, so no further
+// exchange is needed.  Only rank 0 writes results (the caller passes o/prim/act as null on the other ranks).
+template <bool CLUSTER>
 __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model_t& mdl, const FormCTables& T,
                                   const ismpc_state_t& st, const ismpc_walk_t& wk, const ismpc_formc_inst_t& in,
                                   const double* __restrict__ plan_all, ismpc_formc_out_t* o,
@@ -207,7 +214,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     int status = 0;
 
     if (k0 < 0 || per <= 0 || (long long)k0 + 2 * N > (long long)in.n_steps * per) {
-        if (tid == 0) {
+        if (tid == 0 && o) {
             o->next = st; o->zmp_in[0] = o->zmp_in[1] = 0.0; o->fz0 = 0.0; o->lambda0 = 0.0; o->kkt_res = 0.0;
             o->status = ISMPC_ST_WINDOW; o->iters[0] = o->iters[1] = o->iters[2] = 0;
         }
@@ -272,26 +279,50 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     // unconstrained minimiser x0 = -H^-1 F  (table mat-vec; Hinv symmetric -> coalesced row reads).
     // The 4 warps split the j range; each lane owns outputs i = blk*128 + lane + 32e.  Per-warp partial
     // vectors go to shared memory (zdir/lam/chv/shs are free at this point) and are summed afterwards.
+    int i_lo = 0, i_hi = N;                                 // output rows of x0 this CTA computes
+    if constexpr (CLUSTER) {
+        const unsigned cr = cooperative_groups::this_cluster().block_rank(), cs = cooperative_groups::this_cluster().num_blocks();
+        i_lo = (int)((long long)N * cr / cs); i_hi = (int)((long long)N * (cr + 1) / cs);
+    }
     {
         double* part = (warp == 0) ? sm.zdir : (warp == 1) ? sm.lam : (warp == 2) ? sm.chv : sm.shs;
         const int jlo = (N * warp) / 4, jhi = (N * (warp + 1)) / 4;
-        for (int blk = 0; blk * 128 < N; ++blk) {
+        for (int blk = 0; i_lo + blk * 128 < i_hi; ++blk) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const int ib = blk * 128 + lane;
-            for (int j = jlo; j < jhi; ++j) {
+            const int ib = i_lo + blk * 128 + lane;
+            int j = jlo;
+            for (; j + 1 < jhi; j += 2) {                      // two table rows in flight per pass
+                const double f0 = sm.Fz[j], f1 = sm.Fz[j + 1];
+                const double* h0 = T.Hinv + (size_t)j * N + ib;
+                const double* h1 = h0 + N;
+                double v0[4], v1[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { v0[e] = ib + 32 * e < i_hi ? __ldg(h0 + 32 * e) : 0.0; v1[e] = ib + 32 * e < i_hi ? __ldg(h1 + 32 * e) : 0.0; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += v0[e] * f0 + v1[e] * f1;
+            }
+            if (j < jhi) {
                 const double fj = sm.Fz[j];
                 const double* hr = T.Hinv + (size_t)j * N + ib;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (ib + 32 * e < N) acc[e] += __ldg(hr + 32 * e) * fj;
+                for (int e = 0; e < 4; ++e) if (ib + 32 * e < i_hi) acc[e] += __ldg(hr + 32 * e) * fj;
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (ib + 32 * e < N) part[ib + 32 * e] = acc[e];
+            for (int e = 0; e < 4; ++e) if (ib + 32 * e < i_hi) part[ib + 32 * e] = acc[e];
         }
     }
     __syncthreads();
     ISMPC_PHASE(4);
-    for (int i = tid; i < N; i += FORMC_THREADS) sm.f[i] = -(sm.zdir[i] + sm.lam[i] + sm.chv[i] + sm.shs[i]);
-    __syncthreads();
+    for (int i = i_lo + tid; i < i_hi; i += FORMC_THREADS) {
+        const double v = -(sm.zdir[i] + sm.lam[i] + sm.chv[i] + sm.shs[i]);
+        sm.f[i] = v;
+        if constexpr (CLUSTER) {
+            auto cl = cooperative_groups::this_cluster();
+            const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
+            for (unsigned p = 0; p < cs; ++p) if (p != cr) cl.map_shared_rank(sm.f, p)[i] = v;
+        }
+    }
+    if constexpr (CLUSTER) cooperative_groups::this_cluster().sync(); else __syncthreads();
     ISMPC_PHASE(5);
 
     // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
@@ -521,7 +552,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     }
 
     // ================= integrate (MPCSolver.cpp:402-422) =================
-    if (tid == 0) {
+    if (tid == 0 && o) {
         double a00, a01, a10, a11, b0, b1;
         if (lam0 < 2.0) { a00 = 1.0; a01 = dt; a10 = 0.0; a11 = 1.0; b0 = 0.0; b1 = 0.0; }
         else {

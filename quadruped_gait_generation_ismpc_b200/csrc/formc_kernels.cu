@@ -131,10 +131,37 @@ formc_tick_kernel(FormCArgs a)
         const ismpc_state_t st = a.state[inst];
         const ismpc_walk_t wk = a.walk[inst];
         const ismpc_formc_inst_t in = a.inst[inst];
-        formc_tick(sm, a.model, a.T, st, wk, in, a.plan, a.out + inst,
+        formc_tick<false>(sm, a.model, a.T, st, wk, in, a.plan, a.out + inst,
                    a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
                    a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
         __syncthreads();
+    }
+}
+
+// Cluster-per-QP variant for long horizons: a cluster of CS CTAs owns one instance (see formc_tick<true>).
+__global__ void __launch_bounds__(FORMC_THREADS)
+formc_tick_cluster_kernel(FormCArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto cl = cooperative_groups::this_cluster();
+    const unsigned cs = cl.num_blocks(), cr = cl.block_rank();
+    FormCShared sm;
+    formc_carve(smem_raw, a.model.N, sm);
+    if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    cl.sync();                                   // peers' shared memory is live before anyone stores into it
+    uint32_t parity = 0;
+    const int N = a.model.N;
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    for (int inst = cluster_id; inst < a.n; inst += n_clusters) {
+        const ismpc_state_t st = a.state[inst];
+        const ismpc_walk_t wk = a.walk[inst];
+        const ismpc_formc_inst_t in = a.inst[inst];
+        const bool lead = cr == 0;
+        formc_tick<true>(sm, a.model, a.T, st, wk, in, a.plan, lead ? a.out + inst : nullptr,
+                         lead && a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
+                         lead && a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
+        cl.sync();                               // nobody stores the next instance's slice while a peer still reads
     }
 }
 
@@ -178,7 +205,7 @@ formc_rollout_kernel(FormCRolloutArgs ra)
             if (tick >= pu.ct0 && tick < pu.ct1) {     // impulsive push (quad_as_bip_bang.m:104-114)
                 st.com_vel[0] += a.model.dt * pu.ax; st.com_vel[1] += a.model.dt * pu.ay;
             }
-            formc_tick(sm, a.model, a.T, st, wk, in, a.plan, &s_out, nullptr, nullptr, parity);
+            formc_tick<false>(sm, a.model, a.T, st, wk, in, a.plan, &s_out, nullptr, nullptr, parity);
             __syncthreads();
             st = s_out.next;
             acc_status |= s_out.status;
@@ -199,17 +226,39 @@ formc_rollout_kernel(FormCRolloutArgs ra)
     }
 }
 
-int formc_tick_launch(const FormCArgs& a, int grid, cudaStream_t st)
+// CTAs of the cluster kernel that one SM keeps resident at horizon N (for the cluster-size policy in api.cu).
+int formc_cluster_ctas_per_sm(int N)
+{
+    size_t smem = formc_smem_bytes(N);
+    cudaFuncSetAttribute(formc_tick_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, formc_tick_cluster_kernel, FORMC_THREADS, smem) != cudaSuccess) nb = 1;
+    return nb > 0 ? nb : 1;
+}
+
+int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream_t st)
 {
     size_t smem = formc_smem_bytes(a.model.N);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(formc_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(formc_tick_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    formc_tick_kernel<<<grid, FORMC_THREADS, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    if (cluster_size <= 1) {
+        formc_tick_kernel<<<grid, FORMC_THREADS, smem, st>>>(a);
+        return (int)cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid * cluster_size); cfg.blockDim = dim3(FORMC_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, formc_tick_cluster_kernel, a);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,

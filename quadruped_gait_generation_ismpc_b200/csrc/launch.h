@@ -11,7 +11,8 @@ struct FormAArgs;
 
 int formc_setup_launch(const ismpc_formc_model_t& m, double* work, double* Hinv, double* G, double* M,
                        int* d_info, cudaStream_t st, long long* launches);
-int formc_tick_launch(const FormCArgs& a, int grid, cudaStream_t st);
+int formc_cluster_ctas_per_sm(int N);
+int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream_t st);
 int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                          const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
                          cudaStream_t st);

@@ -113,3 +113,22 @@ def test_rollout_matches_tick_by_tick(handle):
         wk["mpc_iter"] = np.floor(wk["control_iter"] * 0.01 / 0.01).astype(np.int32)   # Controller.cpp:504, in doubles
         wk["sim_time"] += 1
     assert np.array_equal(r["walk"]["footstep_counter"], wk["footstep_counter"])
+
+
+@pytest.mark.parametrize("N,cs", [(100, 2), (100, 4), (200, 1), (200, 8), (400, 2)])
+def test_cluster_per_qp_identical_to_cta_per_qp(handle, N, cs):
+    """Config 4: the thread-block-cluster variant (x0 mat-vec split over the cluster, slices exchanged through
+    distributed shared memory) gives bit-identical results to one CTA per QP."""
+    n = 48
+    steps = (2 * N + 900) // 45 + 3
+    state, walk, inst, plan = synth.formc_batch(n, seed=1000 + N, N=N, n_steps=steps, z_spread=0.05)
+    handle.formc_set_model(abi.formc_model(N=N))
+    try:
+        handle.set_option("formc_cluster_size", 1 if cs != 1 else 4)
+        a = handle.formc_solve_batch(state, walk, inst, plan)
+        handle.set_option("formc_cluster_size", cs)
+        b = handle.formc_solve_batch(state, walk, inst, plan)
+    finally:
+        handle.set_option("formc_cluster_size", 0)
+    assert np.array_equal(a["primal"], b["primal"]) and np.array_equal(a["active"], b["active"])
+    assert a["out"].tobytes() == b["out"].tobytes()
