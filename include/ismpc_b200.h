@@ -226,6 +226,53 @@ int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t*
                         double* fs_plan, int plan_rows, const ismpc_push_t* push,
                         double* traj_opt, int32_t* status_opt, int mem, void* stream);
 
+/* ismpc_forma_rollout plus the per-tick predicted footstep (predicted_xfs(1), predicted_yfs(1)) that the scripts
+ * hand to their second QP: pred_traj_opt (nullable) n x n_ticks x 2 doubles. */
+int ismpc_forma_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                           const int32_t* fs_timing, int timing_len,
+                           double* fs_plan, int plan_rows, const ismpc_push_t* push,
+                           double* traj_opt, double* pred_traj_opt, int32_t* status_opt, int mem, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Real-foot placement (the scripts' "SECOND QUAD_PROG") and trajectory export -- the stage     */
+/* after the hot path and the data format its only consumer (AMR_code_DART/Controller.cpp:      */
+/* 147-281) reads.                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+enum { ISMPC_GAIT_TROT = 0, ISMPC_GAIT_WALK = 1 };
+
+typedef struct {
+    double disp_forw, disp_i, disp_o;                    /* init_quadruped.m:31-35: 0.5, 0.4, 0.4 */
+    double disp_forw_dummy, disp_i_dummy, disp_o_dummy;  /* halves, init_quadruped.m:33-36 */
+    int32_t gait;            /* ISMPC_GAIT_TROT: quad_as_bip_no_plots.m:332-426 + compute_two_feet1.m
+                                ISMPC_GAIT_WALK: quad_walk_no_plots.m:334-504 + compute_one_feet_walk.m */
+    int32_t wrap_counter;    /* walk: 0 = the 8-phase counter never wraps (quad_walk_no_plots.m:527),
+                                      1 = it wraps 8 -> 1 (quad_walk.m:688) */
+} ismpc_feet_model_t;
+
+typedef struct {
+    double phi;                        /* heading (init_quadruped.m:9) */
+    int32_t j, fs_counter;             /* 1-based tick and fsCounter of the first tick of pred_traj */
+    int32_t timing_first, n_timing;    /* this instance's fs_timing */
+    int32_t plan_first_row, plan_rows; /* this instance's rows of foot_plan */
+} ismpc_feet_inst_t;
+
+/* Replays the second stage over n_ticks ticks: for every tick, the geometry of compute_two_feet1 / compute_one_feet_walk
+ * (closed-form line intersections in place of the scripts' symbolic `solve`) and the 4- / 2-variable QP (H = I, every
+ * row bounds one variable: a per-variable clip).  foot_plan: rows x 8 doubles per instance
+ * (rear-left x,y | rear-right | front-right | front-left, init_quadruped.m:151-152), modified in place.
+ * pred_traj: n x n_ticks x 2 from ismpc_forma_rollout_ex. */
+int ismpc_feet_place_rollout(ismpc_handle* h, int n, int n_ticks, const ismpc_feet_model_t* model,
+                             const ismpc_feet_inst_t* inst, const int32_t* fs_timing, int timing_len,
+                             const double* pred_traj, double* foot_plan, int foot_plan_rows, int mem, void* stream);
+
+/* Foot trajectories exactly as the scripts write them to foot_{fl,fr,rl,rr}_*.txt (quad_as_bip_no_plots.m:482-509,
+ * quad_walk_no_plots.m:563-613): per step `fixed` samples on the ground then `swing` samples (trot), or `swing`
+ * samples per step with phases 2/4/6/8 swinging fl/rr/fr/rl (walk, fixed = 0); swing height -3.2e-5 k^2 + 1.6e-3 k.
+ * Outputs: n x n_steps*(fixed+swing) x 3 doubles each. */
+int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_t* model, const ismpc_feet_inst_t* inst,
+                      const double* foot_plan, int foot_plan_rows, int n_steps, int fixed, int swing,
+                      double* fl, double* fr, double* rl, double* rr, int mem, void* stream);
+
 /* solveQP(H, f, A, lbA, ubA) (AMR_code_DART/utils.cpp:89-139) for n independent dense QPs of one shape:
  * min 1/2 x'Hx + g'x  s.t. lbA <= A x <= ubA.  H: n x nV x nV, g: n x nV, A: n x nC x nV (row-major),
  * lbA/ubA: n x nC.  x: n x nV.  y_opt (nullable): n x nC constraint duals (qpOASES sign);

@@ -671,11 +671,11 @@ int oracle_forma_tick(const oracle_forma_params* p, oracle_qp_fn solver,
 }
 
 /* bang.m:99-563 (QP-1 loop only) */
-int oracle_forma_closed_loop(const oracle_forma_params* p, oracle_qp_fn solver,
-                             double st[6], double* fs_plan, int n_fs,
-                             const int* fs_timing, int n_timing, int ds, int n_ticks,
-                             int push_fs, int push_ct0, int push_ct1, double push_ax, double push_ay,
-                             double* traj, int* nwsr_total)
+int oracle_forma_closed_loop2(const oracle_forma_params* p, oracle_qp_fn solver,
+                              double st[6], double* fs_plan, int n_fs,
+                              const int* fs_timing, int n_timing, int ds, int n_ticks,
+                              int push_fs, int push_ct0, int push_ct1, double push_ax, double push_ay,
+                              double* traj, int* nwsr_total, double* pred_traj, int* fsc_traj)
 {
     int fails = 0, fs_counter = 1, ct = 0, first_ramp = 1, wsr = 0;
     double cur[2] = {fs_plan[0], fs_plan[1]};             /* bang.m:50-51 */
@@ -693,6 +693,8 @@ int oracle_forma_closed_loop(const oracle_forma_params* p, oracle_qp_fn solver,
             double* t = traj + (size_t)(j - 1) * 6;
             t[0] = st[0]; t[1] = st[3]; t[2] = st[1]; t[3] = st[4]; t[4] = st[2]; t[5] = st[5];
         }
+        if (pred_traj) { pred_traj[(size_t)(j - 1) * 2] = o.pred_fs[0]; pred_traj[(size_t)(j - 1) * 2 + 1] = o.pred_fs[1]; }
+        if (fsc_traj) fsc_traj[j - 1] = fs_counter;
         ct = ct + 1;
         if (fs_counter + 1 <= n_timing && j + 1 >= fs_timing[fs_counter]) { /* :529  fs_timing(fsCounter+1) */
             fs_counter += 1;
@@ -709,3 +711,167 @@ int oracle_forma_closed_loop(const oracle_forma_params* p, oracle_qp_fn solver,
     if (nwsr_total) *nwsr_total = wsr;
     return fails;
 }
+
+int oracle_forma_closed_loop(const oracle_forma_params* p, oracle_qp_fn solver,
+                             double st[6], double* fs_plan, int n_fs,
+                             const int* fs_timing, int n_timing, int ds, int n_ticks,
+                             int push_fs, int push_ct0, int push_ct1, double push_ax, double push_ay,
+                             double* traj, int* nwsr_total)
+{
+    return oracle_forma_closed_loop2(p, solver, st, fs_plan, n_fs, fs_timing, n_timing, ds, n_ticks, push_fs,
+                                     push_ct0, push_ct1, push_ax, push_ay, traj, nwsr_total, NULL, NULL);
+}
+
+/* ======================================================================================================
+ * Real-foot placement stage ("SECOND QUAD_PROG") and trajectory export
+ * ====================================================================================================== */
+#define FP(r, c) foot_plan[(size_t)((r) - 1) * 8 + ((c) - 1)]   /* MATLAB 1-based foot_plan(r,c) */
+
+/* compute_two_feet1.m:5-16 == compute_one_feet_walk.m:99-113: line through the two fixed feet (polyfit of degree 1
+ * through two points), line of opposite slope through the ZMP, their intersection, and the offset of the ZMP from
+ * it.  The scripts use the symbolic toolbox (`solve`); this is the same 2x2 intersection in closed form.
+ * A horizontal diagonal (slope 0) has no intersection in the scripts (solve returns empty and they error out):
+ * reported as ok = 0 and treated as "nothing changes". */
+static int diag_offset(const double fixed[4], const double zmp[2], double* slope, double* dist_x, double* dist_y)
+{
+    const double m = (fixed[3] - fixed[1]) / (fixed[2] - fixed[0]);
+    const double q = fixed[1] - m * fixed[0];
+    *slope = m;
+    if (!(fabs(m) > 0.0) || !isfinite(m)) { *dist_x = 0.0; *dist_y = 0.0; return 0; }
+    const double xs = (zmp[1] + m * zmp[0] - q) / (2.0 * m);   /* m x + q = zmp_y - m (x - zmp_x) */
+    const double ys = m * xs + q;
+    *dist_x = zmp[0] - xs; *dist_y = zmp[1] - ys;
+    return 1;
+}
+
+static double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+int oracle_feet_trot_tick(const oracle_feet_params* p, int fs_counter, const double pred[2], double phi,
+                          double* foot_plan, int rows)
+{
+    const int fs = fs_counter;
+    if (fs < 1 || fs + 1 > rows) return 0;
+    const int odd = (fs % 2) == 1;
+    /* odd: rr and fl stay, rl and fr move (quad_as_bip_no_plots.m:339,364); even: rl and fr stay, rr and fl move (:389) */
+    const int fc1 = odd ? 3 : 1, fc2 = odd ? 7 : 5;     /* fixed feet columns (x) in row fs */
+    const int mc1 = odd ? 1 : 3, mc2 = odd ? 5 : 7;     /* free feet columns (x) in row fs+1 */
+    const double fixed[4] = {FP(fs, fc1), FP(fs, fc1 + 1), FP(fs, fc2), FP(fs, fc2 + 1)};
+    const double free_[4] = {FP(fs + 1, mc1), FP(fs + 1, mc1 + 1), FP(fs + 1, mc2), FP(fs + 1, mc2 + 1)};
+    double m, dx, dy;
+    int changed = 0;
+    if (diag_offset(fixed, pred, &m, &dx, &dy)) {
+        /* compute_two_feet1.m:18-38: the free feet slide along the heading phi onto the line of slope -m through the ZMP */
+        double x1, y1, x2, y2;
+        if (phi == 3.14159265358979323846 / 2) {        /* MATLAB: phi==pi/2 */
+            x1 = free_[0]; x2 = free_[2];
+            y1 = pred[1] - m * (x1 - pred[0]); y2 = pred[1] - m * (x2 - pred[0]);
+        } else {
+            const double t = tan(phi);
+            x1 = (pred[1] + m * pred[0] + t * free_[0] - free_[1]) / (t + m);
+            y1 = t * (x1 - free_[0]) + free_[1];
+            x2 = (pred[1] + m * pred[0] + t * free_[2] - free_[3]) / (t + m);
+            y2 = t * (x2 - free_[2]) + free_[3];
+        }
+        changed = (dy != 0.0 || dx != 0.0);
+        if (changed) {                                   /* foot_plan(fsCounter+1,:) = quattro_piedi */
+            FP(fs + 1, mc1) = x1; FP(fs + 1, mc1 + 1) = y1; FP(fs + 1, mc2) = x2; FP(fs + 1, mc2 + 1) = y2;
+            FP(fs + 1, fc1) = fixed[0]; FP(fs + 1, fc1 + 1) = fixed[1]; FP(fs + 1, fc2) = fixed[2]; FP(fs + 1, fc2 + 1) = fixed[3];
+        }
+    }
+    /* 4-variable QP, H = I, six one-sided rows each on a single variable (:344-410) -> clip per variable.
+     * Variable order: odd  X = (rl.x, rl.y, fr.x, fr.y); even X = (fl.x, fl.y, rr.x, rr.y). */
+    const int dummy = (odd && fs == 1);
+    const double d_o = dummy ? p->disp_o_dummy : p->disp_o, d_i = dummy ? p->disp_i_dummy : p->disp_i;
+    const double d_f = dummy ? p->disp_forw_dummy : p->disp_forw;
+    const int a = odd ? 1 : 7, b = odd ? 5 : 3;         /* first / second foot of X (x column) */
+    const double X1 = fmin(FP(fs + 1, a), FP(fs, a) + d_f);
+    const double X2 = clipd(FP(fs + 1, a + 1), FP(fs, a + 1) - d_i, FP(fs, a + 1) + d_o);
+    const double X3 = fmin(FP(fs + 1, b), FP(fs, b) + d_f);
+    const double X4 = clipd(FP(fs + 1, b + 1), FP(fs, b + 1) - d_o, FP(fs, b + 1) + d_i);
+    FP(fs + 1, a) = X1; FP(fs + 1, a + 1) = X2; FP(fs + 1, b) = X3; FP(fs + 1, b + 1) = X4;
+    return changed;
+}
+
+int oracle_feet_walk_tick(const oracle_feet_params* p, int counter, int fs_counter, const double pred[2],
+                          double* foot_plan, int rows)
+{
+    const int fs = fs_counter;
+    if (counter != 2 && counter != 4 && counter != 6 && counter != 8) return 0;
+    if (fs < 1 || fs + 8 > rows) return 0;               /* MATLAB would grow the array; callers size it */
+    /* diagonal of the two feet that stay: rl-fr for phases 2 and 4, rr-fl for 6 and 8 (quad_walk_no_plots.m:342,379,421,438) */
+    const int d1 = (counter <= 4) ? 1 : 3, d2 = (counter <= 4) ? 5 : 7;
+    const int mc = counter == 2 ? 7 : counter == 4 ? 3 : counter == 6 ? 5 : 1;   /* the foot that moves */
+    const double fixed[4] = {FP(fs, d1), FP(fs, d1 + 1), FP(fs, d2), FP(fs, d2 + 1)};
+    double m, dx, dy;
+    int changed = 0;
+    if (diag_offset(fixed, pred, &m, &dx, &dy)) {
+        const double xf = FP(fs + 1, mc) + dx, yf = FP(fs + 1, mc + 1) + dy;   /* compute_one_feet_walk.m:115-116 */
+        changed = (dy != 0.0 || dx != 0.0);
+        if (changed) for (int l = 1; l <= 8; ++l) { FP(fs + l, mc) = xf; FP(fs + l, mc + 1) = yf; }
+    }
+    const int dummy = (counter <= 4) && fs <= 4;
+    const double d_o = dummy ? p->disp_o_dummy : p->disp_o, d_i = dummy ? p->disp_i_dummy : p->disp_i;
+    const double d_f = dummy ? p->disp_forw_dummy : p->disp_forw;
+    /* left feet (phases 2: fl, 8: rl) may move outwards by disp_o / inwards by disp_i; right feet (4: rr, 6: fr) mirrored */
+    const int left = (counter == 2 || counter == 8);
+    const double up = left ? d_o : d_i, dn = left ? d_i : d_o;
+    const double X1 = fmin(FP(fs + 1, mc), FP(fs, mc) + d_f);
+    const double X2 = clipd(FP(fs + 1, mc + 1), FP(fs, mc + 1) - dn, FP(fs, mc + 1) + up);
+    for (int l = 1; l <= 8; ++l) {
+        FP(fs + l, mc) = X1;
+        if (counter != 8 || l == 1) FP(fs + l, mc + 1) = X2;   /* :500-503 writes foot_plan(fsCounter+1,2) only: copied */
+    }
+    return changed;
+}
+
+static void put3(double* dst, size_t k, double x, double y, double z) { dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z; }
+
+void oracle_feet_export_trot(const double* foot_plan_c, int rows, int n_steps, int fixed, int swing,
+                             double* fl, double* fr, double* rl, double* rr)
+{
+    const double* foot_plan = foot_plan_c;
+    size_t k = 0;
+    for (int i = 1; i <= n_steps && i + 1 <= rows; ++i) {
+        for (int s = 1; s <= fixed; ++s, ++k) {
+            put3(fl, k, FP(i, 7), FP(i, 8), 0.0); put3(rr, k, FP(i, 3), FP(i, 4), 0.0);
+            put3(fr, k, FP(i, 5), FP(i, 6), 0.0); put3(rl, k, FP(i, 1), FP(i, 2), 0.0);
+        }
+        for (int j = 1; j <= swing; ++j, ++k) {
+            const double z = -0.000032 * j * j + 0.0016 * j;
+            if (i % 2 == 1) {
+                put3(fl, k, FP(i, 7), FP(i, 8), 0.0); put3(rr, k, FP(i, 3), FP(i, 4), 0.0);
+                put3(rl, k, FP(i, 1) + (FP(i + 1, 1) - FP(i, 1)) / swing * j, FP(i, 2) + (FP(i + 1, 2) - FP(i, 2)) / swing * j, z);
+                put3(fr, k, FP(i, 5) + (FP(i + 1, 5) - FP(i, 5)) / swing * j, FP(i, 6) + (FP(i + 1, 6) - FP(i, 6)) / swing * j, z);
+            } else {
+                put3(rl, k, FP(i, 1), FP(i, 2), 0.0); put3(fr, k, FP(i, 5), FP(i, 6), 0.0);
+                put3(fl, k, FP(i, 7) + (FP(i + 1, 7) - FP(i, 7)) / swing * j, FP(i, 8) + (FP(i + 1, 8) - FP(i, 8)) / swing * j, z);
+                put3(rr, k, FP(i, 3) + (FP(i + 1, 3) - FP(i, 3)) / swing * j, FP(i, 4) + (FP(i + 1, 4) - FP(i, 4)) / swing * j, z);
+            }
+        }
+    }
+}
+
+void oracle_feet_export_walk(const double* foot_plan_c, int rows, int n_steps, int step_duration,
+                             double* fl, double* fr, double* rl, double* rr)
+{
+    const double* foot_plan = foot_plan_c;
+    size_t k = 0;
+    int conteggio = 1;
+    for (int i = 1; i <= n_steps && i + 1 <= rows; ++i) {
+        for (int s = 1; s <= step_duration; ++s, ++k) {
+            const double z = -0.000032 * s * s + 0.0016 * s;
+            const int mv = (conteggio == 2) ? 7 : (conteggio == 4) ? 3 : (conteggio == 6) ? 5 : (conteggio == 8) ? 1 : 0;
+            double* dst[4] = {rl, rr, fr, fl};
+            for (int f = 0; f < 4; ++f) {
+                const int c = 2 * f + 1;
+                if (c == mv)
+                    put3(dst[f], k, FP(i, c) + (FP(i + 1, c) - FP(i, c)) / step_duration * s,
+                         FP(i, c + 1) + (FP(i + 1, c + 1) - FP(i, c + 1)) / step_duration * s, z);
+                else
+                    put3(dst[f], k, FP(i, c), FP(i, c + 1), 0.0);
+            }
+        }
+        conteggio = (conteggio == 8) ? 1 : conteggio + 1;
+    }
+}
+#undef FP

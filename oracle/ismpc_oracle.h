@@ -175,6 +175,39 @@ int oracle_forma_closed_loop(const oracle_forma_params* p, oracle_qp_fn solver,
                              int push_fs, int push_ct0, int push_ct1, double push_ax, double push_ay,
                              double* traj, int* nwsr_total);
 
+/* Same loop; additionally records, per tick, the predicted footstep handed to the second QP
+ * (pred_traj: n_ticks x 2, nullable) and the fsCounter the tick ran with (fsc_traj: n_ticks, nullable). */
+int oracle_forma_closed_loop2(const oracle_forma_params* p, oracle_qp_fn solver,
+                              double st[6], double* fs_plan, int n_fs,
+                              const int* fs_timing, int n_timing, int ds, int n_ticks,
+                              int push_fs, int push_ct0, int push_ct1, double push_ax, double push_ay,
+                              double* traj, int* nwsr_total, double* pred_traj, int* fsc_traj);
+
+/* ---- real-foot placement stage (the scripts' "SECOND QUAD_PROG") and trajectory export ---- */
+typedef struct {
+    double disp_forw, disp_i, disp_o;                   /* init_quadruped.m:31-35 */
+    double disp_forw_dummy, disp_i_dummy, disp_o_dummy; /* init_quadruped.m:33-36 */
+} oracle_feet_params;
+
+/* foot_plan: rows x 8 row-major, columns (1-based in MATLAB) 1,2 = rear-left x,y; 3,4 = rear-right;
+ * 5,6 = front-right; 7,8 = front-left (init_quadruped.m:151-152).
+ * Trot, one tick: trotting/quad_as_bip_no_plots.m:332-426 + trotting/compute_two_feet1.m.
+ * pred = (predicted_xfs(1), predicted_yfs(1)); fs_counter 1-based.  Returns `changed`. */
+int oracle_feet_trot_tick(const oracle_feet_params* p, int fs_counter, const double pred[2], double phi,
+                          double* foot_plan, int rows);
+/* Walk, one tick: walking/quad_walk_no_plots.m:334-504 + walking/compute_one_feet_walk.m.
+ * counter: the 8-phase counter (acts for 2, 4, 6, 8 only).  Returns `changed` (0 when the phase does nothing). */
+int oracle_feet_walk_tick(const oracle_feet_params* p, int counter, int fs_counter, const double pred[2],
+                          double* foot_plan, int rows);
+/* Foot trajectories as written to foot_{fl,fr,rl,rr}_*.txt: n_steps*(fixed+swing) samples x 3 each.
+ * Trot (quad_as_bip_no_plots.m:482-509): per step `fixed` samples on the ground, then `swing` samples with the
+ * diagonal pair rl/fr (odd step) or fl/rr (even step) interpolated and z = -3.2e-5 k^2 + 1.6e-3 k. */
+void oracle_feet_export_trot(const double* foot_plan, int rows, int n_steps, int fixed, int swing,
+                             double* fl, double* fr, double* rl, double* rr);
+/* Walk (quad_walk_no_plots.m:563-613): step_duration samples per step; phases 2/4/6/8 swing fl/rr/fr/rl. */
+void oracle_feet_export_walk(const double* foot_plan, int rows, int n_steps, int step_duration,
+                             double* fl, double* fr, double* rl, double* rr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -211,6 +211,72 @@ def forma_build(p, st, cur_fs, fs_store, j, fs_counter, fs_timing, ds, fs_plan, 
     return Hd, g, A, lb, ub
 
 
+class FeetParams(C.Structure):
+    _fields_ = [("disp_forw", C.c_double), ("disp_i", C.c_double), ("disp_o", C.c_double),
+                ("disp_forw_dummy", C.c_double), ("disp_i_dummy", C.c_double), ("disp_o_dummy", C.c_double)]
+
+
+def feet_params(disp_forw=0.5, disp_i=0.4, disp_o=0.4):
+    """init_quadruped.m:31-36 / init_quadruped2.m:31-36."""
+    return FeetParams(disp_forw, disp_i, disp_o, disp_forw / 2, disp_i / 2, disp_o / 2)
+
+
+def feet_trot_tick(fp, fs_counter, pred, phi, foot_plan, kind="auto"):
+    """In place on foot_plan (rows x 8, C-contiguous float64). Returns changed."""
+    L = lib(kind)
+    pred = np.ascontiguousarray(pred, dtype=np.float64)
+    L.oracle_feet_trot_tick.restype = C.c_int
+    return L.oracle_feet_trot_tick(C.byref(fp), C.c_int(fs_counter), _p(pred), C.c_double(phi), _p(foot_plan),
+                                   C.c_int(foot_plan.shape[0]))
+
+
+def feet_walk_tick(fp, counter, fs_counter, pred, foot_plan, kind="auto"):
+    L = lib(kind)
+    pred = np.ascontiguousarray(pred, dtype=np.float64)
+    L.oracle_feet_walk_tick.restype = C.c_int
+    return L.oracle_feet_walk_tick(C.byref(fp), C.c_int(counter), C.c_int(fs_counter), _p(pred), _p(foot_plan),
+                                   C.c_int(foot_plan.shape[0]))
+
+
+def feet_export(foot_plan, n_steps, gait, fixed=30, swing=50, step_duration=50, kind="auto"):
+    """Returns dict(fl, fr, rl, rr) of (samples x 3) arrays as the scripts write them to foot_*.txt."""
+    L = lib(kind)
+    foot_plan = np.ascontiguousarray(foot_plan, dtype=np.float64)
+    n_steps = min(n_steps, foot_plan.shape[0] - 1)
+    per = fixed + swing if gait == "trot" else step_duration
+    out = {k: np.zeros((n_steps * per, 3)) for k in ("fl", "fr", "rl", "rr")}
+    if gait == "trot":
+        L.oracle_feet_export_trot(_p(foot_plan), C.c_int(foot_plan.shape[0]), C.c_int(n_steps), C.c_int(fixed),
+                                  C.c_int(swing), _p(out["fl"]), _p(out["fr"]), _p(out["rl"]), _p(out["rr"]))
+    else:
+        L.oracle_feet_export_walk(_p(foot_plan), C.c_int(foot_plan.shape[0]), C.c_int(n_steps), C.c_int(step_duration),
+                                  _p(out["fl"]), _p(out["fr"]), _p(out["rl"]), _p(out["rr"]))
+    return out
+
+
+def forma_closed_loop_pred(p, st, fs_plan, fs_timing, ds, n_ticks, push=(0, 0, 0, 0.0, 0.0), solver=None,
+                           kind="auto", nwsr_cap=300):
+    """forma_closed_loop that also returns the per-tick predicted footstep (n_ticks x 2) and fsCounter (n_ticks)."""
+    L = lib(kind)
+    if solver is None:
+        solver = default_solver(kind)
+    fn = L.oracle_qpoases_solve if solver == SOLVER_QPOASES else L.oracle_qp_dual_active_set
+    if solver == SOLVER_QPOASES:
+        L.oracle_qpoases_set_nwsr(C.c_int(nwsr_cap))
+    st = np.array(st, dtype=np.float64)
+    fs_plan = np.array(fs_plan, dtype=np.float64)
+    fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
+    traj = np.zeros((n_ticks, 6)); pred = np.zeros((n_ticks, 2)); fsc = np.zeros(n_ticks, dtype=np.int32)
+    wsr = C.c_int(0)
+    L.oracle_forma_closed_loop2.restype = C.c_int
+    fails = L.oracle_forma_closed_loop2(C.byref(p), fn, _p(st), _p(fs_plan), C.c_int(fs_plan.shape[0]),
+                                        _p(fs_timing, C.c_int), C.c_int(len(fs_timing)), C.c_int(ds),
+                                        C.c_int(n_ticks), C.c_int(push[0]), C.c_int(push[1]), C.c_int(push[2]),
+                                        C.c_double(push[3]), C.c_double(push[4]), _p(traj), C.byref(wsr),
+                                        _p(pred), _p(fsc, C.c_int))
+    return traj, fails, pred, fsc, fs_plan
+
+
 def forma_closed_loop(p, st, fs_plan, fs_timing, ds, n_ticks, push=(0, 0, 0, 0.0, 0.0), solver=None,
                       kind="auto", nwsr_cap=300):
     """MATLAB closed loop (QP-1 only). Returns traj (n_ticks x 6: x,y,xd,yd,xz,yz), fails, nwsr_total, final plan."""

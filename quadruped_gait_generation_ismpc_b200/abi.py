@@ -30,13 +30,20 @@ FORMA_OUT = np.dtype([("st", "f8", 6), ("pred_fs", "f8", 2 * MAX_FSTEPS), ("kkt_
 PUSH = np.dtype([("fs", "i4"), ("ct0", "i4"), ("ct1", "i4"), ("reserved", "i4"),
                  ("ax", "f8"), ("ay", "f8")], align=True)
 
+FEET_MODEL = np.dtype([("disp_forw", "f8"), ("disp_i", "f8"), ("disp_o", "f8"), ("disp_forw_dummy", "f8"),
+                       ("disp_i_dummy", "f8"), ("disp_o_dummy", "f8"), ("gait", "i4"), ("wrap_counter", "i4")], align=True)
+FEET_INST = np.dtype([("phi", "f8"), ("j", "i4"), ("fs_counter", "i4"), ("timing_first", "i4"), ("n_timing", "i4"),
+                      ("plan_first_row", "i4"), ("plan_rows", "i4")], align=True)
+GAIT_TROT, GAIT_WALK = 0, 1
+
 SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
          "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
-         "ismpc_forma_out_t": 192, "ismpc_push_t": 32}
+         "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32}
 DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
           "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
           "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
-          "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH}
+          "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH, "ismpc_feet_model_t": FEET_MODEL,
+          "ismpc_feet_inst_t": FEET_INST}
 
 # status bits
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
@@ -61,4 +68,14 @@ def forma_model(dt=0.01, g_eta=9.8, q_zdot=1.0, q_foot=1e7, disp_forw=0.5, disp_
     m["dt"], m["g_eta"], m["q_zdot"], m["q_foot"] = dt, g_eta, q_zdot, q_foot
     m["disp_forw"], m["disp_forw_dummy"], m["disp_L"] = disp_forw, disp_forw_dummy, disp_L
     m["C"], m["P"], m["F"] = C, P, F
+    return m
+
+
+def feet_model(gait, disp_forw=0.5, disp_i=0.4, disp_o=0.4, wrap_counter=0):
+    """Reference constants: trotting/init_quadruped.m:31-36 == walking/init_quadruped2.m:31-36."""
+    m = np.zeros(1, dtype=FEET_MODEL)
+    m["disp_forw"], m["disp_i"], m["disp_o"] = disp_forw, disp_i, disp_o
+    m["disp_forw_dummy"], m["disp_i_dummy"], m["disp_o_dummy"] = disp_forw / 2, disp_i / 2, disp_o / 2
+    m["gait"] = GAIT_TROT if gait in ("trot", GAIT_TROT) else GAIT_WALK
+    m["wrap_counter"] = wrap_counter
     return m

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libismpc_b200.so")
 EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy", "ismpc_last_cuda_error",
            "ismpc_kernel_launches", "ismpc_formc_set_model", "ismpc_formc_solve_batch", "ismpc_formc_rollout",
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
-           "ismpc_measure_fp64_peak", "ismpc_set_option"]
+           "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
+           "ismpc_feet_export"]
 
 _lib = None
 
@@ -59,6 +60,9 @@ def lib():
     L.ismpc_forma_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_forma_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_forma_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_forma_rollout_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    L.ismpc_feet_place_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ismpc_feet_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
     L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
     _lib = L
     return L
@@ -196,6 +200,43 @@ class Handle:
                                          abi.MEM_HOST, None)
         self._check(rc, "ismpc_forma_rollout")
         return dict(inst=inst, fs_plan=fs_plan, traj=traj, status=status)
+
+    def forma_rollout_pred(self, inst, fs_timing, fs_plan, n_ticks, push=None):
+        """forma_rollout that also returns the per-tick predicted footstep (n x n_ticks x 2) for the feet stage."""
+        n = len(inst)
+        inst = inst.copy()
+        fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
+        fs_plan = np.array(fs_plan, dtype=np.float64)
+        traj = np.zeros((n, n_ticks, 6)); pred = np.zeros((n, n_ticks, 2))
+        status = np.zeros(n, dtype=np.int32)
+        rc = self._L.ismpc_forma_rollout_ex(self._h, n, n_ticks, _ptr(inst), _ptr(fs_timing), len(fs_timing),
+                                            _ptr(fs_plan), fs_plan.shape[0], _ptr(push), _ptr(traj), _ptr(pred),
+                                            _ptr(status), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_forma_rollout_ex")
+        return dict(inst=inst, fs_plan=fs_plan, traj=traj, pred=pred, status=status)
+
+    # ---- real-foot placement and export ------------------------------------------------------------
+    def feet_place_rollout(self, model, finst, fs_timing, pred, foot_plan):
+        """foot_plan: (total_rows x 8) float64, returned updated."""
+        n, n_ticks = pred.shape[0], pred.shape[1]
+        fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
+        pred = np.ascontiguousarray(pred, dtype=np.float64)
+        foot_plan = np.array(foot_plan, dtype=np.float64)
+        rc = self._L.ismpc_feet_place_rollout(self._h, n, n_ticks, _ptr(model), _ptr(finst), _ptr(fs_timing),
+                                              len(fs_timing), _ptr(pred), _ptr(foot_plan), foot_plan.shape[0],
+                                              abi.MEM_HOST, None)
+        self._check(rc, "ismpc_feet_place_rollout")
+        return foot_plan
+
+    def feet_export(self, model, finst, foot_plan, n_steps, fixed, swing):
+        n = len(finst)
+        foot_plan = np.ascontiguousarray(foot_plan, dtype=np.float64)
+        out = {k: np.zeros((n, n_steps * (fixed + swing), 3)) for k in ("fl", "fr", "rl", "rr")}
+        rc = self._L.ismpc_feet_export(self._h, n, _ptr(model), _ptr(finst), _ptr(foot_plan), foot_plan.shape[0], n_steps,
+                                       fixed, swing, _ptr(out["fl"]), _ptr(out["fr"]), _ptr(out["rl"]), _ptr(out["rr"]),
+                                       abi.MEM_HOST, None)
+        self._check(rc, "ismpc_feet_export")
+        return out
 
     def forma_rollout_raw(self, n, n_ticks, inst, fs_timing, timing_len, fs_plan, plan_rows, push=None, traj=None,
                           status=None, mem=abi.MEM_DEVICE, stream=None):

@@ -42,6 +42,7 @@ struct ismpc_handle {
     DevBuf s_state, s_walk, s_cinst, s_cout, s_plan, s_primal, s_active, s_push, s_traj, s_status;
     DevBuf s_ainst, s_aout, s_timing, a_Lwork, a_queue;
     DevBuf q_in, q_out, q_work;
+    DevBuf s_pred, f_inst, f_plan, f_out;
 };
 
 static int fail_cuda(ismpc_handle* h, cudaError_t e, const char* where)
@@ -92,7 +93,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
     cudaSetDevice(h->device);
     DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
-                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work};
+                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
     delete h;
     return ISMPC_OK;
@@ -277,7 +278,7 @@ extern "C" int ismpc_forma_set_model(ismpc_handle* h, const ismpc_forma_model_t*
 static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc_forma_inst_t* inst,
                         const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
                         const ismpc_push_t* push, ismpc_forma_out_t* out, double* primal_opt, int8_t* active_opt,
-                        double* traj_opt, int32_t* status_opt, int mem, void* stream)
+                        double* traj_opt, double* pred_opt, int32_t* status_opt, int mem, void* stream)
 {
     if (!h) return ISMPC_ERR_ARG;
     if (!h->forma_ready) return ISMPC_ERR_MODEL;
@@ -299,7 +300,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     if (mem == ISMPC_MEM_DEVICE) {
         a.inst = inst; a.fs_timing = fs_timing; a.fs_plan = fs_plan; a.out = out; a.primal = primal_opt;
         a.active = (signed char*)active_opt;
-        int rc = rollout ? forma_rollout_launch(a, lp, inst, fs_plan, push, n_ticks, traj_opt, status_opt, st)
+        int rc = rollout ? forma_rollout_launch(a, lp, inst, fs_plan, push, n_ticks, traj_opt, pred_opt, status_opt, st)
                          : forma_tick_launch(a, lp, st);
         h->launches += rollout ? 2 : 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
@@ -314,6 +315,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     if (active_opt && h->s_active.ensure(mb * nV)) return ISMPC_ERR_ALLOC;
     if (push && h->s_push.ensure(mb * sizeof(ismpc_push_t))) return ISMPC_ERR_ALLOC;
     if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (pred_opt && h->s_pred.ensure((size_t)n * n_ticks * 2 * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (status_opt && h->s_status.ensure(mb * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
     CK(cudaMemcpyAsync(h->s_ainst.p, inst, n * sizeof(ismpc_forma_inst_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_timing.p, fs_timing, (size_t)timing_len * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -327,7 +329,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     if (rollout)
         rc = forma_rollout_launch(a, lp, (ismpc_forma_inst_t*)h->s_ainst.p, (double*)h->s_plan.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
-                                  traj_opt ? (double*)h->s_traj.p : nullptr,
+                                  traj_opt ? (double*)h->s_traj.p : nullptr, pred_opt ? (double*)h->s_pred.p : nullptr,
                                   status_opt ? (int32_t*)h->s_status.p : nullptr, st);
     else
         rc = forma_tick_launch(a, lp, st);
@@ -337,6 +339,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
         CK(cudaMemcpyAsync(inst, h->s_ainst.p, n * sizeof(ismpc_forma_inst_t), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(fs_plan, h->s_plan.p, (size_t)plan_rows * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (traj_opt) CK(cudaMemcpyAsync(traj_opt, h->s_traj.p, (size_t)n * n_ticks * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (pred_opt) CK(cudaMemcpyAsync(pred_opt, h->s_pred.p, (size_t)n * n_ticks * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (status_opt) CK(cudaMemcpyAsync(status_opt, h->s_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     } else {
         CK(cudaMemcpyAsync(out, h->s_aout.p, n * sizeof(ismpc_forma_out_t), cudaMemcpyDeviceToHost, st));
@@ -353,7 +356,7 @@ extern "C" int ismpc_forma_solve_batch(ismpc_handle* h, int n, const ismpc_forma
 {
     return forma_common(h, n, 1, false, const_cast<ismpc_forma_inst_t*>(inst), fs_timing, timing_len,
                         const_cast<double*>(fs_plan), plan_rows, nullptr, out, primal_opt, active_opt, nullptr,
-                        nullptr, mem, stream);
+                        nullptr, nullptr, mem, stream);
 }
 
 extern "C" int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
@@ -362,7 +365,98 @@ extern "C" int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_fo
                                    void* stream)
 {
     return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
-                        nullptr, traj_opt, status_opt, mem, stream);
+                        nullptr, traj_opt, nullptr, status_opt, mem, stream);
+}
+
+extern "C" int ismpc_forma_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                                      const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
+                                      const ismpc_push_t* push, double* traj_opt, double* pred_traj_opt,
+                                      int32_t* status_opt, int mem, void* stream)
+{
+    return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
+                        nullptr, traj_opt, pred_traj_opt, status_opt, mem, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Real-foot placement and trajectory export
+// ---------------------------------------------------------------------------------------------------
+static bool feet_model_ok(const ismpc_feet_model_t* m)
+{
+    return m && (m->gait == ISMPC_GAIT_TROT || m->gait == ISMPC_GAIT_WALK);
+}
+
+extern "C" int ismpc_feet_place_rollout(ismpc_handle* h, int n, int n_ticks, const ismpc_feet_model_t* model,
+                                        const ismpc_feet_inst_t* inst, const int32_t* fs_timing, int timing_len,
+                                        const double* pred_traj, double* foot_plan, int foot_plan_rows, int mem,
+                                        void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!feet_model_ok(model)) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || n_ticks < 0 || !inst || !fs_timing || timing_len <= 0 || !pred_traj || !foot_plan ||
+        foot_plan_rows <= 0)
+        return ISMPC_ERR_ARG;
+    if (n == 0 || n_ticks == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = feet_place_launch(n, n_ticks, *model, inst, fs_timing, pred_traj, foot_plan, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_place_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t bi = (size_t)n * sizeof(ismpc_feet_inst_t), bt = (size_t)timing_len * sizeof(int32_t);
+    const size_t bp = (size_t)n * n_ticks * 2 * sizeof(double), bf = (size_t)foot_plan_rows * 8 * sizeof(double);
+    if (h->f_inst.ensure(bi) || h->s_timing.ensure(bt) || h->s_pred.ensure(bp) || h->f_plan.ensure(bf)) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->f_inst.p, inst, bi, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_timing.p, fs_timing, bt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_pred.p, pred_traj, bp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->f_plan.p, foot_plan, bf, cudaMemcpyHostToDevice, st));
+    int rc = feet_place_launch(n, n_ticks, *model, (const ismpc_feet_inst_t*)h->f_inst.p, (const int32_t*)h->s_timing.p,
+                               (const double*)h->s_pred.p, (double*)h->f_plan.p, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_place_launch");
+    CK(cudaMemcpyAsync(foot_plan, h->f_plan.p, bf, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_t* model, const ismpc_feet_inst_t* inst,
+                                 const double* foot_plan, int foot_plan_rows, int n_steps, int fixed, int swing,
+                                 double* fl, double* fr, double* rl, double* rr, int mem, void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!feet_model_ok(model)) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || !inst || !foot_plan || foot_plan_rows <= 0 || n_steps < 0 || fixed < 0 || swing <= 0 ||
+        !fl || !fr || !rl || !rr)
+        return ISMPC_ERR_ARG;
+    if (n == 0 || n_steps == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = feet_export_launch(n, *model, inst, foot_plan, n_steps, fixed, swing, fl, fr, rl, rr, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_export_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t bi = (size_t)n * sizeof(ismpc_feet_inst_t), bf = (size_t)foot_plan_rows * 8 * sizeof(double);
+    const size_t bo = (size_t)n * n_steps * (fixed + swing) * 3 * sizeof(double);
+    if (h->f_inst.ensure(bi) || h->f_plan.ensure(bf) || h->f_out.ensure(4 * bo)) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->f_inst.p, inst, bi, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->f_plan.p, foot_plan, bf, cudaMemcpyHostToDevice, st));
+    double* o = (double*)h->f_out.p;
+    const size_t od = bo / sizeof(double);
+    int rc = feet_export_launch(n, *model, (const ismpc_feet_inst_t*)h->f_inst.p, (const double*)h->f_plan.p, n_steps,
+                                fixed, swing, o, o + od, o + 2 * od, o + 3 * od, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_export_launch");
+    CK(cudaMemcpyAsync(fl, o, bo, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(fr, o + od, bo, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(rl, o + 2 * od, bo, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(rr, o + 3 * od, bo, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

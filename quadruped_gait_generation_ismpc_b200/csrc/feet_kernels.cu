@@ -1,0 +1,173 @@
+// feet_kernels.cu -- the stage after the hot path: real-foot placement (the MATLAB scripts' "SECOND QUAD_PROG")
+// and the foot-trajectory export in the layout the reference's Controller reads.
+//
+// Reference map:
+//   trotting/compute_two_feet1.m:5-16, walking/compute_one_feet_walk.m:99-116  -> diag_offset()
+//   trotting/quad_as_bip_no_plots.m:332-426                                    -> feet_trot_tick()
+//   walking/quad_walk_no_plots.m:334-504                                       -> feet_walk_tick()
+//   trotting/quad_as_bip_no_plots.m:482-509, walking/quad_walk_no_plots.m:563-613 -> feet_export_kernel
+// The work per tick is a handful of scalar operations with a data-dependent update of the instance's foot plan, and
+// ticks are sequential: one thread per instance walks its ticks; instances are independent.  The export is one thread
+// per (instance, sample).
+#include "common.cuh"
+#include "launch.h"
+
+namespace ismpc {
+
+#define FP(r, c) fp[(size_t)((r) - 1) * 8 + ((c) - 1)]   // MATLAB 1-based foot_plan(r,c)
+
+// Line through the two fixed feet, line of opposite slope through the ZMP, offset of the ZMP from their intersection.
+__device__ __forceinline__ bool diag_offset(const double fixed[4], double zx, double zy, double& m, double& dx, double& dy)
+{
+    m = (fixed[3] - fixed[1]) / (fixed[2] - fixed[0]);
+    const double q = fixed[1] - m * fixed[0];
+    if (!(fabs(m) > 0.0) || !isfinite(m)) { dx = 0.0; dy = 0.0; return false; }   // no intersection: nothing changes
+    const double xs = (zy + m * zx - q) / (2.0 * m);
+    const double ys = m * xs + q;
+    dx = zx - xs; dy = zy - ys;
+    return true;
+}
+
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ inline void feet_trot_tick(const ismpc_feet_model_t& p, int fs, double zx, double zy, double phi, double* fp, int rows)
+{
+    if (fs < 1 || fs + 1 > rows) return;
+    const bool odd = (fs % 2) == 1;
+    const int fc1 = odd ? 3 : 1, fc2 = odd ? 7 : 5;     // feet that stay (x columns, row fs)
+    const int mc1 = odd ? 1 : 3, mc2 = odd ? 5 : 7;     // feet that move (x columns, row fs+1)
+    const double fixed[4] = {FP(fs, fc1), FP(fs, fc1 + 1), FP(fs, fc2), FP(fs, fc2 + 1)};
+    const double fr0 = FP(fs + 1, mc1), fr1 = FP(fs + 1, mc1 + 1), fr2 = FP(fs + 1, mc2), fr3 = FP(fs + 1, mc2 + 1);
+    double m, dx, dy;
+    if (diag_offset(fixed, zx, zy, m, dx, dy)) {
+        double x1, y1, x2, y2;
+        if (phi == 3.14159265358979323846 / 2) {          // compute_two_feet1.m:19-25
+            x1 = fr0; x2 = fr2;
+            y1 = zy - m * (x1 - zx); y2 = zy - m * (x2 - zx);
+        } else {                                          // :26-37
+            const double t = tan(phi);
+            x1 = (zy + m * zx + t * fr0 - fr1) / (t + m); y1 = t * (x1 - fr0) + fr1;
+            x2 = (zy + m * zx + t * fr2 - fr3) / (t + m); y2 = t * (x2 - fr2) + fr3;
+        }
+        if (dy != 0.0 || dx != 0.0) {                     // foot_plan(fsCounter+1,:) = quattro_piedi
+            FP(fs + 1, mc1) = x1; FP(fs + 1, mc1 + 1) = y1; FP(fs + 1, mc2) = x2; FP(fs + 1, mc2 + 1) = y2;
+            FP(fs + 1, fc1) = fixed[0]; FP(fs + 1, fc1 + 1) = fixed[1]; FP(fs + 1, fc2) = fixed[2]; FP(fs + 1, fc2 + 1) = fixed[3];
+        }
+    }
+    const bool dummy = odd && fs == 1;
+    const double d_o = dummy ? p.disp_o_dummy : p.disp_o, d_i = dummy ? p.disp_i_dummy : p.disp_i;
+    const double d_f = dummy ? p.disp_forw_dummy : p.disp_forw;
+    const int a = odd ? 1 : 7, b = odd ? 5 : 3;
+    const double X1 = fmin(FP(fs + 1, a), FP(fs, a) + d_f);
+    const double X2 = clipd(FP(fs + 1, a + 1), FP(fs, a + 1) - d_i, FP(fs, a + 1) + d_o);
+    const double X3 = fmin(FP(fs + 1, b), FP(fs, b) + d_f);
+    const double X4 = clipd(FP(fs + 1, b + 1), FP(fs, b + 1) - d_o, FP(fs, b + 1) + d_i);
+    FP(fs + 1, a) = X1; FP(fs + 1, a + 1) = X2; FP(fs + 1, b) = X3; FP(fs + 1, b + 1) = X4;
+}
+
+__device__ inline void feet_walk_tick(const ismpc_feet_model_t& p, int counter, int fs, double zx, double zy, double* fp, int rows)
+{
+    if (counter != 2 && counter != 4 && counter != 6 && counter != 8) return;
+    if (fs < 1 || fs + 8 > rows) return;
+    const int d1 = (counter <= 4) ? 1 : 3, d2 = (counter <= 4) ? 5 : 7;
+    const int mc = counter == 2 ? 7 : counter == 4 ? 3 : counter == 6 ? 5 : 1;
+    const double fixed[4] = {FP(fs, d1), FP(fs, d1 + 1), FP(fs, d2), FP(fs, d2 + 1)};
+    double m, dx, dy;
+    if (diag_offset(fixed, zx, zy, m, dx, dy)) {
+        const double xf = FP(fs + 1, mc) + dx, yf = FP(fs + 1, mc + 1) + dy;
+        if (dy != 0.0 || dx != 0.0) for (int l = 1; l <= 8; ++l) { FP(fs + l, mc) = xf; FP(fs + l, mc + 1) = yf; }
+    }
+    const bool dummy = (counter <= 4) && fs <= 4;
+    const double d_o = dummy ? p.disp_o_dummy : p.disp_o, d_i = dummy ? p.disp_i_dummy : p.disp_i;
+    const double d_f = dummy ? p.disp_forw_dummy : p.disp_forw;
+    const bool left = (counter == 2 || counter == 8);
+    const double up = left ? d_o : d_i, dn = left ? d_i : d_o;
+    const double X1 = fmin(FP(fs + 1, mc), FP(fs, mc) + d_f);
+    const double X2 = clipd(FP(fs + 1, mc + 1), FP(fs, mc + 1) - dn, FP(fs, mc + 1) + up);
+    for (int l = 1; l <= 8; ++l) {
+        FP(fs + l, mc) = X1;
+        if (counter != 8 || l == 1) FP(fs + l, mc + 1) = X2;     // quad_walk_no_plots.m:500-503, copied as written
+    }
+}
+
+__global__ void feet_place_kernel(int n, int n_ticks, ismpc_feet_model_t mdl, const ismpc_feet_inst_t* inst,
+                                  const int32_t* fs_timing, const double* pred_traj, double* foot_plan)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ismpc_feet_inst_t in = inst[i];
+    const int32_t* ft = fs_timing + in.timing_first;
+    double* fp = foot_plan + (size_t)in.plan_first_row * 8;
+    int j = in.j, fsc = in.fs_counter;
+    int counter = fsc;                                   // both start at 1 and advance together (quad_walk_no_plots.m:526-527)
+    if (mdl.wrap_counter) counter = (fsc - 1) % 8 + 1;
+    for (int t = 0; t < n_ticks; ++t) {
+        const double zx = pred_traj[((size_t)i * n_ticks + t) * 2], zy = pred_traj[((size_t)i * n_ticks + t) * 2 + 1];
+        if (mdl.gait == ISMPC_GAIT_TROT) feet_trot_tick(mdl, fsc, zx, zy, in.phi, fp, in.plan_rows);
+        else feet_walk_tick(mdl, counter, fsc, zx, zy, fp, in.plan_rows);
+        if (fsc + 1 <= in.n_timing && j + 1 >= ft[fsc]) {
+            fsc += 1;
+            counter = mdl.wrap_counter ? (counter == 8 ? 1 : counter + 1) : counter + 1;
+        }
+        j += 1;
+    }
+}
+
+__global__ void feet_export_kernel(int n, ismpc_feet_model_t mdl, const ismpc_feet_inst_t* inst, const double* foot_plan,
+                                   int n_steps, int fixed, int swing, double* fl, double* fr, double* rl, double* rr)
+{
+    const int per = fixed + swing;
+    const long long total = (long long)n * n_steps * per;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int i = (int)(gid / ((long long)n_steps * per));
+    const int k = (int)(gid - (long long)i * n_steps * per);
+    const int step = k / per + 1, s = k - (step - 1) * per + 1;        // 1-based step and sample within the step
+    const ismpc_feet_inst_t in = inst[i];
+    const double* fp = foot_plan + (size_t)in.plan_first_row * 8;
+    double* dst[4] = {rl, rr, fr, fl};
+    int mvA = 0, mvB = 0, kk = 0;                                       // x columns of the swinging feet, swing sample index
+    if (step + 1 <= in.plan_rows) {
+        if (mdl.gait == ISMPC_GAIT_TROT) {
+            if (s > fixed) { kk = s - fixed; if (step % 2 == 1) { mvA = 1; mvB = 5; } else { mvA = 7; mvB = 3; } }
+        } else {
+            const int c = (step - 1) % 8 + 1;                           // conteggio
+            kk = s;
+            mvA = c == 2 ? 7 : c == 4 ? 3 : c == 6 ? 5 : c == 8 ? 1 : 0;
+        }
+    }
+    const double z = -0.000032 * kk * kk + 0.0016 * kk;
+    for (int f = 0; f < 4; ++f) {
+        const int c = 2 * f + 1;
+        double x = 0.0, y = 0.0, zz = 0.0;
+        if (step + 1 <= in.plan_rows) {
+            x = FP(step, c); y = FP(step, c + 1);
+            if (c == mvA || c == mvB) {
+                x = FP(step, c) + (FP(step + 1, c) - FP(step, c)) / swing * kk;
+                y = FP(step, c + 1) + (FP(step + 1, c + 1) - FP(step, c + 1)) / swing * kk;
+                zz = z;
+            }
+        }
+        double* o = dst[f] + (size_t)gid * 3;
+        o[0] = x; o[1] = y; o[2] = zz;
+    }
+}
+#undef FP
+
+int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const int32_t* fs_timing,
+                      const double* pred_traj, double* foot_plan, cudaStream_t st)
+{
+    feet_place_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, n_ticks, m, inst, fs_timing, pred_traj, foot_plan);
+    return (int)cudaGetLastError();
+}
+
+int feet_export_launch(int n, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const double* foot_plan, int n_steps,
+                       int fixed, int swing, double* fl, double* fr, double* rl, double* rr, cudaStream_t st)
+{
+    const long long total = (long long)n * n_steps * (fixed + swing);
+    if (total <= 0) return 0;
+    feet_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, m, inst, foot_plan, n_steps, fixed, swing, fl, fr, rl, rr);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ismpc

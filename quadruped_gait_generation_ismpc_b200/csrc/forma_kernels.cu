@@ -77,6 +77,7 @@ struct FormARolloutArgs {
     const ismpc_push_t* push;
     int n_ticks;
     double* traj;
+    double* pred;          // nullable, n x n_ticks x 2: predicted footstep handed to the second QP
     int32_t* status;
 };
 
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_roll
             forma_integrate(eta, a.model.dt, s3, zd0);
             if (ra.traj && lane < 3)
                 ra.traj[((size_t)inst * ra.n_ticks + tick) * 6 + 2 * lane + axis] = s3[lane];   // x,y,xd,yd,xz,yz
+            if (ra.pred && lane == 0) ra.pred[((size_t)inst * ra.n_ticks + tick) * 2 + axis] = pred;
             ct += 1;
             bool switched = false;
             if (fsc + 1 <= in.n_timing && j + 1 >= ft[fsc]) {                                  // bang.m:529
@@ -215,8 +217,8 @@ int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStrea
 }
 
 int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_forma_inst_t* inst_io,
-                         double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status,
-                         cudaStream_t st)
+                         double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, double* pred,
+                         int32_t* status, cudaStream_t st)
 {
     FormAArgs a = a_in;
     a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = p.warm_start;
@@ -225,7 +227,7 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
-    FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, status};
+    FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status};
     kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
     forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing);
     return (int)cudaGetLastError();

@@ -21,8 +21,12 @@ struct FormALaunchPlan { int R, warps_per_cta, grid, use_pdas, warm_start; size_
 void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p);
 int forma_tick_launch(const FormAArgs& a, const FormALaunchPlan& p, cudaStream_t st);
 int forma_rollout_launch(const FormAArgs& a, const FormALaunchPlan& p, ismpc_forma_inst_t* inst_io,
-                         double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status,
-                         cudaStream_t st);
+                         double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, double* pred,
+                         int32_t* status, cudaStream_t st);
+int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst,
+                      const int32_t* fs_timing, const double* pred_traj, double* foot_plan, cudaStream_t st);
+int feet_export_launch(int n, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const double* foot_plan,
+                       int n_steps, int fixed, int swing, double* fl, double* fr, double* rl, double* rr, cudaStream_t st);
 
 int qp_dense_launch(int n, int nV, int nC, const double* H, const double* g, const double* A, const double* lbA,
                     const double* ubA, double* x, double* y, signed char* ws, int32_t* status, int32_t* iters,
