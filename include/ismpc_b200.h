@@ -22,7 +22,10 @@
  * void* (NULL = default stream).  With ISMPC_MEM_DEVICE every data pointer is a device pointer, the
  * call only enqueues work on `stream` and returns; with ISMPC_MEM_HOST every data pointer is a host
  * pointer (pinned for best speed), the call copies in, launches, copies out and synchronises the
- * stream before returning.  The caller owns all buffers; the handle owns only its workspace.  One
+ * stream before returning; ISMPC_MEM_HOST_ASYNC (ismpc_formc_solve_batch only) is the same without the final
+ * synchronisation: the call returns as soon as the copies and the kernel are enqueued, the host buffers must be
+ * pinned and stay untouched, and the handle must not be used again, until the caller has synchronised `stream` --
+ * two handles on two streams give a double-buffered pipeline.  The caller owns all buffers; the handle owns only its workspace.  One
  * handle per GPU, not shared between threads.  Functions return 0 or a negative ISMPC_ERR_* code;
  * per-instance problems are reported in out[i].status -- the library never calls exit().
  * There is no CPU fallback: every entry point fails with ISMPC_ERR_CUDA if no sm_100 device works.
@@ -46,7 +49,7 @@ enum {
     ISMPC_ERR_ALLOC = -4
 };
 
-enum { ISMPC_MEM_HOST = 0, ISMPC_MEM_DEVICE = 1 };
+enum { ISMPC_MEM_HOST = 0, ISMPC_MEM_DEVICE = 1, ISMPC_MEM_HOST_ASYNC = 2 };
 
 /* per-instance status bits (out[i].status) */
 enum {

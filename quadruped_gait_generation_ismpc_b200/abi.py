@@ -49,7 +49,7 @@ DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": F
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
 ST_GI_FALLBACK = 128    # informational: form-A result came from the dual active-set fallback
 ST_FAIL_MASK = ST_Z_FAIL | ST_X_FAIL | ST_Y_FAIL | ST_WINDOW | ST_QP_FAIL
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 
 
 def formc_model(dt=0.01, dtc=0.01, mass=50.0, g=9.81, q_p=1005000.0, q_v=100.0, q_u=0.01,

@@ -183,7 +183,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
         return ISMPC_OK;
     }
-    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
     const size_t mb = (size_t)h->max_batch;
     if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
         h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t)) ||
@@ -206,7 +206,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     CK(cudaMemcpyAsync(out, h->s_cout.p, n * sizeof(ismpc_formc_out_t), cudaMemcpyDeviceToHost, st));
     if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * 3 * N, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (mem == ISMPC_MEM_HOST) CK(cudaStreamSynchronize(st));
     return ISMPC_OK;
 }
 
