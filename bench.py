@@ -167,6 +167,7 @@ def main():
     h = binding.Handle(device=local, max_batch=max(n, 8192))
     model = abi.formc_model(N=HORIZON)
     h.formc_set_model(model)
+    h.formc_prepare_gait(35, 10)          # parameters.cpp:43-44 (device-resident calls cannot read the gait themselves)
 
     # ---- inputs: distinct batches rotating over a footprint larger than L2 -------------------------------
     seeds = [synth.SEED0 ^ 2 ^ (rank * 7919 + s) for s in range(4)]
@@ -256,7 +257,7 @@ def main():
     DEPTH = 2
     pipe = []
     for s_ in range(DEPTH):
-        hh = binding.Handle(device=local, max_batch=max(n, 1024)); hh.formc_set_model(model)
+        hh = binding.Handle(device=local, max_batch=max(n, 1024)); hh.formc_set_model(model); hh.formc_prepare_gait(35, 10)
         pipe.append({"h": hh, "stream": torch.cuda.Stream(device=dev), "out": torch.zeros(d2h, dtype=torch.uint8).pin_memory()})
     checksum = [0]
 
@@ -338,7 +339,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["form_a"] = {"error": repr(e)}
         try:
-            h.formc_set_model(model)
+            h.formc_set_model(model); h.formc_prepare_gait(35, 10)
             line["closed_loop_form_c"] = bench_formc_rollout(h, torch, dev, stream)
         except Exception as e:  # noqa: BLE001
             line["closed_loop_form_c"] = {"error": repr(e)}

@@ -184,6 +184,12 @@ int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops_out);
  * (H_z^-1 and friends) for this model.  Must be called before ismpc_formc_solve_batch. */
 int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* model);
 
+/* Optional, after ismpc_formc_set_model: declares the step timing (S single-support, F_ds double-support samples;
+ * parameters.cpp:43-44) most instances use, so that the flight-phase equalities of stage 1 (MPCSolver.cpp:223-243)
+ * are folded into one precomputed projector table per mpcIter.  Results do not change; instances with another
+ * (S, F_ds) take the generic path.  Calls with host buffers do this by themselves from the first instance. */
+int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds);
+
 /* One tick of MPCSolver::solve (MPCSolver.cpp:204-501) for n independent instances.
  * plan_xyzt: plan_rows x 4 doubles row-major (x, y, z, t) -- ftsp_and_timings (Controller.cpp:89-97).
  * primal_opt (nullable): n x 3N doubles  [f(N) | u_x(N) | u_y(N)] per instance.

@@ -17,7 +17,7 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_kernel_launches", "ismpc_formc_set_model", "ismpc_formc_solve_batch", "ismpc_formc_rollout",
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
-           "ismpc_feet_export"]
+           "ismpc_feet_export", "ismpc_formc_prepare_gait"]
 
 _lib = None
 
@@ -54,6 +54,7 @@ def lib():
     L.ismpc_destroy.argtypes = [C.c_void_p]
     L.ismpc_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ismpc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.ismpc_formc_prepare_gait.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
@@ -123,6 +124,9 @@ class Handle:
     def formc_set_model(self, model):
         self._check(self._L.ismpc_formc_set_model(self._h, _ptr(model)), "ismpc_formc_set_model")
         self.formc = model.copy()
+
+    def formc_prepare_gait(self, S, F_ds):
+        self._check(self._L.ismpc_formc_prepare_gait(self._h, int(S), int(F_ds)), "ismpc_formc_prepare_gait")
 
     def formc_solve_batch(self, state, walk, inst, plan, want_primal=True, want_active=True):
         """Host-memory call (numpy arrays in, numpy arrays out)."""

@@ -34,7 +34,8 @@ struct ismpc_handle {
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
-    DevBuf c_tables, c_work, c_info;
+    DevBuf c_tables, c_work, c_info, c_ptab;
+    int gait_S = 0, gait_F = 0;            // prepared gait (projector tables in c_ptab), 0 = none
     // form A
     bool forma_ready = false;
     ismpc_forma_model_t am{};
@@ -91,7 +92,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
 {
     if (!h) return ISMPC_ERR_ARG;
     cudaSetDevice(h->device);
-    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
@@ -134,6 +135,7 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
     CK(cudaMemcpy(&info, h->c_info.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) return ISMPC_ERR_MODEL;     // H_z not positive definite
     h->cm = *m;
+    h->gait_S = h->gait_F = 0;
     h->c_ctas_per_sm = formc_cluster_ctas_per_sm(m->N);
     h->formc_ready = true;
     return ISMPC_OK;
@@ -158,6 +160,30 @@ static void formc_fill_args(ismpc_handle* h, FormCArgs& a, int n)
     const double* T = (const double*)h->c_tables.p;
     a.n = n; a.model = h->cm;
     a.T.Hinv = T; a.T.G = T + NN; a.T.M = T + 2 * NN;
+    a.T.P = (h->gait_S + h->gait_F > 0) ? (const double*)h->c_ptab.p : nullptr;
+    a.T.gS = h->gait_S; a.T.gF = h->gait_F;
+}
+
+extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!h->formc_ready) return ISMPC_ERR_MODEL;
+    if (S < 0 || F_ds < 0 || S + F_ds <= 0 || S + F_ds > 4096) return ISMPC_ERR_ARG;
+    if (h->gait_S == S && h->gait_F == F_ds) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t NN = (size_t)h->cm.N * h->cm.N;
+    h->gait_S = h->gait_F = 0;
+    if (h->c_ptab.ensure((size_t)(S + F_ds) * NN * sizeof(double))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemset(h->c_info.p, 0, sizeof(int)));
+    int rc = formc_prepare_gait_launch(h->cm.N, S, F_ds, (const double*)h->c_tables.p, (double*)h->c_ptab.p,
+                                       (int*)h->c_info.p, 0, &h->launches);
+    if (rc == -1) return ISMPC_OK;             // block too large for shared memory: stay on the generic path
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_prepare_gait_launch");
+    int info = 0;
+    CK(cudaMemcpy(&info, h->c_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info != 0) return ISMPC_ERR_MODEL;
+    h->gait_S = S; h->gait_F = F_ds;
+    return ISMPC_OK;
 }
 
 extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state_t* state, const ismpc_walk_t* walk,
@@ -184,6 +210,11 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
+    if (h->gait_S + h->gait_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+        int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);      // host buffers: the gait can be read here
+        if (prc != ISMPC_OK) return prc;
+        formc_fill_args(h, a, n);
+    }
     const size_t mb = (size_t)h->max_batch;
     if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
         h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t)) ||
@@ -233,6 +264,11 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    if (h->gait_S + h->gait_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+        int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);
+        if (prc != ISMPC_OK) return prc;
+        formc_fill_args(h, a, n);
+    }
     const size_t mb = (size_t)h->max_batch;
     if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
         h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double)))

@@ -27,6 +27,11 @@ struct FormCTables {      // device pointers, N x N row-major each (built once p
     const double* Hinv;   // H_z^-1
     const double* G;      // S_bar_z * H_z^-1
     const double* M;      // S_bar_z * H_z^-1 * S_bar_z'
+    // Prepared gait (ismpc_formc_prepare_gait): for every mpcIter m of a step of gS + gF ticks, the projector
+    //   P_m = H^-1 - H^-1[:,K] (H^-1_KK)^-1 H^-1[K,:],   K = flight-phase columns at mpcIter m (MPCSolver.cpp:223-243),
+    // so that f = -P_m F_z is the minimiser under the equalities f_K = 0 in ONE table mat-vec.  Null if not prepared.
+    const double* P;      // (gS + gF) x N x N
+    int gS, gF;
 };
 
 struct FormCShared {      // per-CTA shared memory carve-up (all pointers into dynamic smem)
@@ -80,6 +85,44 @@ __device__ __forceinline__ double midpoint_value(const double* rows, int first, 
     return a * 1.0 + (b - a) * ((double)(r - S) / (double)F);
 }
 
+// out_k = scale * sum_{j<k} (k-j) x_j  (the S_bar_z pattern: a prefix sum of a prefix sum, shifted by one), by one warp.
+// Up to 4 elements per lane stay in registers (N <= 128); longer vectors go through the shared-memory scans.
+__device__ __forceinline__ void warp_double_prefix_shifted(const double* x, double* out, double* scr, int N, double scale)
+{
+    const int lane = lane_id();
+    int lo, hi; lane_chunk(N, lane, lo, hi);
+    if (hi - lo <= 4 && ((N + 31) >> 5) <= 4) {
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = lo + e < hi ? x[lo + e] : 0.0;
+        v[1] += v[0]; v[2] += v[1]; v[3] += v[2];                       // first-level local prefix
+        double incl = warp_incl_scan(v[3]);
+        const double off1 = incl - v[3];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] += off1;                      // P1_i for i in chunk (padding repeats the last)
+        double w[4];
+        w[0] = lo < hi ? v[0] : 0.0;
+#pragma unroll
+        for (int e = 1; e < 4; ++e) w[e] = w[e - 1] + (lo + e < hi ? v[e] : 0.0);
+        const double t2 = w[3];                                          // padding adds 0: w[3] is the chunk total
+        double incl2 = warp_incl_scan(t2);
+        const double off2 = incl2 - t2;
+        // out_k = scale * P2_{k-1}: lane writes out[i+1] for its i, out[0] = 0
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (lo + e < hi && lo + e + 1 < N) out[lo + e + 1] = scale * (w[e] + off2);
+        if (lane == 0) out[0] = 0.0;
+        __syncwarp();
+        return;
+    }
+    for (int i = lane; i < N; i += 32) scr[i] = x[i];
+    __syncwarp();
+    warp_prefix_sum_smem(scr, N);
+    warp_prefix_sum_smem(scr, N);
+    for (int i = lane; i < N; i += 32) out[i] = (i == 0) ? 0.0 : scale * scr[i - 1];
+    __syncwarp();
+}
+
 // ---- vertical QP policy for the dual active-set engine -------------------------------------------
 struct VertProb {
     int N;
@@ -93,16 +136,7 @@ struct VertProb {
     __device__ double hi(int) const { return fzmax; }
     __device__ void on_step(double) const {}
     // rv_k = (S_bar_z x)_k = c1 * sum_{j<k} (k-j) x_j  -> two prefix sums
-    __device__ void eval(const double* x, double* rv) const
-    {
-        const int lane = lane_id();
-        for (int i = lane; i < N; i += 32) scr[i] = x[i];
-        __syncwarp();
-        warp_prefix_sum_smem(scr, N);
-        warp_prefix_sum_smem(scr, N);
-        for (int i = lane; i < N; i += 32) rv[i] = (i == 0) ? 0.0 : c1 * scr[i - 1];
-        __syncwarp();
-    }
+    __device__ void eval(const double* x, double* rv) const { warp_double_prefix_shifted(x, rv, scr, N, c1); }
     __device__ double schur(int a, int b) const
     {
         if (a < N) return (b < N) ? T.M[(size_t)a * N + b] : T.G[(size_t)a * N + (b - N)];
@@ -124,11 +158,19 @@ struct VertProb {
 };
 
 // Exact solve of   min 1/2|u|^2 - mid'u   s.t.  a'u = b,  mid-rho <= u <= mid+rho   by one warp.
-// u_i = mid_i + clip(nu*a_i, -rho, rho); Newton on the piecewise-linear monotone residual in nu, which is
-// the scalar-Schur-complement active-set iteration for this structure (H = I, A = [a'; I]): every pass adds
-// all newly saturated rows at once; |nu| grows monotonically, so it terminates in <= N passes.
-// Returns status (0 ok, 1 infeasible), *nu_out, *iters.
-__device__ inline int knapsack_qp(int N, const double* a, const double* mid, double rho, double b,
+// u_i = mid_i + clip(nu*a_i, -rho, rho); the equality residual is an odd, monotone, piecewise-linear function of nu
+// (the scalar-Schur-complement view of the active-set method for this structure: H = I, A = [a'; I]).
+//  * Direct path: the stability row decays along the horizon (with exact zeros on flight-phase ticks, where B = 0),
+//    so the saturated rows are a PREFIX [0,k).  With P1 = prefix sums of |a| and S2 = suffix sums of a^2 every k has
+//    the closed-form candidate t_k = (|r| - rho P1(k)) / S2(k); the one whose own saturation pattern is exactly that
+//    prefix is the solution (checked, not assumed).
+//    One pass, independent of how many rows saturate (a Newton pass per saturated row otherwise: the slowest QP of
+//    a batch used to set the batch tick time).
+//  * Fallback (no candidate is self-consistent, i.e. the saturated set is not a prefix): Newton on the multiplier; every pass adds all newly saturated rows, |nu| grows
+//    monotonically, so it terminates in <= N passes.
+// s1, s2: two scratch vectors [N] in shared memory owned by this warp.
+// Returns status (0 ok, 1 infeasible), *nu_out, *iters (number of saturated rows / Newton passes - 1).
+__device__ inline int knapsack_qp(int N, const double* a, const double* mid, double rho, double b, double* s1, double* s2,
                                   double* nu_out, int* iters_out, double* resid_out)
 {
     const int lane = lane_id();
@@ -140,24 +182,82 @@ __device__ inline int knapsack_qp(int N, const double* a, const double* mid, dou
     const double rabs = fabs(r);
     int status = 0, iters = 0;
     double t = 0.0;           // |nu|
-    int nsat_prev = -1;
     if (aa > 0.0) {
-        t = rabs / aa;
-        for (;;) {
-            double s1 = 0.0, s2 = 0.0; int ns = 0;
-            for (int i = lane; i < N; i += 32) {
-                double ai = fabs(a[i]);
-                if (t * ai > rho) { s1 += ai; ++ns; } else s2 += ai * ai;
+        bool solved = false;
+        {
+            // Candidate k: rows [0,k) saturated (those with a_i = 0 never are and add nothing to either sum).
+            //   P1(k) = sum_{i<k} |a_i|,  S2(k) = sum_{i>=k} a_i^2,  t_k = (|r| - rho P1(k)) / S2(k)
+            // is THE solution iff its own saturation pattern is that prefix:
+            //   t_k * min{|a_i| : i < k, a_i != 0} > rho   and   t_k * max{|a_i| : i >= k} <= rho.
+            // Prefix quantities are laid down per k in an ascending sweep of the lane's chunk (s1, s2), suffix
+            // quantities accumulate in the descending sweep that tests the candidates (small terms first).
+            int lo, hi; lane_chunk(N, lane, lo, hi);
+            const double INF = 1e300;
+            double t1 = 0.0, t2 = 0.0, mn = INF, mx = 0.0;
+            for (int i = lo; i < hi; ++i) {
+                const double ai = fabs(a[i]);
+                t1 += ai; t2 += ai * ai; mx = fmax(mx, ai);
+                if (ai > 0.0) mn = fmin(mn, ai);
             }
-            s1 = warp_sum(s1); s2 = warp_sum(s2); ns = warp_sum_int(ns);
-            if (ns == nsat_prev) break;
-            nsat_prev = ns; ++iters;
-            double rem = rabs - rho * s1;
-            if (!(s2 > 0.0)) { if (rem > 1e-12 * fmax(1.0, rabs)) status = 1; break; }
-            double tn = rem / s2;
-            if (!(tn >= t)) tn = t;   // monotone guard against round-off
-            t = tn;
-            if (iters > N + 2) break;
+            double p1 = t1, sf = t2, pm = mn, sm_ = mx;      // inclusive scans across lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double a1 = __shfl_up_sync(ISMPC_FULL_MASK, p1, o), a3 = __shfl_up_sync(ISMPC_FULL_MASK, pm, o);
+                const double a2 = __shfl_down_sync(ISMPC_FULL_MASK, sf, o), a4 = __shfl_down_sync(ISMPC_FULL_MASK, sm_, o);
+                if (lane >= o) { p1 += a1; pm = fmin(pm, a3); }
+                if (lane + o < 32) { sf += a2; sm_ = fmax(sm_, a4); }
+            }
+            double P1 = p1 - t1;                                                       // exclusive prefix sum
+            double Lm = __shfl_up_sync(ISMPC_FULL_MASK, pm, 1); if (lane == 0) Lm = INF;    // exclusive prefix min
+            double S2 = sf - t2;                                                       // exclusive suffix sum
+            double Mx = __shfl_down_sync(ISMPC_FULL_MASK, sm_, 1); if (lane == 31) Mx = 0.0; // exclusive suffix max
+            for (int k = lo; k < hi; ++k) {
+                s1[k] = P1; s2[k] = Lm;
+                const double ak = fabs(a[k]);
+                P1 += ak; if (ak > 0.0) Lm = fmin(Lm, ak);
+            }
+            int kbest = 0x7fffffff; double tbest = 0.0;
+            for (int k = hi - 1; k >= lo; --k) {
+                const double ak = fabs(a[k]);
+                S2 += ak * ak; Mx = fmax(Mx, ak);
+                if (!(S2 > 0.0)) continue;
+                const double tk = (rabs - rho * s1[k]) / S2;
+                const double lm = s2[k];
+                const bool left = !(lm < INF) || (tk * lm > rho);
+                const bool right = !(tk * Mx > rho);
+                if (left && right && tk >= 0.0) { kbest = k; tbest = tk; }
+            }
+            double key = (double)kbest;
+            int src = lane;
+            warp_argmin(key, src);                // smallest valid k; src = the lane that holds it
+            tbest = __shfl_sync(ISMPC_FULL_MASK, tbest, src);
+            if (key < 2.0e9) {
+                t = tbest; solved = true;
+                int ns = 0;                       // report the number of saturated rows
+                for (int i = lane; i < N; i += 32) ns += (t * fabs(a[i]) > rho);
+                iters = warp_sum_int(ns) + 1;
+            }
+        }
+        if (!solved) {
+            int nsat_prev = -1;
+            iters = 0;
+            t = rabs / aa;
+            for (;;) {
+                double q1 = 0.0, q2 = 0.0; int ns = 0;
+                for (int i = lane; i < N; i += 32) {
+                    double ai = fabs(a[i]);
+                    if (t * ai > rho) { q1 += ai; ++ns; } else q2 += ai * ai;
+                }
+                q1 = warp_sum(q1); q2 = warp_sum(q2); ns = warp_sum_int(ns);
+                if (ns == nsat_prev) break;
+                nsat_prev = ns; ++iters;
+                double rem = rabs - rho * q1;
+                if (!(q2 > 0.0)) { if (rem > 1e-12 * fmax(1.0, rabs)) status = 1; break; }
+                double tn = rem / q2;
+                if (!(tn >= t)) tn = t;   // monotone guard against round-off
+                t = tn;
+                if (iters > N + 2) break;
+            }
         }
     } else if (rabs > 1e-12) status = 1;
     const double nu = sg * t;
@@ -185,7 +285,7 @@ struct FormCArgs {
 
 // Debug-only phase timing (make dbg -> lib/libismpc_b200_dbg.so; never in the product library).
 #ifdef ISMPC_PHASE_TIMING
-#define ISMPC_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase[k] = clock64(); } while (0)
+#define ISMPC_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == (gridDim.x > 8 ? 5 : 0)) g_phase[k] = clock64(); } while (0)
 #else
 #define ISMPC_PHASE(k) do { } while (0)
 #endif
@@ -276,7 +376,19 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     }
     __syncthreads();
     ISMPC_PHASE(3);
-    // unconstrained minimiser x0 = -H^-1 F  (table mat-vec; Hinv symmetric -> coalesced row reads).
+    // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
+    int ne = 0, c_lo = 0;
+    if (wk.footstep_counter > 1) {
+        if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }     // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
+        else { ne = S + F - wk.mpc_iter; c_lo = 0; }                 // Aeq_z(i,i), i < S+F-mpcIter
+        if (c_lo < 0) { ne += c_lo; c_lo = 0; }
+        if (c_lo + ne > N) ne = N - c_lo;
+        if (ne < 0) ne = 0;
+    }
+    // Prepared gait: the projector table of this mpcIter folds the equalities into the mat-vec.
+    const bool use_P = T.P != nullptr && ne > 0 && S == T.gS && F == T.gF && wk.mpc_iter >= 0 && wk.mpc_iter < S + F;
+    const double* __restrict__ Tab = use_P ? T.P + (size_t)wk.mpc_iter * N * N : T.Hinv;
+    // minimiser f = -Tab F  (table mat-vec; the tables are symmetric -> coalesced row reads).
     // The 4 warps split the j range; each lane owns outputs i = blk*128 + lane + 32e.  Per-warp partial
     // vectors go to shared memory (zdir/lam/chv/shs are free at this point) and are summed afterwards.
     int i_lo = 0, i_hi = N;                                 // output rows of x0 this CTA computes
@@ -287,28 +399,36 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     {
         double* part = (warp == 0) ? sm.zdir : (warp == 1) ? sm.lam : (warp == 2) ? sm.chv : sm.shs;
         const int jlo = (N * warp) / 4, jhi = (N * (warp + 1)) / 4;
+        constexpr int U = 4;                                     // table rows in flight per pass (16 loads per lane)
         for (int blk = 0; i_lo + blk * 128 < i_hi; ++blk) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const int ib = i_lo + blk * 128 + lane;
+            bool ok[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ok[e] = ib + 32 * e < i_hi;
             int j = jlo;
-            for (; j + 1 < jhi; j += 2) {                      // two table rows in flight per pass
-                const double f0 = sm.Fz[j], f1 = sm.Fz[j + 1];
-                const double* h0 = T.Hinv + (size_t)j * N + ib;
-                const double* h1 = h0 + N;
-                double v0[4], v1[4];
+            for (; j + U <= jhi; j += U) {
+                double v[U][4], fj[U];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { v0[e] = ib + 32 * e < i_hi ? __ldg(h0 + 32 * e) : 0.0; v1[e] = ib + 32 * e < i_hi ? __ldg(h1 + 32 * e) : 0.0; }
+                for (int u = 0; u < U; ++u) {
+                    const double* hr = Tab + (size_t)(j + u) * N + ib;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc[e] += v0[e] * f0 + v1[e] * f1;
+                    for (int e = 0; e < 4; ++e) v[u][e] = ok[e] ? __ldg(hr + 32 * e) : 0.0;
+                    fj[u] = sm.Fz[j + u];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] += v[u][e] * fj[u];
             }
-            if (j < jhi) {
+            for (; j < jhi; ++j) {
                 const double fj = sm.Fz[j];
-                const double* hr = T.Hinv + (size_t)j * N + ib;
+                const double* hr = Tab + (size_t)j * N + ib;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (ib + 32 * e < i_hi) acc[e] += __ldg(hr + 32 * e) * fj;
+                for (int e = 0; e < 4; ++e) if (ok[e]) acc[e] += __ldg(hr + 32 * e) * fj;
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (ib + 32 * e < i_hi) part[ib + 32 * e] = acc[e];
+            for (int e = 0; e < 4; ++e) if (ok[e]) part[ib + 32 * e] = acc[e];
         }
     }
     __syncthreads();
@@ -325,20 +445,12 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     if constexpr (CLUSTER) cooperative_groups::this_cluster().sync(); else __syncthreads();
     ISMPC_PHASE(5);
 
-    // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
-    int ne = 0, c_lo = 0;
-    if (wk.footstep_counter > 1) {
-        if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }     // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
-        else { ne = S + F - wk.mpc_iter; c_lo = 0; }                 // Aeq_z(i,i), i < S+F-mpcIter
-        if (c_lo < 0) { ne += c_lo; c_lo = 0; }
-        if (c_lo + ne > N) ne = N - c_lo;
-        if (ne < 0) ne = 0;
-    }
-    // keep the unconstrained minimiser for the general path
-    for (int i = tid; i < N; i += FORMC_THREADS) sm.Fz[i] = sm.f[i];
+    // keep the unconstrained minimiser for the general path (with a projector table sm.f is already the
+    // equality-constrained minimiser; the general path then recomputes x0 from H^-1, see below)
+    if (!use_P) for (int i = tid; i < N; i += FORMC_THREADS) sm.Fz[i] = sm.f[i];
     // ---- fast path: equality-constrained minimiser in closed form (all rows of 0 <= S f <= fz_max inactive) ----
     //   f = x0 - H^-1[:,K] mu,  (H^-1)_KK mu = x0_K   with K = [c_lo, c_lo+ne) a contiguous column range
-    const bool fast_eq = (ne > 0 && ne <= 32);
+    const bool fast_eq = (!use_P && ne > 0 && ne <= 32);
     if (fast_eq) {
         double* Sk = sm.das.Js;                                      // ne x ne, row-major (fits: 32*32 <= packed qmax)
         for (int e = tid; e < ne * ne; e += FORMC_THREADS) {
@@ -395,7 +507,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         VertProb vp{N, T, c1, mdl.fz_max, sm.scr};
         int zfail = 0;
         bool done = false;
-        if (fast_eq || ne == 0) {
+        if (fast_eq || ne == 0 || use_P) {
             vp.eval(sm.f, sm.rv);
             double worst = 0.0;
             for (int i = lane; i < N; i += 32) {
@@ -407,7 +519,15 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         }
         if (!done) {
             // general path: dual active set from the unconstrained minimiser (equalities first, never dropped)
-            for (int i = lane; i < N; i += 32) sm.f[i] = sm.Fz[i];
+            if (use_P) {                       // rare: sm.Fz still holds F_z; x0 = -H^-1 F_z by this warp alone
+                for (int i = lane; i < N; i += 32) {
+                    double acc = 0.0;
+                    for (int j = 0; j < N; ++j) acc += __ldg(T.Hinv + (size_t)j * N + i) * sm.Fz[j];
+                    sm.f[i] = -acc;
+                }
+            } else {
+                for (int i = lane; i < N; i += 32) sm.f[i] = sm.Fz[i];
+            }
             __syncwarp();
             for (int e = 0; e < ne; ++e) {
                 int rc = das_add_equality(vp, w, sm.f, sm.zdir, N + c_lo + e, sm.f[c_lo + e], 0.0);
@@ -434,17 +554,11 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     if (prim) for (int i = tid; i < N; i += FORMC_THREADS) prim[i] = sm.f[i];
 
     // ================= STAGE 2: lambda sequence (MPCSolver.cpp:296-309) =================
-    // z_pos = S_bar_z f + T_z z + T_g  (two prefix sums of f), lambda_j = (g + (f_j/m - g)) / z_pos_j
-    if (warp == 0) {
-        for (int i = lane; i < N; i += 32) sm.scr[i] = sm.f[i];
-        __syncwarp();
-        warp_prefix_sum_smem(sm.scr, N);
-        warp_prefix_sum_smem(sm.scr, N);
-    }
-    __syncthreads();
+    // z_pos = S_bar_z f + T_z z + T_g, lambda_j = (g + (f_j/m - g)) / z_pos_j.  S_bar_z f is what the last row
+    // evaluation of stage 1 left in sm.rv (feasibility check of the fast path / final pass of the active set).
     ISMPC_PHASE(10);
     for (int j = tid; j < N; j += FORMC_THREADS) {
-        double sf = (j == 0) ? 0.0 : c1 * sm.scr[j - 1];
+        double sf = sm.rv[j];
         double tg = -g * (dt * dt) * (0.5 * (double)j * (double)(j + 1));
         double zp = sf + 1.0 * z0 + ((double)(j + 1) * dt) * zd0 + tg;
         double zacc = (1.0 / mass) * sm.f[j] - g;
@@ -453,7 +567,8 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         if (lam < 2.0) { sm.chv[j] = 1.0; sm.shs[j] = dt; sm.ssh[j] = 0.0; }       // integrator (:353-355)
         else {
             double s = sqrt(lam);
-            double ch = cosh(s * dt), sh = sinh(s * dt);
+            const double ex = exp(s * dt), ei = 1.0 / ex;                           // cosh / sinh from one exp
+            const double ch = 0.5 * (ex + ei), sh = 0.5 * (ex - ei);
             sm.chv[j] = ch; sm.shs[j] = sh / s; sm.ssh[j] = s * sh;                 // (:357-360)
         }
         sm.dl[j] = exp(-dt * eta * (double)j);                                      // deltas (:183-184)
@@ -524,7 +639,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
             const double b = -(sm.red[4] * c + sm.red[5] * cd) + eta * dt * sm.red[6 + ax];
             const double rho = (wk.footstep_counter > 1) ? in.box_w / 2 : in.box_w_init / 2;   // (:328-338)
             double nu, resid; int it;
-            int rc = knapsack_qp(N, sm.avec, mq, rho, b, &nu, &it, &resid);
+            int rc = knapsack_qp(N, sm.avec, mq, rho, b, ax == 0 ? sm.zdir : sm.Fz, ax == 0 ? sm.scr : sm.rv, &nu, &it, &resid);
             for (int i = lane; i < N; i += 32) {
                 double d = nu * sm.avec[i];
                 double u = mq[i] + fmin(fmax(d, -rho), rho);
@@ -540,6 +655,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         }
         __syncthreads();
         ISMPC_PHASE(13);
+        ISMPC_PHASE(14);
         ux0 = sm.red[8]; uy0 = sm.red[11];
         int e0 = (int)sm.red[9], e1 = (int)sm.red[12];
         status |= (e0 & 1023) | (e1 & 1023);
@@ -557,7 +673,8 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
         if (lam0 < 2.0) { a00 = 1.0; a01 = dt; a10 = 0.0; a11 = 1.0; b0 = 0.0; b1 = 0.0; }
         else {
             double s = sqrt(lam0);
-            double ch = cosh(s * dt), sh = sinh(s * dt);
+            const double ex = exp(s * dt), ei = 1.0 / ex;
+            const double ch = 0.5 * (ex + ei), sh = 0.5 * (ex - ei);
             a00 = ch; a01 = sh / s; a10 = s * sh; a11 = ch; b0 = 1.0 - ch; b1 = -s * sh;
         }
         ismpc_formc_out_t r;

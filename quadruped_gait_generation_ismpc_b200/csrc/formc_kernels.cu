@@ -95,6 +95,81 @@ __global__ void formc_M(ismpc_formc_model_t m, const double* G, double* M)
     M[(size_t)k * N + l] = s;
 }
 
+// Projector tables of a prepared gait: one CTA per mpcIter m builds
+//   P_m = H^-1 - H^-1[:,K] (H^-1_KK)^-1 H^-1[K,:]      (K = flight-phase columns at m; rows/columns K set to exactly 0)
+// Dynamic shared memory: Sk[ne*2ne] (Gauss-Jordan on [H^-1_KK | I]) + W[ne*N] = (H^-1_KK)^-1 H^-1[K,:].
+__global__ void formc_build_P(int N, int S, int F, const double* __restrict__ Hinv, double* __restrict__ P, int* info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = blockIdx.x;
+    int ne, c_lo;
+    if (m < S) { ne = F; c_lo = S - m; } else { ne = S + F - m; c_lo = 0; }
+    if (c_lo < 0) { ne += c_lo; c_lo = 0; }
+    if (c_lo + ne > N) ne = N - c_lo;
+    if (ne < 0) ne = 0;
+    double* Pm = P + (size_t)m * N * N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (ne == 0) {
+        for (size_t e = tid; e < (size_t)N * N; e += nt) Pm[e] = Hinv[e];
+        return;
+    }
+    double* Sk = reinterpret_cast<double*>(smem_raw);            // ne x 2ne
+    double* W = Sk + (size_t)ne * 2 * ne;                        // ne x N
+    const int LD = 2 * ne;
+    for (int e = tid; e < ne * ne; e += nt) {
+        const int r = e / ne, c = e - r * ne;
+        Sk[r * LD + c] = Hinv[(size_t)(c_lo + r) * N + c_lo + c];
+        Sk[r * LD + ne + c] = r == c ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int p = 0; p < ne; ++p) {                               // SPD block: no pivoting needed
+        const double piv = Sk[p * LD + p];
+        if (!(piv > 0.0) && tid == 0) *info = 1000 + m;
+        __syncthreads();
+        for (int c = tid; c < LD; c += nt) if (c != p) Sk[p * LD + c] /= piv;
+        __syncthreads();
+        if (tid == 0) Sk[p * LD + p] = 1.0;
+        for (int e = tid; e < ne * LD; e += nt) {
+            const int r = e / LD, c = e - r * LD;
+            if (r != p && c != p) Sk[r * LD + c] -= Sk[r * LD + p] * Sk[p * LD + c];
+        }
+        __syncthreads();
+        for (int r = tid; r < ne; r += nt) if (r != p) Sk[r * LD + p] = 0.0;
+        __syncthreads();
+    }
+    for (int e = tid; e < ne * N; e += nt) {                     // W = Sk^-1 Hinv[K,:]
+        const int r = e / N, j = e - r * N;
+        double acc = 0.0;
+        for (int k = 0; k < ne; ++k) acc += Sk[r * LD + ne + k] * Hinv[(size_t)(c_lo + k) * N + j];
+        W[e] = acc;
+    }
+    __syncthreads();
+    for (size_t e = tid; e < (size_t)N * N; e += nt) {
+        const int i = (int)(e / N), j = (int)(e - (size_t)i * N);
+        double v = 0.0;
+        if (!(i >= c_lo && i < c_lo + ne) && !(j >= c_lo && j < c_lo + ne)) {
+            v = Hinv[e];
+            for (int k = 0; k < ne; ++k) v -= Hinv[(size_t)i * N + c_lo + k] * W[(size_t)k * N + j];
+        }
+        Pm[e] = v;
+    }
+}
+
+// Returns 0, a cudaError, or -1 if the flight-phase block does not fit in shared memory (then no tables are built).
+int formc_prepare_gait_launch(int N, int S, int F, const double* Hinv, double* P, int* d_info, cudaStream_t st,
+                              long long* launches)
+{
+    int ne_max = F > S + F ? F : S + F;
+    if (ne_max > N) ne_max = N;
+    const size_t smem = ((size_t)ne_max * 2 * ne_max + (size_t)ne_max * N) * sizeof(double);
+    if (smem > (size_t)227 * 1024) return -1;
+    cudaError_t e = cudaFuncSetAttribute(formc_build_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    formc_build_P<<<S + F, 256, smem, st>>>(N, S, F, Hinv, P, d_info);
+    *launches += 1;
+    return (int)cudaGetLastError();
+}
+
 int formc_setup_launch(const ismpc_formc_model_t& m, double* work /*3 N^2*/, double* Hinv, double* G, double* M,
                        int* d_info, cudaStream_t st, long long* launches)
 {

@@ -11,6 +11,8 @@ struct FormAArgs;
 
 int formc_setup_launch(const ismpc_formc_model_t& m, double* work, double* Hinv, double* G, double* M,
                        int* d_info, cudaStream_t st, long long* launches);
+int formc_prepare_gait_launch(int N, int S, int F, const double* Hinv, double* P, int* d_info, cudaStream_t st,
+                              long long* launches);
 int formc_cluster_ctas_per_sm(int N);
 int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream_t st);
 int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,

@@ -132,3 +132,28 @@ def test_cluster_per_qp_identical_to_cta_per_qp(handle, N, cs):
         handle.set_option("formc_cluster_size", 0)
     assert np.array_equal(a["primal"], b["primal"]) and np.array_equal(a["active"], b["active"])
     assert a["out"].tobytes() == b["out"].tobytes()
+
+
+def test_prepared_gait_equals_generic_path(handle):
+    """ismpc_formc_prepare_gait folds the flight-phase equalities into a projector table: same results as the
+    closed-form equality solve of the generic path; instances with another step timing fall back to it."""
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.formc_batch(192, seed=4242, z_spread=0.04)
+    # a third of the batch walks with another timing (S=30, F_ds=15: same 45-tick steps, other flight phase)
+    inst["S"][::3] = 30; inst["F_ds"][::3] = 15
+    handle.formc_set_model(model)                      # drops any prepared gait
+    handle.formc_prepare_gait(17, 3)                   # nobody in the batch uses it -> generic path for everyone
+    g = handle.formc_solve_batch(state, walk, inst, plan)
+    handle.formc_prepare_gait(35, 10)
+    p = handle.formc_solve_batch(state, walk, inst, plan)
+    ok = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
+    assert ok.mean() > 0.7
+    assert np.array_equal(g["out"]["status"], p["out"]["status"])
+    assert primal_rel_err(p["primal"][ok].reshape(-1, 3, 100), g["primal"][ok].reshape(-1, 3, 100)).max() <= 1e-9
+    assert np.array_equal(p["active"][ok], g["active"][ok])
+    assert np.abs(p["out"]["next"]["com_pos"][ok] - g["out"]["next"]["com_pos"][ok]).max() <= 1e-10
+    # the flight-phase forces are exactly zero with the table
+    running = ok & (walk["footstep_counter"] > 1) & (inst["S"] == 35)
+    i = np.nonzero(running & (walk["mpc_iter"] < 35))[0][0]
+    c_lo = 35 - walk["mpc_iter"][i]
+    assert (p["primal"][i, c_lo:c_lo + 10] == 0.0).all()

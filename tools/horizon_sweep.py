@@ -40,6 +40,7 @@ for N in (50, 100, 200, 400):
     steps = (2 * N + 900) // 45 + 3
     st, wk, ins, pl = synth.formc_batch(n, seed=N, N=N, n_steps=steps)
     h.formc_set_model(abi.formc_model(N=N))
+    h.formc_prepare_gait(35, 10)
     d = [to_dev(x) for x in (st, wk, ins, pl)]
     out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
     ref = None

@@ -26,6 +26,8 @@ def to_dev(a):
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if which == "formc":
     h.formc_set_model(abi.formc_model())
+    if not os.environ.get("ISMPC_NO_GAIT"):
+        h.formc_prepare_gait(35, 10)
     st, wk, ins, pl = synth.formc_batch(n)
     d = [to_dev(x) for x in (st, wk, ins, pl)]
     out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
@@ -65,7 +67,9 @@ if os.environ.get("ISMPC_DBG"):
     ph = (C.c_longlong * 64)()
     binding.lib().ismpc_debug_read_phases(ph)
     v = list(ph)[:24]
-    print("phase clocks (CTA 0, deltas in cycles):", [v[i + 1] - v[i] for i in range(len(v) - 1) if v[i + 1] and v[i]])
+    nz = [(i, x) for i, x in enumerate(v) if x]
+    print("phase clocks (CTA 0): stamp -> cycles since the previous non-zero stamp:",
+          [(nz[k][0], nz[k][1] - nz[k - 1][1]) for k in range(1, len(nz))], "total", nz[-1][1] - nz[0][1] if nz else 0)
     names = ["eval", "viol_scan", "schur_col", "apply_J", "apply_Jt", "ratio", "step_dir", "x_mu_update", "append", "drop"]
     acc = list(ph)[32:32 + len(names)]
     tot = float(sum(acc)) or 1.0
