@@ -282,6 +282,30 @@ int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_t* model, c
                       const double* foot_plan, int foot_plan_rows, int n_steps, int fixed, int swing,
                       double* fl, double* fr, double* rl, double* rr, int mem, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Footstep-plan generators (the scripts' initialisation: trotting/init_quadruped.m:4-184,      */
+/* walking/init_quadruped2.m:4-300), one plan per instance, on the device.                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double disp_B, disp_C;                 /* half track and body length: 0.259394, 0.88 (init_quadruped.m:17-18) */
+    double disp_forw, disp_i, disp_o;      /* admissible foot-placement region: 0.5, 0.4, 0.4 (init_quadruped.m:31-35) */
+    int32_t gait;                          /* ISMPC_GAIT_TROT / ISMPC_GAIT_WALK */
+    int32_t N_gait;                        /* number of gait rows: 100 (init_quadruped.m:4) */
+} ismpc_plan_model_t;
+
+typedef struct { double disp_A, phi; } ismpc_plan_req_t;   /* step length and heading (init_quadruped.m:7,9) */
+
+/* Rows a plan of this model occupies: N_gait (trot) or N_gait + 8 (walk: the 8-phase loop writes up to 7 rows past its
+ * start, MATLAB grows the arrays; the first ismpc_plan_valid_rows rows are the plan the scripts end up with). */
+int ismpc_plan_rows(const ismpc_plan_model_t* model);
+int ismpc_plan_valid_rows(const ismpc_plan_model_t* model);
+
+/* foot_plan: n x rows x 8 doubles (rear-left x,y | rear-right | front-right | front-left), center: n x rows x 2 doubles
+ * (the virtual-biped footsteps = intersection of the support polygon's diagonals, closed form in place of the scripts'
+ * symbolic solve), rows = ismpc_plan_rows(model). */
+int ismpc_plan_generate(ismpc_handle* h, int n, const ismpc_plan_model_t* model, const ismpc_plan_req_t* req,
+                        double* foot_plan, double* center, int mem, void* stream);
+
 /* solveQP(H, f, A, lbA, ubA) (AMR_code_DART/utils.cpp:89-139) for n independent dense QPs of one shape:
  * min 1/2 x'Hx + g'x  s.t. lbA <= A x <= ubA.  H: n x nV x nV, g: n x nV, A: n x nC x nV (row-major),
  * lbA/ubA: n x nC.  x: n x nV.  y_opt (nullable): n x nC constraint duals (qpOASES sign);

@@ -35,15 +35,18 @@ FEET_MODEL = np.dtype([("disp_forw", "f8"), ("disp_i", "f8"), ("disp_o", "f8"), 
 FEET_INST = np.dtype([("phi", "f8"), ("j", "i4"), ("fs_counter", "i4"), ("timing_first", "i4"), ("n_timing", "i4"),
                       ("plan_first_row", "i4"), ("plan_rows", "i4")], align=True)
 GAIT_TROT, GAIT_WALK = 0, 1
+PLAN_MODEL = np.dtype([("disp_B", "f8"), ("disp_C", "f8"), ("disp_forw", "f8"), ("disp_i", "f8"), ("disp_o", "f8"),
+                       ("gait", "i4"), ("N_gait", "i4")], align=True)
+PLAN_REQ = np.dtype([("disp_A", "f8"), ("phi", "f8")], align=True)
 
 SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
          "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
-         "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32}
+         "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32, "ismpc_plan_model_t": 48, "ismpc_plan_req_t": 16}
 DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
           "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
           "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
           "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH, "ismpc_feet_model_t": FEET_MODEL,
-          "ismpc_feet_inst_t": FEET_INST}
+          "ismpc_feet_inst_t": FEET_INST, "ismpc_plan_model_t": PLAN_MODEL, "ismpc_plan_req_t": PLAN_REQ}
 
 # status bits
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
@@ -78,4 +81,13 @@ def feet_model(gait, disp_forw=0.5, disp_i=0.4, disp_o=0.4, wrap_counter=0):
     m["disp_forw_dummy"], m["disp_i_dummy"], m["disp_o_dummy"] = disp_forw / 2, disp_i / 2, disp_o / 2
     m["gait"] = GAIT_TROT if gait in ("trot", GAIT_TROT) else GAIT_WALK
     m["wrap_counter"] = wrap_counter
+    return m
+
+
+def plan_model(gait, N_gait=100, disp_B=0.259394, disp_C=0.88, disp_forw=0.5, disp_i=0.4, disp_o=0.4):
+    """Reference constants: trotting/init_quadruped.m:4-36 == walking/init_quadruped2.m:4-36."""
+    m = np.zeros(1, dtype=PLAN_MODEL)
+    m["disp_B"], m["disp_C"], m["disp_forw"], m["disp_i"], m["disp_o"] = disp_B, disp_C, disp_forw, disp_i, disp_o
+    m["gait"] = GAIT_TROT if gait in ("trot", GAIT_TROT) else GAIT_WALK
+    m["N_gait"] = N_gait
     return m

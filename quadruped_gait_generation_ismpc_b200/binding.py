@@ -17,7 +17,8 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_kernel_launches", "ismpc_formc_set_model", "ismpc_formc_solve_batch", "ismpc_formc_rollout",
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
-           "ismpc_feet_export", "ismpc_formc_prepare_gait"]
+           "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
+           "ismpc_plan_generate"]
 
 _lib = None
 
@@ -64,6 +65,9 @@ def lib():
     L.ismpc_forma_rollout_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
     L.ismpc_feet_place_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.ismpc_feet_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    L.ismpc_plan_rows.argtypes = [C.c_void_p]
+    L.ismpc_plan_valid_rows.argtypes = [C.c_void_p]
+    L.ismpc_plan_generate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
     _lib = L
     return L
@@ -218,6 +222,18 @@ class Handle:
                                             _ptr(status), abi.MEM_HOST, None)
         self._check(rc, "ismpc_forma_rollout_ex")
         return dict(inst=inst, fs_plan=fs_plan, traj=traj, pred=pred, status=status)
+
+    # ---- footstep-plan generators -------------------------------------------------------------------
+    def plan_generate(self, model, req):
+        """Returns (foot_plan, center) trimmed to the rows the scripts end up with: (n, rows, 8), (n, rows, 2)."""
+        n = len(req)
+        rows = self._L.ismpc_plan_rows(_ptr(model)); valid = self._L.ismpc_plan_valid_rows(_ptr(model))
+        if rows <= 0:
+            raise IsmpcError("ismpc_plan_rows: invalid plan model")
+        fp = np.zeros((n, rows, 8)); ce = np.zeros((n, rows, 2))
+        rc = self._L.ismpc_plan_generate(self._h, n, _ptr(model), _ptr(req), _ptr(fp), _ptr(ce), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_plan_generate")
+        return fp[:, :valid].copy(), ce[:, :valid].copy()
 
     # ---- real-foot placement and export ------------------------------------------------------------
     def feet_place_rollout(self, model, finst, fs_timing, pred, foot_plan):

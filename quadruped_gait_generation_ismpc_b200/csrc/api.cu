@@ -496,6 +496,58 @@ extern "C" int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Footstep-plan generators
+// ---------------------------------------------------------------------------------------------------
+static bool plan_model_ok(const ismpc_plan_model_t* m)
+{
+    return m && (m->gait == ISMPC_GAIT_TROT || m->gait == ISMPC_GAIT_WALK) && m->N_gait >= 6 && m->N_gait <= 100000 &&
+           m->disp_C > 0 && m->disp_forw > 0 && m->disp_i > 0 && m->disp_o > 0;
+}
+
+extern "C" int ismpc_plan_rows(const ismpc_plan_model_t* m)
+{
+    if (!plan_model_ok(m)) return ISMPC_ERR_MODEL;
+    return m->gait == ISMPC_GAIT_TROT ? m->N_gait : m->N_gait + 8;
+}
+
+extern "C" int ismpc_plan_valid_rows(const ismpc_plan_model_t* m)
+{
+    if (!plan_model_ok(m)) return ISMPC_ERR_MODEL;
+    if (m->gait == ISMPC_GAIT_TROT) return m->N_gait;
+    const int last_j = 6 + 8 * ((m->N_gait - 6) / 8);          // last start row of the 8-phase loop (init_quadruped2.m:141)
+    return last_j + 7 > m->N_gait ? last_j + 7 : m->N_gait;
+}
+
+extern "C" int ismpc_plan_generate(ismpc_handle* h, int n, const ismpc_plan_model_t* model, const ismpc_plan_req_t* req,
+                                   double* foot_plan, double* center, int mem, void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!plan_model_ok(model)) return ISMPC_ERR_MODEL;
+    if (n < 0 || n > h->max_batch || !req || !foot_plan || !center) return ISMPC_ERR_ARG;
+    if (n == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = ismpc_plan_rows(model);
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = plan_generate_launch(n, *model, req, foot_plan, center, rows, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "plan_generate_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t br = (size_t)n * sizeof(ismpc_plan_req_t), bf = (size_t)n * rows * 8 * sizeof(double), bc = bf / 4;
+    if (h->f_inst.ensure(br) || h->f_plan.ensure(bf) || h->f_out.ensure(bc)) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->f_inst.p, req, br, cudaMemcpyHostToDevice, st));
+    int rc = plan_generate_launch(n, *model, (const ismpc_plan_req_t*)h->f_inst.p, (double*)h->f_plan.p, (double*)h->f_out.p, rows, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "plan_generate_launch");
+    CK(cudaMemcpyAsync(foot_plan, h->f_plan.p, bf, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(center, h->f_out.p, bc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Generic dense QP (solveQP seam)
 // ---------------------------------------------------------------------------------------------------
 extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, const double* H, const double* g,

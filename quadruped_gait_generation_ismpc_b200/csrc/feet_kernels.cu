@@ -154,6 +154,106 @@ __global__ void feet_export_kernel(int n, ismpc_feet_model_t mdl, const ismpc_fe
 }
 #undef FP
 
+// ---------------------------------------------------------------------------------------------------------
+// Plan generators: trotting/init_quadruped.m:54-184, walking/init_quadruped2.m:54-300.  One thread per instance;
+// rows depend on their predecessors, instances are independent.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void clip_step(double& x, double& y, double forw, double vert, double phi)
+{
+    if (y > vert || x > forw) {                                   // init_quadruped.m:62-102
+        if (phi > atan(vert / forw)) { y = vert; x = vert * cos(phi) / sin(phi); }
+        else { x = forw; y = forw * sin(phi) / cos(phi); }
+    }
+}
+
+__device__ __forceinline__ void diag_center(const double* row, double* c)   // init_quadruped.m:171-183
+{
+    const double m1 = (row[5] - row[1]) / (row[4] - row[0]), q1 = row[1] - m1 * row[0];   // rear-left -- front-right
+    const double m2 = (row[7] - row[3]) / (row[6] - row[2]), q2 = row[3] - m2 * row[2];   // rear-right -- front-left
+    const double x = (q2 - q1) / (m1 - m2);
+    c[0] = x; c[1] = m1 * x + q1;
+}
+
+__global__ void plan_generate_kernel(int n, ismpc_plan_model_t m, const ismpc_plan_req_t* req, double* foot_plan, double* center, int rows)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double phi = req[idx].phi, dA = req[idx].disp_A;
+    const double B = m.disp_B, C = m.disp_C;
+    const double vert = fmin(m.disp_i, m.disp_o);
+    double xp = dA * cos(phi), yp = dA * sin(phi);
+    double xd = xp / 2, yd = yp / 2;
+    clip_step(xd, yd, m.disp_forw / 2, vert / 2, phi);
+    clip_step(xp, yp, m.disp_forw, vert, phi);
+    double* fp = foot_plan + (size_t)idx * rows * 8;
+    double* ce = center + (size_t)idx * rows * 2;
+    const int N = m.N_gait;
+#define BL(r, c) fp[(size_t)(r) * 8 + 0 + (c)]
+#define BR(r, c) fp[(size_t)(r) * 8 + 2 + (c)]
+#define FR(r, c) fp[(size_t)(r) * 8 + 4 + (c)]
+#define FL(r, c) fp[(size_t)(r) * 8 + 6 + (c)]
+    for (int r = 0; r < rows; ++r) {
+        BL(r, 0) = 0.0; BL(r, 1) = B; BR(r, 0) = 0.0; BR(r, 1) = -B; FL(r, 0) = C; FL(r, 1) = B; FR(r, 0) = C; FR(r, 1) = -B;
+        ce[r * 2] = 0.0; ce[r * 2 + 1] = 0.0;
+    }
+    const double st[2] = {xp, yp};
+    if (m.gait == ISMPC_GAIT_TROT) {
+        if (N > 1) { BL(1, 0) = xd; FR(1, 0) = C + xd; BL(1, 1) = B + yd; FR(1, 1) = -B + yd; }     // init_quadruped.m:113-117
+        for (int j = 3; j <= N; ++j) {                                                              // :120-149
+            const int i = j - 1;
+            for (int c = 0; c < 2; ++c) {
+                if (j % 2 == 0) { BL(i, c) = BL(i - 1, c) + st[c]; FR(i, c) = FR(i - 1, c) + st[c]; BR(i, c) = BR(i - 1, c); FL(i, c) = FL(i - 1, c); }
+                else { BR(i, c) = BR(i - 1, c) + st[c]; FL(i, c) = FL(i - 1, c) + st[c]; BL(i, c) = BL(i - 1, c); FR(i, c) = FR(i - 1, c); }
+            }
+        }
+        ce[0] = C / 2;
+        for (int k = 1; k < N; ++k) diag_center(fp + (size_t)k * 8, ce + (size_t)k * 2);
+    } else {
+        // init_quadruped2.m:114-138 (dummy first half-cycle)
+        const double dm[2] = {xd, yd};
+        const double base[2] = {C, B};
+        for (int c = 0; c < 2; ++c) {
+            FL(2, c) = base[c] + dm[c]; FL(3, c) = FL(2, c); FL(4, c) = FL(2, c);
+            BR(1, c) = BR(0, c); BR(2, c) = BR(0, c); BR(3, c) = BR(2, c); BR(4, c) = BR(3, c) + dm[c];
+        }
+        int grown = N;
+        for (int j = 6; j <= N; j += 8) {                                                           // :141-219
+            const int i = j - 1;
+            for (int c = 0; c < 2; ++c) {
+                FR(i, c) = FR(i - 1, c); FR(i + 1, c) = FR(i, c) + st[c];
+                for (int k = 2; k < 8; ++k) FR(i + k, c) = FR(i + 1, c);
+                BL(i, c) = BL(i - 1, c); BL(i + 1, c) = BL(i, c); BL(i + 2, c) = BL(i, c); BL(i + 3, c) = BL(i + 2, c) + st[c];
+                for (int k = 4; k < 8; ++k) BL(i + k, c) = BL(i + 3, c);
+                FL(i, c) = FL(i - 1, c);
+                for (int k = 1; k < 5; ++k) FL(i + k, c) = FL(i, c);
+                FL(i + 5, c) = FL(i + 4, c) + st[c]; FL(i + 6, c) = FL(i + 5, c); FL(i + 7, c) = FL(i + 5, c);
+                BR(i, c) = BR(i - 1, c);
+                for (int k = 1; k < 7; ++k) BR(i + k, c) = BR(i, c);
+                BR(i + 7, c) = BR(i + 6, c) + st[c];
+            }
+            if (j + 7 > grown) grown = j + 7;
+        }
+        ce[0] = C / 2;
+        const int rc = grown > N ? grown : N;
+        for (int j = 1; j <= N - 4; j += 8) {                                                       // :242-284
+            for (int k = 0; k < 8; k += 2) if (j + k - 1 < grown) diag_center(fp + (size_t)(j + k - 1) * 8, ce + (size_t)(j + k - 1) * 2);
+            for (int k = 1; k < 8; k += 2)
+                if (j + k - 1 < rc) { ce[(size_t)(j + k - 1) * 2] = ce[(size_t)(j + k - 2) * 2]; ce[(size_t)(j + k - 1) * 2 + 1] = ce[(size_t)(j + k - 2) * 2 + 1]; }
+        }
+    }
+#undef BL
+#undef BR
+#undef FR
+#undef FL
+}
+
+int plan_generate_launch(int n, const ismpc_plan_model_t& m, const ismpc_plan_req_t* req, double* foot_plan, double* center,
+                         int rows, cudaStream_t st)
+{
+    plan_generate_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, m, req, foot_plan, center, rows);
+    return (int)cudaGetLastError();
+}
+
 int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const int32_t* fs_timing,
                       const double* pred_traj, double* foot_plan, cudaStream_t st)
 {

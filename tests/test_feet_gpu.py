@@ -95,3 +95,24 @@ def test_trotting_pipeline_matches_the_reference_files(handle):
         assert np.abs(pos - GOLD[key + "_com"]).max() < 1e-5, key
         for k in feet:
             assert np.abs(ex[k][0] - GOLD["%s_%s" % (key, k)]).max() < 1e-5, (key, k)
+
+
+@pytest.mark.parametrize("gait", ["trot", "walk"])
+def test_plan_generators_on_device(handle, gait):
+    """init_quadruped.m / init_quadruped2.m on the device == the host mirrors in plans.py (which the reference's
+    recorded trajectories pin, see the pipeline tests above), for random step lengths and headings incl. clipped ones."""
+    rng = np.random.default_rng(3)
+    n = 64
+    req = np.zeros(n, dtype=abi.PLAN_REQ)
+    req["disp_A"] = rng.uniform(0.03, 0.7, n)                    # beyond 0.5 / 0.4 the step is clipped to the admissible region
+    req["phi"] = rng.choice([0.0, np.pi / 4, np.pi / 2, 0.3, 1.2], size=n)
+    req["disp_A"][:3] = [0.1, 0.15, 0.1]; req["phi"][:3] = [0.0, np.pi / 4, np.pi / 2]
+    for N_gait in (100, 37):
+        fp, ce = handle.plan_generate(abi.plan_model(gait, N_gait=N_gait), req)
+        gen = plans.trot_plan if gait == "trot" else plans.walk_plan
+        for i in range(n):
+            rfp, rce = gen(N_gait=N_gait, disp_A=float(req["disp_A"][i]), phi=float(req["phi"][i]))
+            assert fp[i].shape == rfp.shape and ce[i].shape[0] >= rce.shape[0] - 0
+            assert np.abs(fp[i] - rfp).max() <= 1e-13, (gait, N_gait, i)
+            m = min(len(ce[i]), len(rce))
+            assert np.abs(ce[i][:m] - rce[:m]).max() <= 1e-12, (gait, N_gait, i)
