@@ -306,6 +306,31 @@ int ismpc_plan_valid_rows(const ismpc_plan_model_t* model);
 int ismpc_plan_generate(ismpc_handle* h, int n, const ismpc_plan_model_t* model, const ismpc_plan_req_t* req,
                         double* foot_plan, double* center, int mem, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Batched LIP Kalman filter: the state-estimation step in front of the MPC                     */
+/* (AMR_code_DART/StateFiltering.{hpp,cpp}; single precision like the reference).               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    float h_com, mass, sampling_time, g;     /* StateFiltering.hpp:52-53 (g = 9.81f) */
+    float q_process[3][4];                   /* x, y, z: 2x2 process input noise covariance, row-major (StateFiltering.hpp:60) */
+    float q_measurement[3][9];               /* x, y, z: 3x3 measurement noise covariance, row-major (StateFiltering.hpp:61) */
+} ismpc_kf_model_t;
+
+/* Per axis (x, y, z): state = (position, velocity, acceleration, external force, its derivative)
+ * (StateFiltering.hpp:18) and its 5x5 covariance, row-major. */
+typedef struct { float state[3][5]; float sigma[3][25]; } ismpc_kf_state_t;
+/* One sample: 3 measurements and 1 input per axis (StateFiltering::FilterWithKalman, StateFiltering.cpp:77-79). */
+typedef struct { float meas[3][3]; float input[3]; } ismpc_kf_sample_t;
+
+/* state[i] = identity covariance and (state0, 0, 0) per axis, as the constructor does (StateFiltering.cpp:22-33). */
+int ismpc_kf_init(ismpc_kf_state_t* state, int n, const float* state0_xyz /* n x 3 x 3 */);
+
+/* n_steps calls of FilterWithKalman (predict_z, update_z, predict_xy, update_xy; StateFiltering.cpp:77-133) for n
+ * independent filters: samples n x n_steps, state advanced in place.  zmp_opt (nullable): n x n_steps x 2 floats,
+ * GetZMP() after each step (StateFiltering.cpp:180-186). */
+int ismpc_kf_filter_batch(ismpc_handle* h, int n, int n_steps, const ismpc_kf_model_t* model, ismpc_kf_state_t* state,
+                          const ismpc_kf_sample_t* samples, float* zmp_opt, int mem, void* stream);
+
 /* solveQP(H, f, A, lbA, ubA) (AMR_code_DART/utils.cpp:89-139) for n independent dense QPs of one shape:
  * min 1/2 x'Hx + g'x  s.t. lbA <= A x <= ubA.  H: n x nV x nV, g: n x nV, A: n x nC x nV (row-major),
  * lbA/ubA: n x nC.  x: n x nV.  y_opt (nullable): n x nC constraint duals (qpOASES sign);

@@ -875,3 +875,81 @@ void oracle_feet_export_walk(const double* foot_plan_c, int rows, int n_steps, i
     }
 }
 #undef FP
+
+/* ======================================================================================================
+ * LIP Kalman filter -- AMR_code_DART/StateFiltering.cpp restated with generic small dense helpers (float).
+ * ====================================================================================================== */
+static void kf_mm(const float* a, int ar, int ac, const float* b, int bc, float* out)      /* out = a (ar x ac) * b (ac x bc) */
+{
+    for (int i = 0; i < ar; ++i)
+        for (int j = 0; j < bc; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < ac; ++k) acc += a[i * ac + k] * b[k * bc + j];
+            out[i * bc + j] = acc;
+        }
+}
+static void kf_tr(const float* a, int ar, int ac, float* out)                               /* out = a' */
+{
+    for (int i = 0; i < ar; ++i) for (int j = 0; j < ac; ++j) out[j * ar + i] = a[i * ac + j];
+}
+static void kf_inv3x3(const float* m, float* r)
+{
+    const float a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const float A = e * i - f * h, B = f * g - d * i, C = d * h - e * g;
+    const float det = a * A + b * B + c * C;
+    r[0] = A / det; r[1] = (c * h - b * i) / det; r[2] = (b * f - c * e) / det;
+    r[3] = B / det; r[4] = (a * i - c * g) / det; r[5] = (c * d - a * f) / det;
+    r[6] = C / det; r[7] = (b * g - a * h) / det; r[8] = (a * e - b * d) / det;
+}
+/* predict_z / predict_xy (StateFiltering.cpp:97-103,115-124) */
+static void kf_pred(const float* A, const float* B, const float* q, float u, float* st, float* sg)
+{
+    float t5[5], in2[2] = {u, 0.0f}, bu[5], At[25], AS[25], ASA[25], Bt[10], BQ[10], BQB[25];
+    kf_mm(A, 5, 5, st, 1, t5); kf_mm(B, 5, 2, in2, 1, bu);
+    for (int i = 0; i < 5; ++i) st[i] = t5[i] + bu[i];
+    kf_tr(A, 5, 5, At); kf_mm(A, 5, 5, sg, 5, AS); kf_mm(AS, 5, 5, At, 5, ASA);
+    kf_tr(B, 5, 2, Bt); kf_mm(B, 5, 2, q, 2, BQ); kf_mm(BQ, 5, 2, Bt, 5, BQB);
+    for (int i = 0; i < 25; ++i) sg[i] = ASA[i] + BQB[i];
+}
+/* update_z / update_xy (StateFiltering.cpp:104-112,125-133) */
+static void kf_upd(const float* Cm, const float* R, const float* z, const float* off, float* st, float* sg)
+{
+    float Ct[15], SC[15], CSC[9], S[9], Si[9], K[15], Cs[3], inn[3], Ki[5], KC[25], KCS[25];
+    kf_tr(Cm, 3, 5, Ct); kf_mm(sg, 5, 5, Ct, 3, SC); kf_mm(Cm, 3, 5, SC, 3, CSC);
+    for (int i = 0; i < 9; ++i) S[i] = R[i] + CSC[i];
+    kf_inv3x3(S, Si); kf_mm(SC, 5, 3, Si, 3, K);
+    kf_mm(Cm, 3, 5, st, 1, Cs);
+    for (int i = 0; i < 3; ++i) inn[i] = z[i] - (Cs[i] + off[i]);
+    kf_mm(K, 5, 3, inn, 1, Ki);
+    for (int i = 0; i < 5; ++i) st[i] += Ki[i];
+    kf_mm(K, 5, 3, Cm, 5, KC); kf_mm(KC, 5, 5, sg, 5, KCS);
+    for (int i = 0; i < 25; ++i) sg[i] -= KCS[i];
+}
+void oracle_kf_filter(const oracle_kf_model* m, oracle_kf_state* s, const oracle_kf_sample* samples, int n_steps, float* zmp)
+{
+    const float T = m->sampling_time;
+    const float A[25] = {1.0f, T, T * T / 2, 0, 0,  0, 1.0f, T, T, 0,  0, 0, 1.0f, 0, 0,  0, 0, 0, 1.0f, T,  0, 0, 0, 0, 1.0f};   /* :36-40 */
+    const float B[10] = {T * T * T / 6, 0,  T * T / 2, 0,  T, 0,  0, T * T / 2,  0, T};                                          /* :42-46 */
+    const float Cz[15] = {1.0f, 0, 0, 0, 0,  0, 0, 1.0f, 0, 0,  0, 0, -m->mass, 1.0f, 0};                                         /* :48-50 */
+    float Cxy[15] = {1.0f, 0, 0, 0, 0,  0, 0, 1.0f, 0, 0,  1.0f, 0, 0, 0, 0};                                                     /* :52-54 */
+    const float offz[3] = {0.0f, 0.0f, -m->g * m->mass}, off0[3] = {0.0f, 0.0f, 0.0f};
+    for (int t = 0; t < n_steps; ++t) {
+        const oracle_kf_sample* u = samples + t;
+        kf_pred(A, B, m->q_process[2], u->input[2], s->state[2], s->sigma[2]);             /* predict_z */
+        kf_upd(Cz, m->q_measurement[2], u->meas[2], offz, s->state[2], s->sigma[2]);       /* update_z  */
+        kf_pred(A, B, m->q_process[0], u->input[0], s->state[0], s->sigma[0]);             /* predict_xy */
+        kf_pred(A, B, m->q_process[1], u->input[1], s->state[1], s->sigma[1]);
+        const float f_n = -m->mass * m->g - m->mass * s->state[2][2] + s->state[2][3];     /* update_xy :127-129 */
+        Cxy[2 * 5 + 2] = m->mass * s->state[2][0] / f_n;
+        Cxy[2 * 5 + 3] = -s->state[2][0] / f_n;
+        kf_upd(Cxy, m->q_measurement[0], u->meas[0], off0, s->state[0], s->sigma[0]);
+        kf_upd(Cxy, m->q_measurement[1], u->meas[1], off0, s->state[1], s->sigma[1]);
+        if (zmp) {
+            for (int ax = 0; ax < 2; ++ax) {
+                float acc = 0.0f;
+                for (int l = 0; l < 5; ++l) acc += Cxy[2 * 5 + l] * s->state[ax][l];
+                zmp[t * 2 + ax] = acc;
+            }
+        }
+    }
+}

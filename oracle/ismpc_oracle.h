@@ -208,6 +208,18 @@ void oracle_feet_export_trot(const double* foot_plan, int rows, int n_steps, int
 void oracle_feet_export_walk(const double* foot_plan, int rows, int n_steps, int step_duration,
                              double* fl, double* fr, double* rl, double* rr);
 
+/* ---- LIP Kalman filter (AMR_code_DART/StateFiltering.cpp), single precision like the reference ---- */
+typedef struct {
+    float h_com, mass, sampling_time, g;
+    float q_process[3][4];      /* x, y, z : 2x2 row-major */
+    float q_measurement[3][9];  /* x, y, z : 3x3 row-major */
+} oracle_kf_model;
+typedef struct { float state[3][5]; float sigma[3][25]; } oracle_kf_state;
+typedef struct { float meas[3][3]; float input[3]; } oracle_kf_sample;
+/* n_steps calls of StateFiltering::FilterWithKalman (StateFiltering.cpp:77-133) on one filter; zmp (nullable):
+ * n_steps x 2, GetZMP() (StateFiltering.cpp:180-186) after each call. */
+void oracle_kf_filter(const oracle_kf_model* m, oracle_kf_state* s, const oracle_kf_sample* samples, int n_steps, float* zmp);
+
 #ifdef __cplusplus
 }
 #endif

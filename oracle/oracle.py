@@ -211,6 +211,20 @@ def forma_build(p, st, cur_fs, fs_store, j, fs_counter, fs_timing, ds, fs_plan, 
     return Hd, g, A, lb, ub
 
 
+def kf_filter(model, state, samples, kind="auto"):
+    """CPU restatement of StateFiltering::FilterWithKalman for n filters: model (1,) KF_MODEL, state (n,) KF_STATE,
+    samples (n, n_steps) KF_SAMPLE.  Returns (state advanced, zmp (n, n_steps, 2))."""
+    L = lib(kind)
+    n, n_steps = samples.shape
+    state = state.copy(); samples = np.ascontiguousarray(samples)
+    zmp = np.zeros((n, n_steps, 2), dtype=np.float32)
+    for i in range(n):
+        L.oracle_kf_filter(_vp(model), C.c_void_p(state.ctypes.data + i * state.itemsize),
+                           C.c_void_p(samples.ctypes.data + i * n_steps * samples.itemsize), C.c_int(n_steps),
+                           C.c_void_p(zmp.ctypes.data + i * n_steps * 8))
+    return state, zmp
+
+
 class FeetParams(C.Structure):
     _fields_ = [("disp_forw", C.c_double), ("disp_i", C.c_double), ("disp_o", C.c_double),
                 ("disp_forw_dummy", C.c_double), ("disp_i_dummy", C.c_double), ("disp_o_dummy", C.c_double)]

@@ -38,15 +38,21 @@ GAIT_TROT, GAIT_WALK = 0, 1
 PLAN_MODEL = np.dtype([("disp_B", "f8"), ("disp_C", "f8"), ("disp_forw", "f8"), ("disp_i", "f8"), ("disp_o", "f8"),
                        ("gait", "i4"), ("N_gait", "i4")], align=True)
 PLAN_REQ = np.dtype([("disp_A", "f8"), ("phi", "f8")], align=True)
+KF_MODEL = np.dtype([("h_com", "f4"), ("mass", "f4"), ("sampling_time", "f4"), ("g", "f4"),
+                     ("q_process", "f4", (3, 4)), ("q_measurement", "f4", (3, 9))], align=True)
+KF_STATE = np.dtype([("state", "f4", (3, 5)), ("sigma", "f4", (3, 25))], align=True)
+KF_SAMPLE = np.dtype([("meas", "f4", (3, 3)), ("input", "f4", 3)], align=True)
 
 SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
          "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
-         "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32, "ismpc_plan_model_t": 48, "ismpc_plan_req_t": 16}
+         "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32, "ismpc_plan_model_t": 48, "ismpc_plan_req_t": 16, "ismpc_kf_model_t": 172, "ismpc_kf_state_t": 360,
+         "ismpc_kf_sample_t": 48}
 DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
           "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
           "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
           "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH, "ismpc_feet_model_t": FEET_MODEL,
-          "ismpc_feet_inst_t": FEET_INST, "ismpc_plan_model_t": PLAN_MODEL, "ismpc_plan_req_t": PLAN_REQ}
+          "ismpc_feet_inst_t": FEET_INST, "ismpc_plan_model_t": PLAN_MODEL, "ismpc_plan_req_t": PLAN_REQ,
+          "ismpc_kf_model_t": KF_MODEL, "ismpc_kf_state_t": KF_STATE, "ismpc_kf_sample_t": KF_SAMPLE}
 
 # status bits
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
@@ -90,4 +96,14 @@ def plan_model(gait, N_gait=100, disp_B=0.259394, disp_C=0.88, disp_forw=0.5, di
     m["disp_B"], m["disp_C"], m["disp_forw"], m["disp_i"], m["disp_o"] = disp_B, disp_C, disp_forw, disp_i, disp_o
     m["gait"] = GAIT_TROT if gait in ("trot", GAIT_TROT) else GAIT_WALK
     m["N_gait"] = N_gait
+    return m
+
+
+def kf_model(h_com=0.69, mass=50.0, sampling_time=0.01, g=9.81, q_process=1e-2, q_measurement=1e-4):
+    """StateFiltering's constructor arguments (AMR_code_DART/StateFiltering.hpp:19-22); the reference never
+    instantiates the class, so the noise covariances have no reference values: diagonal defaults."""
+    m = np.zeros(1, dtype=KF_MODEL)
+    m["h_com"], m["mass"], m["sampling_time"], m["g"] = h_com, mass, sampling_time, g
+    m["q_process"][0] = np.tile((np.eye(2) * q_process).reshape(-1), (3, 1))
+    m["q_measurement"][0] = np.tile((np.eye(3) * q_measurement).reshape(-1), (3, 1))
     return m

@@ -18,7 +18,7 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
-           "ismpc_plan_generate"]
+           "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch"]
 
 _lib = None
 
@@ -35,6 +35,16 @@ def build(verbose=False):
     if verbose:
         print(out.stdout[-2000:])
     return LIB_PATH
+
+
+def kf_init(state0_xyz):
+    """(n, 3, 3) float32 initial (pos, vel, acc) per axis -> KF_STATE array (host helper, no GPU needed)."""
+    s0 = np.ascontiguousarray(state0_xyz, dtype=np.float32)
+    st = np.zeros(s0.shape[0], dtype=abi.KF_STATE)
+    rc = lib().ismpc_kf_init(_ptr(st), len(st), _ptr(s0))
+    if rc != 0:
+        raise IsmpcError("ismpc_kf_init failed")
+    return st
 
 
 def lib():
@@ -68,6 +78,8 @@ def lib():
     L.ismpc_plan_rows.argtypes = [C.c_void_p]
     L.ismpc_plan_valid_rows.argtypes = [C.c_void_p]
     L.ismpc_plan_generate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ismpc_kf_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ismpc_kf_filter_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
     _lib = L
     return L
@@ -222,6 +234,18 @@ class Handle:
                                             _ptr(status), abi.MEM_HOST, None)
         self._check(rc, "ismpc_forma_rollout_ex")
         return dict(inst=inst, fs_plan=fs_plan, traj=traj, pred=pred, status=status)
+
+    # ---- batched LIP Kalman filter ------------------------------------------------------------------
+    def kf_filter_batch(self, model, state, samples, want_zmp=True):
+        """state: (n,) KF_STATE (copied, returned advanced); samples: (n, n_steps) KF_SAMPLE."""
+        n, n_steps = samples.shape
+        state = state.copy()
+        samples = np.ascontiguousarray(samples)
+        zmp = np.zeros((n, n_steps, 2), dtype=np.float32) if want_zmp else None
+        rc = self._L.ismpc_kf_filter_batch(self._h, n, n_steps, _ptr(model), _ptr(state), _ptr(samples), _ptr(zmp),
+                                           abi.MEM_HOST, None)
+        self._check(rc, "ismpc_kf_filter_batch")
+        return state, zmp
 
     # ---- footstep-plan generators -------------------------------------------------------------------
     def plan_generate(self, model, req):

@@ -548,6 +548,54 @@ extern "C" int ismpc_plan_generate(ismpc_handle* h, int n, const ismpc_plan_mode
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Batched LIP Kalman filter
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ismpc_kf_init(ismpc_kf_state_t* state, int n, const float* state0_xyz)
+{
+    if (!state || n < 0 || !state0_xyz) return ISMPC_ERR_ARG;
+    for (int i = 0; i < n; ++i) {
+        memset(&state[i], 0, sizeof(ismpc_kf_state_t));
+        for (int ax = 0; ax < 3; ++ax) {
+            for (int c = 0; c < 3; ++c) state[i].state[ax][c] = state0_xyz[((size_t)i * 3 + ax) * 3 + c];
+            for (int d = 0; d < 5; ++d) state[i].sigma[ax][d * 5 + d] = 1.0f;
+        }
+    }
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_kf_filter_batch(ismpc_handle* h, int n, int n_steps, const ismpc_kf_model_t* model,
+                                     ismpc_kf_state_t* state, const ismpc_kf_sample_t* samples, float* zmp_opt, int mem,
+                                     void* stream)
+{
+    if (!h || !model) return ISMPC_ERR_ARG;
+    if (n < 0 || n > h->max_batch || n_steps < 0 || !state || !samples) return ISMPC_ERR_ARG;
+    if (!(model->sampling_time > 0.0f) || !(model->mass > 0.0f)) return ISMPC_ERR_MODEL;
+    if (n == 0 || n_steps == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = kf_filter_launch(n, n_steps, *model, state, samples, zmp_opt, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "kf_filter_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t bs = (size_t)n * sizeof(ismpc_kf_state_t), bu = (size_t)n * n_steps * sizeof(ismpc_kf_sample_t);
+    const size_t bz = (size_t)n * n_steps * 2 * sizeof(float);
+    if (h->f_inst.ensure(bs) || h->f_plan.ensure(bu) || (zmp_opt && h->f_out.ensure(bz))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->f_inst.p, state, bs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->f_plan.p, samples, bu, cudaMemcpyHostToDevice, st));
+    int rc = kf_filter_launch(n, n_steps, *model, (ismpc_kf_state_t*)h->f_inst.p, (const ismpc_kf_sample_t*)h->f_plan.p,
+                              zmp_opt ? (float*)h->f_out.p : nullptr, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "kf_filter_launch");
+    CK(cudaMemcpyAsync(state, h->f_inst.p, bs, cudaMemcpyDeviceToHost, st));
+    if (zmp_opt) CK(cudaMemcpyAsync(zmp_opt, h->f_out.p, bz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Generic dense QP (solveQP seam)
 // ---------------------------------------------------------------------------------------------------
 extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, const double* H, const double* g,

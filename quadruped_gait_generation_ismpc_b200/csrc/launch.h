@@ -27,6 +27,8 @@ int forma_rollout_launch(const FormAArgs& a, const FormALaunchPlan& p, ismpc_for
                          int32_t* status, cudaStream_t st);
 int plan_generate_launch(int n, const ismpc_plan_model_t& m, const ismpc_plan_req_t* req, double* foot_plan, double* center,
                          int rows, cudaStream_t st);
+int kf_filter_launch(int n, int n_steps, const ismpc_kf_model_t& m, ismpc_kf_state_t* state, const ismpc_kf_sample_t* samples,
+                     float* zmp, cudaStream_t st);
 int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst,
                       const int32_t* fs_timing, const double* pred_traj, double* foot_plan, cudaStream_t st);
 int feet_export_launch(int n, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const double* foot_plan,
