@@ -40,6 +40,14 @@ B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 FLOP_FORMC = 2 * HORIZON * HORIZON + 90 * HORIZON
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1e_formc_traffic.json")
+    if os.path.exists(p):
+        return int(json.load(open(p))["dram_bytes_per_launch"])
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -318,7 +326,7 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": load_traffic(), "peak_source": peak_src,
                              "kernel": "formc_tick_kernel", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_instance_tick": B_ALG_FORMC},
                 "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
