@@ -170,6 +170,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     K, W, n = args.steps, max(args.warmup, 3), args.batch
     h = binding.Handle(device=local, max_batch=max(n, 8192))
