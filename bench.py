@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -204,11 +204,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled (nvidia-smi -lms 20) from before the warm-up until the end of the e2e loops:
+    # the device-timed region alone lasts a few milliseconds, shorter than nvidia-smi's start-up
+    clocks = ClockSampler(local); clocks.start()
     for k in range(W):
         step(k)
     barrier()
     # ---- timed region: K steps, CUDA events on the launching stream ---------------------------------------
-    clocks = ClockSampler(local); clocks.start()
     l0 = h.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
@@ -219,7 +221,6 @@ def main():
     barrier()
     total_ms = ev[0].elapsed_time(ev[K])
     launches = h.kernel_launches - l0
-    clk = clocks.stop()
     per_step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     total_ms_max = sharding.max_over_ranks(total_ms, device=dev)
     value = 3.0 * n * world * K / (total_ms_max * 1e-3)
@@ -299,6 +300,7 @@ def main():
     bad = int(((chk["status"] & 7) != 0).sum())
     for p_ in pipe:
         p_["h"].close()
+    clk = clocks.stop()
 
     # ---- final gather of the result records (the only collective on this path) -----------------------------
     last = np.frombuffer(slots[(W + K - 1) % n_slots]["out"].cpu().numpy().tobytes(), dtype=abi.FORMC_OUT)

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 #include "formc.cuh"
+#include "formc_warp.cuh"
 #include "forma.cuh"
 #include "launch.h"
 
@@ -30,12 +31,16 @@ struct ismpc_handle {
     long long launches = 0;
     char err[256] = {0};
     int opt_formc_cluster = 0;     // 0 = automatic
+    int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
+    int w_resident = 0;            // CTAs of the warp kernels the GPU keeps resident at this model's N (0 = not queried yet)
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
     DevBuf c_tables, c_work, c_info, c_ptab;
+    DevBuf c_ric_none, c_ric_gait, c_ws;   // Riccati tables (warp kernels) and the per-warp workspace of their general path
     int gait_S = 0, gait_F = 0;            // prepared gait (projector tables in c_ptab), 0 = none
+    int ric_S = 0, ric_F = 0;              // prepared gait of the Riccati tables (c_ric_gait), 0 = none
     // form A
     bool forma_ready = false;
     ismpc_forma_model_t am{};
@@ -92,7 +97,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
 {
     if (!h) return ISMPC_ERR_ARG;
     cudaSetDevice(h->device);
-    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_ws, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
@@ -106,6 +111,16 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     if (strcmp(name, "formc_cluster_size") == 0) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return ISMPC_ERR_ARG;
         h->opt_formc_cluster = value;
+        return ISMPC_OK;
+    }
+    if (strcmp(name, "formc_variant") == 0) {      // experiment knob: register budget of the warp tick kernel
+        formc_set_variant(value);
+        h->w_resident = 0;
+        return ISMPC_OK;
+    }
+    if (strcmp(name, "formc_kernel") == 0) {
+        if (value < 0 || value > 2) return ISMPC_ERR_ARG;
+        h->opt_formc_kernel = value;
         return ISMPC_OK;
     }
     return ISMPC_ERR_ARG;
@@ -134,8 +149,12 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
     int info = 0;
     CK(cudaMemcpy(&info, h->c_info.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) return ISMPC_ERR_MODEL;     // H_z not positive definite
+    if (h->c_ric_none.ensure((size_t)m->N * FORMC_RIC_W * sizeof(double))) return ISMPC_ERR_ALLOC;
+    rc = formc_riccati_launch(*m, 0, 0, 1, (double*)h->c_ric_none.p, 0, &h->launches);
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_riccati_launch");
+    CK(cudaStreamSynchronize(0));
     h->cm = *m;
-    h->gait_S = h->gait_F = 0;
+    h->gait_S = h->gait_F = 0; h->ric_S = h->ric_F = 0; h->w_resident = 0;
     h->c_ctas_per_sm = formc_cluster_ctas_per_sm(m->N);
     h->formc_ready = true;
     return ISMPC_OK;
@@ -164,19 +183,72 @@ static void formc_fill_args(ismpc_handle* h, FormCArgs& a, int n)
     a.T.gS = h->gait_S; a.T.gF = h->gait_F;
 }
 
+// Warp-per-instance kernels cover N <= 512; the CTA/cluster kernels stay for the cluster latency mode and on request.
+static bool formc_use_warp(const ismpc_handle* h)
+{
+    if (h->opt_formc_kernel == 1 || h->opt_formc_cluster > 0) return false;   // an explicit cluster size asks for the CTA/cluster family
+    return formc_warp_supported(h->cm.N) != 0;
+}
+
+// Resident CTAs of the warp kernels are queried once per model (the occupancy query costs microseconds per call).
+static int formc_warp_grid_cached(ismpc_handle* h, int n)
+{
+    if (h->w_resident <= 0) h->w_resident = formc_warp_grid(h->cm.N, 1 << 30, h->sm_count);
+    return n < h->w_resident ? n : h->w_resident;
+}
+
+// One tick launch (either kernel family) on device-resident arguments.
+static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStream_t st)
+{
+    if (!formc_use_warp(h)) return formc_tick_launch(a, n, formc_cluster_size(h, n), st);
+    const int grid = formc_warp_grid_cached(h, n);
+    FormCWarpArgs wa;
+    wa.base = a;
+    wa.R.none = (const double*)h->c_ric_none.p;
+    wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
+    wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
+    wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
+    if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
+    wa.ws = (double*)h->c_ws.p;
+    return formc_tick_warp_launch(wa, grid, st);
+}
+
+static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
+                                const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, cudaStream_t st)
+{
+    if (!formc_use_warp(h)) return formc_rollout_launch(a, state_io, walk_io, push, n_ticks, traj, status, n, st);
+    const int grid = formc_warp_grid_cached(h, n);
+    FormCWarpArgs wa;
+    wa.base = a;
+    wa.R.none = (const double*)h->c_ric_none.p;
+    wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
+    wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
+    wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
+    if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
+    wa.ws = (double*)h->c_ws.p;
+    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, grid, st);
+}
+
 extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)
 {
     if (!h) return ISMPC_ERR_ARG;
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
     if (S < 0 || F_ds < 0 || S + F_ds <= 0 || S + F_ds > 4096) return ISMPC_ERR_ARG;
-    if (h->gait_S == S && h->gait_F == F_ds) return ISMPC_OK;
+    if (h->gait_S == S && h->gait_F == F_ds && h->ric_S == S && h->ric_F == F_ds) return ISMPC_OK;
     CK(cudaSetDevice(h->device));
     const size_t NN = (size_t)h->cm.N * h->cm.N;
-    h->gait_S = h->gait_F = 0;
+    h->gait_S = h->gait_F = 0; h->ric_S = h->ric_F = 0;
+    // Riccati gain tables of the warp kernels: one pattern per mpcIter
+    if (h->c_ric_gait.ensure((size_t)(S + F_ds) * h->cm.N * FORMC_RIC_W * sizeof(double))) return ISMPC_ERR_ALLOC;
+    int rc = formc_riccati_launch(h->cm, S, F_ds, 0, (double*)h->c_ric_gait.p, 0, &h->launches);
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_riccati_launch");
+    CK(cudaStreamSynchronize(0));
+    h->ric_S = S; h->ric_F = F_ds;
+    // projector tables of the CTA/cluster kernels
     if (h->c_ptab.ensure((size_t)(S + F_ds) * NN * sizeof(double))) return ISMPC_ERR_ALLOC;
     CK(cudaMemset(h->c_info.p, 0, sizeof(int)));
-    int rc = formc_prepare_gait_launch(h->cm.N, S, F_ds, (const double*)h->c_tables.p, (double*)h->c_ptab.p,
-                                       (int*)h->c_info.p, 0, &h->launches);
+    rc = formc_prepare_gait_launch(h->cm.N, S, F_ds, (const double*)h->c_tables.p, (double*)h->c_ptab.p,
+                                   (int*)h->c_info.p, 0, &h->launches);
     if (rc == -1) return ISMPC_OK;             // block too large for shared memory: stay on the generic path
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_prepare_gait_launch");
     int info = 0;
@@ -204,13 +276,13 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     if (mem == ISMPC_MEM_DEVICE) {
         a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt; a.plan_rows = plan_rows;
         a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
-        int rc = formc_tick_launch(a, n, formc_cluster_size(h, n), st);
+        int rc = formc_launch_tick(h, a, n, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
-    if (h->gait_S + h->gait_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+    if (h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
         int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);      // host buffers: the gait can be read here
         if (prc != ISMPC_OK) return prc;
         formc_fill_args(h, a, n);
@@ -231,7 +303,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     a.out = (ismpc_formc_out_t*)h->s_cout.p;
     a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
     a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
-    int rc = formc_tick_launch(a, n, formc_cluster_size(h, n), st);
+    int rc = formc_launch_tick(h, a, n, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
     CK(cudaMemcpyAsync(out, h->s_cout.p, n * sizeof(ismpc_formc_out_t), cudaMemcpyDeviceToHost, st));
@@ -258,13 +330,13 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     a.out = nullptr; a.primal = nullptr; a.active = nullptr; a.plan_rows = plan_rows;
     if (mem == ISMPC_MEM_DEVICE) {
         a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt;
-        int rc = formc_rollout_launch(a, state, walk, push, n_ticks, traj_opt, status_opt, n, st);
+        int rc = formc_launch_rollout(h, a, n, state, walk, push, n_ticks, traj_opt, status_opt, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
-    if (h->gait_S + h->gait_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+    if (h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
         int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);
         if (prc != ISMPC_OK) return prc;
         formc_fill_args(h, a, n);
@@ -283,10 +355,10 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     if (push) CK(cudaMemcpyAsync(h->s_push.p, push, n * sizeof(ismpc_push_t), cudaMemcpyHostToDevice, st));
     a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
     a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = (const double*)h->s_plan.p;
-    int rc = formc_rollout_launch(a, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
+    int rc = formc_launch_rollout(h, a, n, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr,
-                                  status_opt ? (int32_t*)h->s_status.p : nullptr, n, st);
+                                  status_opt ? (int32_t*)h->s_status.p : nullptr, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
     CK(cudaMemcpyAsync(state, h->s_state.p, n * sizeof(ismpc_state_t), cudaMemcpyDeviceToHost, st));
@@ -686,9 +758,17 @@ extern "C" int ismpc_measure_fp64_peak(ismpc_handle* h, int reps, double* tflops
 }
 
 #ifdef ISMPC_PHASE_TIMING
-__device__ long long ismpc::g_phase[64];
 extern "C" int ismpc_debug_read_phases(long long* out64)
 {
     return (int)cudaMemcpyFromSymbol(out64, ismpc::g_phase, sizeof(long long) * 64);
+}
+extern "C" int ismpc_debug_read_trace(long long* out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, ismpc::g_trace, sizeof(long long) * n);
+}
+extern "C" int ismpc_debug_reset_phases(void)
+{
+    static const long long zero[64] = {0};
+    return (int)cudaMemcpyToSymbol(ismpc::g_phase, zero, sizeof(zero));
 }
 #endif

@@ -11,7 +11,10 @@ namespace ismpc {
 // g_phase[0..31]: form-C tick phase stamps of CTA 0; g_phase[32..63]: accumulated cycles per section of the
 // dual active-set loop over all warps (DasTimer).
 #ifdef ISMPC_PHASE_TIMING
-extern __device__ long long g_phase[64];
+__device__ long long g_phase[64];     // defined here: the debug build is a single translation unit (unity_dbg.cu)
+__device__ long long g_trace[3 * 8192];   // per CTA of the warp tick kernel: start / end (globaltimer ns), SM id
+__device__ __forceinline__ long long dbg_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int dbg_smid() { int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
 struct DasTimer {
     long long t;
     __device__ __forceinline__ void start() { t = clock64(); }

@@ -1,0 +1,709 @@
+// formc_warp.cuh -- formulation C (MPCSolver::solve), one WARP (= one 32-thread CTA) per instance.
+//
+// Same reference map as formc.cuh (AMR_code_DART/MPCSolver.cpp:204-501); what changes is the shape of the work:
+//
+//  * Lane l owns the E = ceil(N/32) consecutive horizon samples [l*E, l*E+E) of every length-N vector (E = 4 at
+//    N = 100).  Vectors live in the CTA's shared memory as [e][lane] (conflict-free, and private to the lane that
+//    owns the sample); every stage is a short ROLLED loop over e plus one warp scan over shuffles.  There is no
+//    CTA barrier anywhere, and the whole tick is ~1.5 k SASS instructions, so it stays in the instruction caches:
+//    the first, fully unrolled register version of this kernel executed 5 k straight-line instructions per
+//    instance and spent half its time waiting for instruction fetch (profiles/r1h_*).  The CTA is one warp so that
+//    every branch is provably warp-uniform for the compiler (no WARPSYNC/ENDCOLLECTIVE pairs around the shuffles).
+//  * Stage 1 (vertical QP, MPCSolver.cpp:220-269) is not solved through H_z^-1 at all.  min 1/2 f'H_z f + F_z'f with
+//    H_z = q_p S'S + q_v Sv'Sv + q_u I is the condensed form of a finite-horizon LQ tracking problem on the double
+//    integrator  x_k = (p_k, V_k),  x_{k+1} = A x_k + B v_k,  A = [1 dt; 0 1],  B = [dt^2; dt],  v_k = f_k/m - g,
+//    with stage cost q_p (p_k - h - mid_z[k])^2 + q_v V_k^2 + q_u m^2 v_k^2   (S_bar_z[k][j] = (k-j) dt^2/m, j < k).
+//    Its minimiser -- the same f, the QP is strictly convex -- follows from the Riccati recursion: gains K_k and
+//    1/R_k depend only on the model and on WHICH samples carry the flight-phase equality f_k = 0 (there the input
+//    is fixed: P_k = Q + A'P_{k+1}A), i.e. on mpcIter; they are tabulated per mpcIter of a prepared gait (N x 4
+//    doubles per pattern instead of an N x N projector) or recomputed in-warp for any other (S, F_ds).
+//    The instance-dependent part is two affine recurrences with 2x2 coefficient matrices,
+//        s_k = Phi_k' s_{k+1} + w_k   (backward, w_k from the reference height)  and
+//        x_{k+1} = Phi_k x_k + B omega_k   (forward, omega_k from s_{k+1}),
+//    each evaluated as a chunked warp scan over affine maps: O(N) work, O(log 32) depth, 3 KB of table reads per
+//    instance instead of the 80 KB row-sweep of the N x N table.
+//  * The rows 0 <= S_bar_z f <= fz_max are then checked (S_bar_z f = p - T_z z0 - T_g); only if one is violated the
+//    warp runs the general dual active set (das.cuh) on a per-warp GLOBAL-memory workspace (rare path).
+//  * Stage 2: cosh(s dt), sinh(s dt)/s and s sinh(s dt) are even in s = sqrt(lambda), i.e. power series in
+//    lambda dt^2 (<= 0.04 on this path): 9 terms reach 1e-17, no sqrt / exp / division.
+//  * Stage 3: x and y share the stability row, so the prefix/suffix scans of the knapsack solve (formc.cuh:
+//    knapsack_qp) are done once for both axes; a non-prefix saturation pattern falls back to Newton passes on the
+//    multiplier (both axes per pass).
+#pragma once
+#include "formc.cuh"
+
+namespace ismpc {
+
+constexpr int FORMC_RIC_W = 4;          // doubles per (pattern, sample) in the Riccati tables
+constexpr int FORMC_WARP_VECS = 11;     // shared-memory vectors per instance (E*32 doubles each)
+
+struct FormCRiccati {
+    const double* none;   // [N][4]            pattern without equalities (footstepCounter <= 1), built with the model
+    const double* gait;   // [gS+gF][N][4]     one pattern per mpcIter of the prepared gait; null if none
+    int gS, gF;
+};
+
+// Flight-phase samples [c_lo, c_lo+ne) of the horizon at mpcIter m (MPCSolver.cpp:223-243, indices as written there).
+__host__ __device__ inline void formc_flight_range(int N, int S, int F, int mpc_iter, int& c_lo, int& ne)
+{
+    if (mpc_iter < S) { ne = F; c_lo = S - mpc_iter; }       // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
+    else { ne = S + F - mpc_iter; c_lo = 0; }                // Aeq_z(i,i), i < S+F-mpcIter
+    if (c_lo < 0) { ne += c_lo; c_lo = 0; }
+    if (c_lo + ne > N) ne = N - c_lo;
+    if (ne < 0) ne = 0;
+}
+
+// One backward step of the Riccati recursion for sample k, given P = P_{k+1} (symmetric 2x2).
+// Table entry: free sample  -> (K0, K1, 1/R, 0)      v_k = -K x_k - (B's_{k+1})/R
+//              fixed sample -> (e0, e1, 0, -g)       v_k = -g,  s_k = q_k + A's_{k+1} + e,  e = -g A'P_{k+1}B
+struct RicP { double p00, p01, p11; };
+__host__ __device__ __forceinline__ void riccati_step(RicP& P, bool fixed, double dt, double rho, double qp, double qv,
+                                                      double g, double& a, double& b, double& c, double& d)
+{
+    const double B0 = dt * dt, B1 = dt;
+    const double pb0 = P.p00 * B0 + P.p01 * B1, pb1 = P.p01 * B0 + P.p11 * B1;          // P B
+    const double n00 = P.p00, n01 = P.p00 * dt + P.p01, n11 = (P.p00 * dt + 2.0 * P.p01) * dt + P.p11;   // A'PA
+    const double h0 = pb0, h1 = dt * pb0 + pb1;                                           // (B'PA)'
+    if (fixed) {
+        a = -g * h0; b = -g * h1; c = 0.0; d = -g;
+        P.p00 = qp + n00; P.p01 = n01; P.p11 = qv + n11;
+    } else {
+        const double rinv = 1.0 / (rho + B0 * pb0 + B1 * pb1);
+        a = h0 * rinv; b = h1 * rinv; c = rinv; d = 0.0;
+        P.p00 = qp + n00 - h0 * a; P.p01 = n01 - h0 * b; P.p11 = qv + n11 - h1 * b;
+    }
+}
+
+#ifdef ISMPC_PHASE_TIMING
+#define ISMPC_WPHASE(k) do { const long long n_ = clock64(); if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_phase[k]), (unsigned long long)(n_ - wt_)); wt_ = clock64(); } while (0)
+#define ISMPC_WPHASE_BEGIN long long wt_ = clock64()
+#define ISMPC_WCOUNT(k) do { if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_phase[k]), 1ULL); } while (0)
+#else
+#define ISMPC_WPHASE(k) do { } while (0)
+#define ISMPC_WPHASE_BEGIN do { } while (0)
+#define ISMPC_WCOUNT(k) do { } while (0)
+#endif
+
+// u / per and u % per for 0 <= u < 2^22 through a float reciprocal (exact after one correction step).
+__device__ __forceinline__ void fast_divmod(int u, int per, float rcp, int& q, int& r)
+{
+    q = (int)((float)u * rcp);
+    r = u - q * per;
+    if (r < 0) { --q; r += per; }
+    if (r >= per) { ++q; r -= per; }
+}
+
+// MPCSolver.cpp:167-180: (x, y, z) of ftsp_midpoint at step index i, in-step sample r.
+// (the ramp weight (r-S)/F is formed as (r-S) * (1/F): one rounding more than the reference's division, 1e-16 relative)
+template <bool WANT_Z>
+__device__ __forceinline__ void midpoint_xyz(const double* __restrict__ rows, int n_steps, int S, double invF, int i, int r,
+                                             double& x, double& y, double& z)
+{
+    x = 0.0; y = 0.0; z = 0.0;
+    if (i >= n_steps - 1) return;                                     // last step's rows stay 0
+    const double w = r < S ? 0.0 : (double)(r - S) * invF;
+    const int j = r < S ? i : i + 1;                                  // r < S: b := a, the ramp term vanishes exactly
+    const double ax = __ldg(rows + 4 * i), ay = __ldg(rows + 4 * i + 1);
+    const double bx = __ldg(rows + 4 * j), by = __ldg(rows + 4 * j + 1);
+    x = ax * 1.0 + (bx - ax) * w; y = ay * 1.0 + (by - ay) * w;
+    if (WANT_Z) {
+        const double az = __ldg(rows + 4 * i + 2), bz = __ldg(rows + 4 * j + 2);
+        z = az * 1.0 + (bz - az) * w;
+    }
+}
+
+// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; x normal and finite on this path (CoM heights).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Per-warp global workspace of the general vertical path (doubles).
+__host__ __device__ inline size_t formc_warp_ws_doubles(int N)
+{
+    size_t d = (size_t)4 * N + (FORMC_QMAX * (FORMC_QMAX + 1)) / 2 + 3 * FORMC_QMAX;
+    size_t bytes = FORMC_QMAX * sizeof(int) + FORMC_QMAX + (size_t)N;
+    return ((d + (bytes + 7) / 8) + 3) & ~(size_t)3;
+}
+__host__ __device__ inline int formc_warp_epl(int N) { return (N + 31) >> 5; }
+__host__ __device__ inline size_t formc_warp_smem_bytes(int N)
+{
+    return (size_t)FORMC_WARP_VECS * formc_warp_epl(N) * 32 * sizeof(double);
+}
+
+struct FormCWarpShared {     // [e*32 + lane] each
+    double *mx, *my;         // midpoint window x, y
+    double *rq;              // -q_p (h + mid_z)
+    double *ta, *tb, *tc, *td;   // Riccati table entries of this instance's pattern; later: P1, Lm (knapsack), cosh, sinh/s
+    double *om;              // omega; later s*sinh
+    double *f, *p;           // forces, CoM heights
+    double *av;              // stability row
+};
+__device__ __forceinline__ void formc_warp_carve(double* base, int E, FormCWarpShared& s)
+{
+    const int L = E * 32;
+    s.mx = base; s.my = base + L; s.rq = base + 2 * L; s.ta = base + 3 * L; s.tb = base + 4 * L; s.tc = base + 5 * L;
+    s.td = base + 6 * L; s.om = base + 7 * L; s.f = base + 8 * L; s.p = base + 9 * L; s.av = base + 10 * L;
+}
+
+// Vertical LQ solve with the table entries in sm.ta..td: fills sm.om, sm.f (forces), sm.p (z_pos_k).
+// x0 = (z0 + dt zd0, zd0).
+__device__ __forceinline__ void riccati_solve(const FormCWarpShared& sm, int N, int E, int lane, double dt, double mass,
+                                              double g, double x00, double x01)
+{
+    const double B0 = dt * dt, B1 = dt;
+    // ---- backward: s_k = Phi_k' s_{k+1} + w_k, s_N = 0.  Chunk map s_lo = M s_hi + v.
+    double m00 = 1.0, m01 = 0.0, m10 = 0.0, m11 = 1.0, v0 = 0.0, v1 = 0.0;
+#pragma unroll 1
+    for (int e = E - 1; e >= 0; --e) {
+        if (lane * E + e < N) {
+            const int x = e * 32 + lane;
+            const double a = sm.ta[x], b = sm.tb[x];
+            const bool fixed = sm.td[x] != 0.0;
+            const double K0 = fixed ? 0.0 : a, K1 = fixed ? 0.0 : b;
+            const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+            const double w0 = sm.rq[x] + (fixed ? a : 0.0), w1 = fixed ? b : 0.0;
+            const double n00 = f00 * m00 + f10 * m10, n01 = f00 * m01 + f10 * m11;
+            const double n10 = f01 * m00 + f11 * m10, n11 = f01 * m01 + f11 * m11;
+            const double u0 = f00 * v0 + f10 * v1 + w0, u1 = f01 * v0 + f11 * v1 + w1;
+            m00 = n00; m01 = n01; m10 = n10; m11 = n11; v0 = u0; v1 = u1;
+        }
+    }
+    // inclusive suffix composition over lanes: (M, v)_L := (M, v)_L o (M, v)_{L+o}
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        const double h00 = __shfl_down_sync(ISMPC_FULL_MASK, m00, o), h01 = __shfl_down_sync(ISMPC_FULL_MASK, m01, o);
+        const double h10 = __shfl_down_sync(ISMPC_FULL_MASK, m10, o), h11 = __shfl_down_sync(ISMPC_FULL_MASK, m11, o);
+        const double g0 = __shfl_down_sync(ISMPC_FULL_MASK, v0, o), g1 = __shfl_down_sync(ISMPC_FULL_MASK, v1, o);
+        if (lane + o < 32) {
+            v0 += m00 * g0 + m01 * g1; v1 += m10 * g0 + m11 * g1;
+            const double n00 = m00 * h00 + m01 * h10, n01 = m00 * h01 + m01 * h11;
+            const double n10 = m10 * h00 + m11 * h10, n11 = m10 * h01 + m11 * h11;
+            m00 = n00; m01 = n01; m10 = n10; m11 = n11;
+        }
+    }
+    double s0 = __shfl_down_sync(ISMPC_FULL_MASK, v0, 1), s1 = __shfl_down_sync(ISMPC_FULL_MASK, v1, 1);   // s at the chunk's end
+    if (lane == 31) { s0 = 0.0; s1 = 0.0; }
+    // omega_k = d_k - (1/R_k) B's_{k+1}  (free: d = 0; fixed: 1/R = 0, d = -g)
+#pragma unroll 1
+    for (int e = E - 1; e >= 0; --e) {
+        if (lane * E + e < N) {
+            const int x = e * 32 + lane;
+            const double a = sm.ta[x], b = sm.tb[x], d = sm.td[x];
+            const bool fixed = d != 0.0;
+            const double K0 = fixed ? 0.0 : a, K1 = fixed ? 0.0 : b;
+            sm.om[x] = d - sm.tc[x] * (B0 * s0 + B1 * s1);
+            const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+            const double w0 = sm.rq[x] + (fixed ? a : 0.0), w1 = fixed ? b : 0.0;
+            const double u0 = f00 * s0 + f10 * s1 + w0, u1 = f01 * s0 + f11 * s1 + w1;
+            s0 = u0; s1 = u1;
+        }
+    }
+    // ---- forward: x_{k+1} = Phi_k x_k + B omega_k.  Chunk map x_hi = M x_lo + v; lane 0 folds x_0 in (M := 0).
+    m00 = 1.0; m01 = 0.0; m10 = 0.0; m11 = 1.0; v0 = 0.0; v1 = 0.0;
+    if (lane == 0) { v0 = x00; v1 = x01; m00 = 0.0; m11 = 0.0; }
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        if (lane * E + e < N) {
+            const int x = e * 32 + lane;
+            const bool fixed = sm.td[x] != 0.0;
+            const double K0 = fixed ? 0.0 : sm.ta[x], K1 = fixed ? 0.0 : sm.tb[x];
+            const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+            const double om = sm.om[x];
+            const double u0 = f00 * v0 + f01 * v1 + B0 * om, u1 = f10 * v0 + f11 * v1 + B1 * om;
+            const double n00 = f00 * m00 + f01 * m10, n01 = f00 * m01 + f01 * m11;
+            const double n10 = f10 * m00 + f11 * m10, n11 = f10 * m01 + f11 * m11;
+            m00 = n00; m01 = n01; m10 = n10; m11 = n11;     // lane 0: stays 0
+            v0 = u0; v1 = u1;
+        }
+    }
+    // inclusive prefix composition over lanes: (M, v)_L := (M, v)_L o (M, v)_{L-o}
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        const double h00 = __shfl_up_sync(ISMPC_FULL_MASK, m00, o), h01 = __shfl_up_sync(ISMPC_FULL_MASK, m01, o);
+        const double h10 = __shfl_up_sync(ISMPC_FULL_MASK, m10, o), h11 = __shfl_up_sync(ISMPC_FULL_MASK, m11, o);
+        const double g0 = __shfl_up_sync(ISMPC_FULL_MASK, v0, o), g1 = __shfl_up_sync(ISMPC_FULL_MASK, v1, o);
+        if (lane >= o) {
+            v0 += m00 * g0 + m01 * g1; v1 += m10 * g0 + m11 * g1;
+            const double n00 = m00 * h00 + m01 * h10, n01 = m00 * h01 + m01 * h11;
+            const double n10 = m10 * h00 + m11 * h10, n11 = m10 * h01 + m11 * h11;
+            m00 = n00; m01 = n01; m10 = n10; m11 = n11;
+        }
+    }
+    double c0 = __shfl_up_sync(ISMPC_FULL_MASK, v0, 1), c1 = __shfl_up_sync(ISMPC_FULL_MASK, v1, 1);       // x at the chunk's start
+    if (lane == 0) { c0 = x00; c1 = x01; }
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int x = e * 32 + lane;
+        if (lane * E + e < N) {
+            const bool fixed = sm.td[x] != 0.0;
+            const double K0 = fixed ? 0.0 : sm.ta[x], K1 = fixed ? 0.0 : sm.tb[x];
+            const double om = sm.om[x];
+            sm.p[x] = c0;
+            const double vk = om - (K0 * c0 + K1 * c1);
+            sm.f[x] = fixed ? 0.0 : mass * (vk + g);
+            const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+            const double u0 = f00 * c0 + f01 * c1 + B0 * om, u1 = f10 * c0 + f11 * c1 + B1 * om;
+            c0 = u0; c1 = u1;
+        } else { sm.p[x] = 1.0; sm.f[x] = 0.0; }
+    }
+}
+
+// Table entries of one pattern -> sm.ta..td
+__device__ __forceinline__ void riccati_load(const FormCWarpShared& sm, const double* __restrict__ tab, int N, int E, int lane)
+{
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e, x = e * 32 + lane;
+        double2 q0 = make_double2(0.0, 0.0), q1 = make_double2(0.0, 0.0);
+        if (i < N) {
+            q0 = __ldg(reinterpret_cast<const double2*>(tab + (size_t)i * FORMC_RIC_W));
+            q1 = __ldg(reinterpret_cast<const double2*>(tab + (size_t)i * FORMC_RIC_W + 2));
+        }
+        sm.ta[x] = q0.x; sm.tb[x] = q0.y; sm.tc[x] = q1.x; sm.td[x] = q1.y;
+    }
+}
+
+// General vertical path (a row of 0 <= S_bar_z f <= fz_max is violated at the equality-constrained minimiser):
+// dual active set from the unconstrained minimiser, equalities first.  ws: this warp's global workspace, with the
+// unconstrained minimiser already stored in ws[0..N).  On return ws[0..N) = f, ws[N..2N) = S_bar_z f, state bytes
+// at the returned pointer.  Returns 0 or ISMPC_ST_Z_FAIL.
+static __device__ __noinline__ int formc_vertical_general(int N, FormCTables T, double c1, double fz_max, double* ws, int c_lo,
+                                                          int ne, int* it_z, signed char** state_out)
+{
+    const int lane = lane_id();
+    double* d = ws;
+    double* x = d; d += N;
+    double* rv = d; d += N;
+    double* z = d; d += N;
+    double* scr = d; d += N;
+    DasWork w;
+    w.Js = d; d += (FORMC_QMAX * (FORMC_QMAX + 1)) / 2;
+    w.Jg = nullptr; w.R = FORMC_QMAX;
+    w.mu = d; d += FORMC_QMAX; w.r = d; d += FORMC_QMAX; w.y = d; d += FORMC_QMAX;
+    w.wid = reinterpret_cast<int*>(d);
+    w.wsg = reinterpret_cast<signed char*>(w.wid + FORMC_QMAX);
+    w.state = w.wsg + FORMC_QMAX;
+    w.qmax = FORMC_QMAX; w.q = 0; w.neq = 0;
+    for (int i = lane; i < N; i += 32) w.state[i] = 0;
+    __syncwarp();
+    VertProb vp{N, T, c1, fz_max, scr};
+    int zfail = 0;
+    for (int e = 0; e < ne; ++e) {
+        int rc = das_add_equality(vp, w, x, z, N + c_lo + e, x[c_lo + e], 0.0);
+        if (rc < 0) zfail = 1;
+        __syncwarp();
+    }
+    w.neq = w.q;
+    int rc = das_solve(vp, w, x, rv, z, 4 * N + 16, it_z);
+    __syncwarp();
+    *state_out = w.state;
+    return (rc != 0 || zfail) ? ISMPC_ST_Z_FAIL : 0;
+}
+
+// cosh(x), sinh(x)/s, s*sinh(x) with x = s*dt, s = sqrt(lam), as power series in y = lam*dt^2 (y <= 0.25).
+__device__ __forceinline__ void lip_series(double lam, double dt, double& ch, double& shs, double& ssh)
+{
+    const double y = lam * dt * dt;
+    // cosh = sum y^k/(2k)!,  sinh(x)/x = sum y^k/(2k+1)!   (Horner, k = 8..0)
+    double c = 1.0 / 20922789888000.0, s = 1.0 / 355687428096000.0;
+    c = c * y + 1.0 / 87178291200.0;  s = s * y + 1.0 / 1307674368000.0;
+    c = c * y + 1.0 / 479001600.0;    s = s * y + 1.0 / 6227020800.0;
+    c = c * y + 1.0 / 3628800.0;      s = s * y + 1.0 / 39916800.0;
+    c = c * y + 1.0 / 40320.0;        s = s * y + 1.0 / 362880.0;
+    c = c * y + 1.0 / 720.0;          s = s * y + 1.0 / 5040.0;
+    c = c * y + 1.0 / 24.0;           s = s * y + 1.0 / 120.0;
+    c = c * y + 0.5;                  s = s * y + 1.0 / 6.0;
+    c = c * y + 1.0;                  s = s * y + 1.0;
+    ch = c; shs = dt * s; ssh = lam * dt * s;
+}
+__device__ __forceinline__ void lip_matrices(double lam, double dt, double& ch, double& shs, double& ssh)
+{
+    if (lam < 2.0) { ch = 1.0; shs = dt; ssh = 0.0; }                               // integrator (MPCSolver.cpp:353-355)
+    else if (lam * dt * dt <= 0.25) lip_series(lam, dt, ch, shs, ssh);
+    else {
+        const double s = sqrt(lam);
+        const double ex = exp(s * dt), ei = 1.0 / ex;
+        const double c = 0.5 * (ex + ei), sh = 0.5 * (ex - ei);
+        ch = c; shs = sh / s; ssh = s * sh;                                          // (:357-360)
+    }
+}
+
+struct FormCWarpArgs {
+    FormCArgs base;
+    FormCRiccati R;
+    double* ws;            // per-warp workspaces of the general vertical path
+    size_t ws_stride;      // doubles per warp
+};
+
+// One tick of one instance by one warp.  Result record in r (identical in all lanes); prim/act optional.
+__device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const ismpc_formc_model_t& mdl, const FormCTables& T,
+                                                const FormCRiccati& R, const ismpc_state_t& st, const ismpc_walk_t& wk,
+                                                const ismpc_formc_inst_t& in, const double* __restrict__ plan_all,
+                                                double* ws, ismpc_formc_out_t& r, double* prim, signed char* act)
+{
+    const int lane = lane_id();
+    const int N = mdl.N, E = formc_warp_epl(N);
+    const double dt = mdl.dt, mass = mdl.mass, g = mdl.g;
+    const double h = in.com_height;
+    const double eta = sqrt(g / h);                       // parameters.cpp:41
+    const int S = in.S, F = in.F_ds, per = S + F;
+    const int k0 = (int)(wk.sim_time / (dt / mdl.dtc));   // MPCSolver.cpp:259,329
+    int status = 0;
+    ISMPC_WPHASE_BEGIN;
+
+    r.next = st; r.zmp_in[0] = r.zmp_in[1] = 0.0; r.fz0 = 0.0; r.lambda0 = 0.0; r.kkt_res = 0.0;
+    r.status = 0; r.iters[0] = r.iters[1] = r.iters[2] = 0;
+    // (votes make the branch conditions provably warp-uniform for the compiler: the records are the same in all lanes)
+    if (__any_sync(ISMPC_FULL_MASK, k0 < 0 || per <= 0 || (long long)k0 + 2 * N > (long long)in.n_steps * per)) {
+        r.status = ISMPC_ST_WINDOW;
+        return;
+    }
+    __syncwarp();                                          // the previous instance's shared-memory reads are done
+
+    // ---- midpoint window (MPCSolver.cpp:167-180): samples [k0, k0+N), and the anticipative tail (:381-383)
+    //      sum_i exp(-dt eta i) mid[k0+N+i] accumulated on the fly ----
+    const double* rows = plan_all + (size_t)in.plan_first_row * 4;
+    double tx = 0.0, ty = 0.0;
+    {
+        const int q0 = k0 / per, r0 = k0 - q0 * per;
+        const float rcp = 1.0f / (float)per;
+        const double invF = 1.0 / (double)F;
+        const double qd = exp(-dt * eta);
+        double dl = exp(-dt * eta * (double)(lane * E));                             // deltas (:183-184), dl_i = qd^i
+#pragma unroll 1
+        for (int e = 0; e < E; ++e) {
+            const int i = lane * E + e, x = e * 32 + lane;
+            double mxv = 0.0, myv = 0.0, mzv = 0.0;
+            if (i < N) {
+                int qi, ri;
+                fast_divmod(r0 + i, per, rcp, qi, ri);
+                midpoint_xyz<true>(rows, in.n_steps, S, invF, q0 + qi, ri, mxv, myv, mzv);
+                double xt, yt, zt;
+                fast_divmod(r0 + N + i, per, rcp, qi, ri);
+                midpoint_xyz<false>(rows, in.n_steps, S, invF, q0 + qi, ri, xt, yt, zt);
+                tx += dl * xt; ty += dl * yt;
+            }
+            sm.mx[x] = mxv; sm.my[x] = myv; sm.rq[x] = -mdl.q_p * (h + mzv);
+            dl *= qd;
+        }
+    }
+    ISMPC_WPHASE(0);
+
+    // ================= STAGE 1: vertical QP (MPCSolver.cpp:220-269) =================
+    const double z0 = st.com_pos[2], zd0 = st.com_vel[2];
+    const double c1 = dt * dt / mass;
+    const bool running = wk.footstep_counter > 1;
+    int ne = 0, c_lo = 0;
+    if (running) formc_flight_range(N, S, F, wk.mpc_iter, c_lo, ne);
+    {
+        const double* tab = nullptr;
+        if (ne == 0) tab = R.none;
+        else if (R.gait != nullptr && S == R.gS && F == R.gF && wk.mpc_iter >= 0 && wk.mpc_iter < per)
+            tab = R.gait + (size_t)wk.mpc_iter * N * FORMC_RIC_W;
+        if (__any_sync(ISMPC_FULL_MASK, tab != nullptr)) riccati_load(sm, tab, N, E, lane);
+        else {
+            // another step timing than the prepared one: every lane runs the recursion, the owner keeps the sample
+            ISMPC_WCOUNT(30);
+            RicP P{0.0, 0.0, 0.0};
+            const double rho = mdl.q_u * mass * mass;
+            int ol = (N - 1) / E, oe = (N - 1) - ol * E;      // owner lane / slot of sample k
+#pragma unroll 1
+            for (int k = N - 1; k >= 0; --k) {
+                double a, b, c, d;
+                riccati_step(P, k >= c_lo && k < c_lo + ne, dt, rho, mdl.q_p, mdl.q_v, g, a, b, c, d);
+                if (lane == ol) { const int x = oe * 32 + lane; sm.ta[x] = a; sm.tb[x] = b; sm.tc[x] = c; sm.td[x] = d; }
+                if (--oe < 0) { oe = E - 1; --ol; }
+            }
+        }
+    }
+    riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
+    ISMPC_WPHASE(1);
+    // rows 0 <= S_bar_z f <= fz_max  (:158-160):  S_bar_z f = p - T_z z0 - T_g
+    double viol = 0.0;
+    bool bad = false;
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int k = lane * E + e;
+        if (k < N) {
+            const double base = 1.0 * z0 + ((double)(k + 1) * dt) * zd0 - g * (dt * dt) * (0.5 * (double)k * (double)(k + 1));
+            const double v = sm.p[e * 32 + lane] - base;
+            bad = bad || (fmin(v + 1e-10, (mdl.fz_max - v) + 1e-10 * (1.0 + fabs(mdl.fz_max))) < 0.0);
+            viol = fmax(viol, fmax(-v, v - mdl.fz_max));
+        }
+    }
+    int it_z = 0;
+    const bool general = __any_sync(ISMPC_FULL_MASK, bad);
+    signed char* zstate = nullptr;
+    if (general) {
+        ISMPC_WCOUNT(31);
+        // general path: unconstrained minimiser -> workspace -> dual active set -> back to shared memory
+        if (ne > 0) {
+            riccati_load(sm, R.none, N, E, lane);
+            riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
+        }
+        for (int e = 0; e < E; ++e) if (lane * E + e < N) ws[lane * E + e] = sm.f[e * 32 + lane];
+        __syncwarp();
+        status |= formc_vertical_general(N, T, c1, mdl.fz_max, ws, c_lo, ne, &it_z, &zstate);
+        viol = 0.0;
+        for (int e = 0; e < E; ++e) {
+            const int k = lane * E + e;
+            if (k < N) {
+                const double base = 1.0 * z0 + ((double)(k + 1) * dt) * zd0 - g * (dt * dt) * (0.5 * (double)k * (double)(k + 1));
+                const double v = ws[N + k];
+                sm.f[e * 32 + lane] = ws[k];
+                sm.p[e * 32 + lane] = v + base;
+                viol = fmax(viol, fmax(-v, v - mdl.fz_max));
+            }
+        }
+        __syncwarp();
+    }
+    viol = warp_max(viol);
+    double kkt = fmax(0.0, viol);
+    if (prim) for (int e = 0; e < E; ++e) if (lane * E + e < N) prim[lane * E + e] = sm.f[e * 32 + lane];
+    if (act) for (int e = 0; e < E; ++e) if (lane * E + e < N) act[lane * E + e] = zstate ? zstate[lane * E + e] : (signed char)0;
+    ISMPC_WPHASE(2);
+
+    // ================= STAGE 2: lambda sequence (MPCSolver.cpp:296-309), fused with the chunk products of the
+    // stability row a_i = C_sc A_{N-1}...A_{i+1} B_i, C_sc = [1, 1/eta] (:351-379): backward row-vector
+    // recurrence c_{i-1} = c_i A_i, a_i = c_i B_i =================
+    double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;
+    double lam_first = 0.0, f_first = 0.0;
+#pragma unroll 1
+    for (int e = E - 1; e >= 0; --e) {
+        const int x = e * 32 + lane;
+        double ch = 1.0, shs = 0.0, ssh = 0.0;                                       // padding: identity
+        if (lane * E + e < N) {
+            const double fe = sm.f[x];
+            const double zacc = (1.0 / mass) * fe - g;
+            const double l = (g + zacc) * fast_rcp(sm.p[x]);
+            lip_matrices(l, dt, ch, shs, ssh);
+            lam_first = l; f_first = fe;                                             // e = 0 is written last
+            const double n00 = p00 * ch + p01 * ssh, n01 = p00 * shs + p01 * ch;
+            const double n10 = p10 * ch + p11 * ssh, n11 = p10 * shs + p11 * ch;
+            p00 = n00; p01 = n01; p10 = n10; p11 = n11;
+        }
+        sm.tc[x] = ch; sm.td[x] = shs; sm.om[x] = ssh;
+    }
+    const double fz0 = __shfl_sync(ISMPC_FULL_MASK, f_first, 0);
+    const double lam0 = __shfl_sync(ISMPC_FULL_MASK, lam_first, 0);
+    double nz0 = 1.0 * z0 + dt * zd0, nz1 = zd0 + (dt / mass) * fz0 - dt * g;        // (:274)
+    if (isnan(nz0)) { nz0 = h; status |= ISMPC_ST_NAN_GUARD; }                        // (:277-278)
+    if (isnan(nz1)) { nz1 = 0.0; status |= ISMPC_ST_NAN_GUARD; }
+    ISMPC_WPHASE(3);
+
+    // ================= STAGE 3: horizontal QPs (MPCSolver.cpp:322-398) =================
+    double ux0 = 0.0, uy0 = 0.0;
+    int it_x = 0, it_y = 0;
+    const bool horizontal = __any_sync(ISMPC_FULL_MASK, lam0 > 2.0);                 // lam0 is the same in all lanes
+    if (horizontal) {
+        // inclusive suffix products over lanes, then T_L = P_31 ... P_{L+1}
+#pragma unroll 1
+        for (int o = 1; o < 32; o <<= 1) {
+            const double q00 = __shfl_down_sync(ISMPC_FULL_MASK, p00, o), q01 = __shfl_down_sync(ISMPC_FULL_MASK, p01, o);
+            const double q10 = __shfl_down_sync(ISMPC_FULL_MASK, p10, o), q11 = __shfl_down_sync(ISMPC_FULL_MASK, p11, o);
+            if (lane + o < 32) {
+                const double n00 = q00 * p00 + q01 * p10, n01 = q00 * p01 + q01 * p11;
+                const double n10 = q10 * p00 + q11 * p10, n11 = q10 * p01 + q11 * p11;
+                p00 = n00; p01 = n01; p10 = n10; p11 = n11;
+            }
+        }
+        double t00 = __shfl_down_sync(ISMPC_FULL_MASK, p00, 1), t01 = __shfl_down_sync(ISMPC_FULL_MASK, p01, 1);
+        double t10 = __shfl_down_sync(ISMPC_FULL_MASK, p10, 1), t11 = __shfl_down_sync(ISMPC_FULL_MASK, p11, 1);
+        if (lane == 31) { t00 = 1; t01 = 0; t10 = 0; t11 = 1; }
+        const double cs0 = 1.0, cs1 = 1.0 / eta;                                     // C_sc (:375-377), nominal eta
+        double c0 = cs0 * t00 + cs1 * t10, c1r = cs0 * t01 + cs1 * t11;
+        // stability row + the lane-local sums of the knapsack solve
+        const double INF = 1e300;
+        double amx = 0.0, amy = 0.0, t1 = 0.0, t2 = 0.0, mx = 0.0, mn = INF;
+#pragma unroll 1
+        for (int e = E - 1; e >= 0; --e) {
+            const int x = e * 32 + lane;
+            const double ch = sm.tc[x], shs = sm.td[x], ssh = sm.om[x];
+            const double a = c0 * (1.0 - ch) + c1r * (-ssh);                         // B_i = [1-ch; -s*sh]; 0 on padding
+            sm.av[x] = a;
+            const double n0 = c0 * ch + c1r * ssh, n1 = c0 * shs + c1r * ch;
+            c0 = n0; c1r = n1;
+            const double ai = fabs(a);
+            amx += a * sm.mx[x]; amy += a * sm.my[x];
+            t1 += ai; t2 += ai * ai; mx = fmax(mx, ai);
+            if (ai > 0.0) mn = fmin(mn, ai);
+        }
+        const double ps0 = __shfl_sync(ISMPC_FULL_MASK, c0, 0), ps1 = __shfl_sync(ISMPC_FULL_MASK, c1r, 0);   // C_sc * phi_state
+        ISMPC_WPHASE(4);
+
+        // ---- knapsack solve for both axes (formc.cuh: knapsack_qp), scans over |a| shared ----
+        const double rho = running ? in.box_w / 2 : in.box_w_init / 2;                // (:328-338)
+        double aa = t2;
+#pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) {                                            // five sums in one butterfly
+            const double s0 = __shfl_xor_sync(ISMPC_FULL_MASK, tx, o), s1 = __shfl_xor_sync(ISMPC_FULL_MASK, ty, o);
+            const double s2 = __shfl_xor_sync(ISMPC_FULL_MASK, amx, o), s3 = __shfl_xor_sync(ISMPC_FULL_MASK, amy, o);
+            const double s4 = __shfl_xor_sync(ISMPC_FULL_MASK, aa, o);
+            tx += s0; ty += s1; amx += s2; amy += s3; aa += s4;
+        }
+        const double bx = -(ps0 * st.com_pos[0] + ps1 * st.com_vel[0]) + eta * dt * tx;   // (:381-384)
+        const double by = -(ps0 * st.com_pos[1] + ps1 * st.com_vel[1]) + eta * dt * ty;
+        const double rx = bx - amx, ry = by - amy;
+        const double sgx = rx >= 0.0 ? 1.0 : -1.0, sgy = ry >= 0.0 ? 1.0 : -1.0;
+        const double rax = fabs(rx), ray = fabs(ry);
+        double tqx = 0.0, tqy = 0.0;
+        int stx = 0, sty = 0;
+        if (__any_sync(ISMPC_FULL_MASK, aa > 0.0)) {                                  // (the same in all lanes)
+            // P1 = sum |a| before k, Lm = min nonzero |a| before k, S2 = sum a^2 from k on, Mx = max |a| from k on
+            double p1 = t1, sf = t2, pm = mn, sm_ = mx;
+#pragma unroll 1
+            for (int o = 1; o < 32; o <<= 1) {
+                const double a1 = __shfl_up_sync(ISMPC_FULL_MASK, p1, o), a3 = __shfl_up_sync(ISMPC_FULL_MASK, pm, o);
+                const double a2 = __shfl_down_sync(ISMPC_FULL_MASK, sf, o), a4 = __shfl_down_sync(ISMPC_FULL_MASK, sm_, o);
+                if (lane >= o) { p1 += a1; pm = fmin(pm, a3); }
+                if (lane + o < 32) { sf += a2; sm_ = fmax(sm_, a4); }
+            }
+            double P1 = p1 - t1;
+            double Lm = __shfl_up_sync(ISMPC_FULL_MASK, pm, 1); if (lane == 0) Lm = INF;
+            double S2 = sf - t2;
+            double Mx = __shfl_down_sync(ISMPC_FULL_MASK, sm_, 1); if (lane == 31) Mx = 0.0;
+#pragma unroll 1
+            for (int e = 0; e < E; ++e) {
+                const int x = e * 32 + lane;
+                sm.ta[x] = P1; sm.tb[x] = Lm;
+                const double ak = fabs(sm.av[x]);
+                P1 += ak; if (ak > 0.0) Lm = fmin(Lm, ak);
+            }
+            int kbx = 0x7fffffff, kby = 0x7fffffff;
+            double nbx = 0.0, dbx = 1.0, nby = 0.0, dby = 1.0;
+#pragma unroll 1
+            for (int e = E - 1; e >= 0; --e) {
+                const int x = e * 32 + lane;
+                const double ak = fabs(sm.av[x]);
+                S2 += ak * ak; Mx = fmax(Mx, ak);
+                const bool vk = (lane * E + e < N) && (S2 > 0.0);
+                const double lm = sm.tb[x], rs = rho * S2, rp = rho * sm.ta[x];
+                // candidate t_k = num / S2, tested in multiplied-out form (S2 > 0): one division per axis at the end
+                const double numx = rax - rp, numy = ray - rp;
+                const bool nl = !(lm < INF);
+                if (vk && (nl || numx * lm > rs) && !(numx * Mx > rs) && numx >= 0.0) { kbx = lane * E + e; nbx = numx; dbx = S2; }
+                if (vk && (nl || numy * lm > rs) && !(numy * Mx > rs) && numy >= 0.0) { kby = lane * E + e; nby = numy; dby = S2; }
+            }
+            // the smallest valid k wins; its lane broadcasts the quotient
+            int gx = kbx, gy = kby;
+#pragma unroll 1
+            for (int o = 16; o > 0; o >>= 1) {
+                gx = min(gx, __shfl_xor_sync(ISMPC_FULL_MASK, gx, o)); gy = min(gy, __shfl_xor_sync(ISMPC_FULL_MASK, gy, o));
+            }
+            const unsigned wx = __ballot_sync(ISMPC_FULL_MASK, kbx == gx), wy = __ballot_sync(ISMPC_FULL_MASK, kby == gy);
+            tqx = __shfl_sync(ISMPC_FULL_MASK, nbx / dbx, __ffs(wx) - 1);
+            tqy = __shfl_sync(ISMPC_FULL_MASK, nby / dby, __ffs(wy) - 1);
+            const bool needx = gx == 0x7fffffff, needy = gy == 0x7fffffff;
+            if (__any_sync(ISMPC_FULL_MASK, needx || needy)) {
+                // The saturated set is not a prefix (|a| is not monotone where lambda varies): semismooth Newton on the
+                // multiplier from the unsaturated start, both axes in one pass; every pass adds all newly saturated rows,
+                // |nu| grows monotonically, so it ends after a handful of passes (<= N).
+                ISMPC_WCOUNT(29);
+                double ux_ = needx ? rax / aa : tqx, uy_ = needy ? ray / aa : tqy;
+                int prevx = needx ? -1 : -2, prevy = needy ? -1 : -2;           // -2: axis already solved
+#pragma unroll 1
+                for (int it = 0; it < N + 3; ++it) {
+                    double q1x = 0.0, q2x = 0.0, q1y = 0.0, q2y = 0.0;
+                    int cnt = 0;
+#pragma unroll 1
+                    for (int e = 0; e < E; ++e) {
+                        const double ai = fabs(sm.av[e * 32 + lane]);
+                        const bool sx = ux_ * ai > rho, sy = uy_ * ai > rho;
+                        q1x += sx ? ai : 0.0; q2x += sx ? 0.0 : ai * ai;
+                        q1y += sy ? ai : 0.0; q2y += sy ? 0.0 : ai * ai;
+                        cnt += (sx ? 1 : 0) + (sy ? 1024 : 0);
+                    }
+#pragma unroll 1
+                    for (int o = 16; o > 0; o >>= 1) {
+                        q1x += __shfl_xor_sync(ISMPC_FULL_MASK, q1x, o); q2x += __shfl_xor_sync(ISMPC_FULL_MASK, q2x, o);
+                        q1y += __shfl_xor_sync(ISMPC_FULL_MASK, q1y, o); q2y += __shfl_xor_sync(ISMPC_FULL_MASK, q2y, o);
+                        cnt += __shfl_xor_sync(ISMPC_FULL_MASK, cnt, o);
+                    }
+                    const int nx = cnt & 1023, ny = cnt >> 10;
+                    const bool donex = prevx == -2 || nx == prevx, doney = prevy == -2 || ny == prevy;
+                    if (__all_sync(ISMPC_FULL_MASK, donex && doney)) break;
+                    if (!donex) {
+                        prevx = nx;
+                        const double rem = rax - rho * q1x;
+                        if (!(q2x > 0.0)) { if (rem > 1e-12 * fmax(1.0, rax)) stx = 1; prevx = -2; }
+                        else { const double tn = rem / q2x; if (tn >= ux_) ux_ = tn; }
+                    }
+                    if (!doney) {
+                        prevy = ny;
+                        const double rem = ray - rho * q1y;
+                        if (!(q2y > 0.0)) { if (rem > 1e-12 * fmax(1.0, ray)) sty = 1; prevy = -2; }
+                        else { const double tn = rem / q2y; if (tn >= uy_) uy_ = tn; }
+                    }
+                }
+                tqx = ux_; tqy = uy_;
+            }
+        } else {
+            if (rax > 1e-12) stx = 1;
+            if (ray > 1e-12) sty = 1;
+        }
+        const double nux = sgx * tqx, nuy = sgy * tqy;
+        // first input, saturation counts and the equality residuals of the final points
+        double aux = 0.0, auy = 0.0;
+        int nsx = 0, nsy = 0;
+#pragma unroll 1
+        for (int e = E - 1; e >= 0; --e) {
+            const int i = lane * E + e, x = e * 32 + lane;
+            const double a = sm.av[x];
+            const double dx = nux * a, dy = nuy * a;
+            const double uxe = sm.mx[x] + fmin(fmax(dx, -rho), rho), uye = sm.my[x] + fmin(fmax(dy, -rho), rho);
+            aux += a * uxe; auy += a * uye;
+            nsx += (tqx * fabs(a) > rho); nsy += (tqy * fabs(a) > rho);
+            ux0 = uxe; uy0 = uye;                                                     // e = 0 is written last
+            if (i < N) {
+                if (prim) { prim[N + i] = uxe; prim[2 * N + i] = uye; }
+                if (act) {
+                    act[N + i] = (signed char)((dx > rho) ? 1 : ((dx < -rho) ? -1 : 0));
+                    act[2 * N + i] = (signed char)((dy > rho) ? 1 : ((dy < -rho) ? -1 : 0));
+                }
+            }
+        }
+#pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) {
+            aux += __shfl_xor_sync(ISMPC_FULL_MASK, aux, o); auy += __shfl_xor_sync(ISMPC_FULL_MASK, auy, o);
+            nsx += __shfl_xor_sync(ISMPC_FULL_MASK, nsx, o); nsy += __shfl_xor_sync(ISMPC_FULL_MASK, nsy, o);
+        }
+        ux0 = __shfl_sync(ISMPC_FULL_MASK, ux0, 0); uy0 = __shfl_sync(ISMPC_FULL_MASK, uy0, 0);
+        it_x = nsx; it_y = nsy;
+        if (stx) status |= ISMPC_ST_X_FAIL;
+        if (sty) status |= ISMPC_ST_Y_FAIL;
+        kkt = fmax(kkt, fmax(fabs(aux - bx), fabs(auy - by)));
+        ISMPC_WPHASE(5);
+    } else {
+        status |= ISMPC_ST_XY_SKIPPED;
+        if (prim) for (int i = lane; i < 2 * N; i += 32) prim[N + i] = 0.0;
+        if (act) for (int i = lane; i < 2 * N; i += 32) act[N + i] = 0;
+    }
+
+    // ================= integrate (MPCSolver.cpp:402-422) =================
+    {
+        double a00, a01, a10, a11, b0, b1;
+        if (lam0 < 2.0) { a00 = 1.0; a01 = dt; a10 = 0.0; a11 = 1.0; b0 = 0.0; b1 = 0.0; }
+        else {
+            double ch, shs, ssh;
+            lip_matrices(lam0, dt, ch, shs, ssh);
+            a00 = ch; a01 = shs; a10 = ssh; a11 = ch; b0 = 1.0 - ch; b1 = -ssh;
+        }
+        r.next.com_pos[0] = a00 * st.com_pos[0] + a01 * st.com_vel[0] + b0 * ux0;
+        r.next.com_vel[0] = a10 * st.com_pos[0] + a11 * st.com_vel[0] + b1 * ux0;
+        r.next.com_pos[1] = a00 * st.com_pos[1] + a01 * st.com_vel[1] + b0 * uy0;
+        r.next.com_vel[1] = a10 * st.com_pos[1] + a11 * st.com_vel[1] + b1 * uy0;
+        r.next.com_pos[2] = nz0; r.next.com_vel[2] = nz1;
+        r.zmp_in[0] = ux0; r.zmp_in[1] = uy0; r.fz0 = fz0; r.lambda0 = lam0; r.kkt_res = kkt;
+        r.status = status; r.iters[0] = it_z; r.iters[1] = it_x; r.iters[2] = it_y;
+    }
+    ISMPC_WPHASE(6);
+}
+
+}  // namespace ismpc

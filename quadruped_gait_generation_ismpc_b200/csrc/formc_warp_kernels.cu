@@ -1,0 +1,170 @@
+// formc_warp_kernels.cu -- formulation C, warp-per-instance kernels (see formc_warp.cuh) and the Riccati tables.
+#include "formc_warp.cuh"
+#include "launch.h"
+
+namespace ismpc {
+
+// Riccati tables: thread t builds pattern t.  none != 0: the single pattern without equalities; otherwise pattern
+// t = mpcIter of a gait with S single-support and F double-support samples (flight-phase samples fixed to f = 0).
+__global__ void formc_build_riccati(ismpc_formc_model_t m, int S, int F, int n_pat, int none, double* __restrict__ tab)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pat) return;
+    const int N = m.N;
+    int c_lo = 0, ne = 0;
+    if (!none) formc_flight_range(N, S, F, t, c_lo, ne);
+    RicP P{0.0, 0.0, 0.0};
+    const double rho = m.q_u * m.mass * m.mass;
+    double* o = tab + (size_t)t * N * FORMC_RIC_W;
+    for (int k = N - 1; k >= 0; --k) {
+        double a, b, c, d;
+        riccati_step(P, k >= c_lo && k < c_lo + ne, m.dt, rho, m.q_p, m.q_v, m.g, a, b, c, d);
+        o[(size_t)k * FORMC_RIC_W + 0] = a; o[(size_t)k * FORMC_RIC_W + 1] = b;
+        o[(size_t)k * FORMC_RIC_W + 2] = c; o[(size_t)k * FORMC_RIC_W + 3] = d;
+    }
+}
+
+int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, double* tab, cudaStream_t st,
+                         long long* launches)
+{
+    const int n_pat = none ? 1 : S + F;
+    formc_build_riccati<<<(n_pat + 63) / 64, 64, 0, st>>>(m, S, F, n_pat, none, tab);
+    *launches += 1;
+    return (int)cudaGetLastError();
+}
+
+__device__ __forceinline__ void store_record(ismpc_formc_out_t* dst, const ismpc_formc_out_t& r)
+{
+    // 128-byte record, 16-byte aligned (cudaMalloc / array of 128-byte records): eight 16-byte stores by one lane
+    const double2* s = reinterpret_cast<const double2*>(&r);
+    double2* d = reinterpret_cast<double2*>(dst);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(ismpc_formc_out_t) / 16); ++k) d[k] = s[k];
+}
+
+// Fused tick: one warp (a 32-thread CTA) per instance, grid-stride over the batch.
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB)
+formc_tick_warp_kernel(FormCWarpArgs wa)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const FormCArgs& a = wa.base;
+    const int lane = threadIdx.x;
+    const int N = a.model.N;
+    FormCWarpShared sm;
+    formc_warp_carve(smem_d, formc_warp_epl(N), sm);
+    double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
+#ifdef ISMPC_PHASE_TIMING
+    if (lane == 0 && blockIdx.x < 8192) { g_trace[3 * blockIdx.x] = dbg_globaltimer(); g_trace[3 * blockIdx.x + 2] = dbg_smid(); }
+#endif
+    for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
+        const ismpc_state_t st = a.state[inst];
+        const ismpc_walk_t wk = a.walk[inst];
+        const ismpc_formc_inst_t in = a.inst[inst];
+        ismpc_formc_out_t r;
+        formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
+                        a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
+                        a.active ? a.active + (size_t)inst * 3 * N : nullptr);
+        if (lane == 0) store_record(a.out + inst, r);
+    }
+#ifdef ISMPC_PHASE_TIMING
+    if (lane == 0 && blockIdx.x < 8192) g_trace[3 * blockIdx.x + 1] = dbg_globaltimer();
+#endif
+}
+
+// Closed loop: the warp keeps its instance and advances it n_ticks times (Controller::update bookkeeping,
+// Controller.cpp:297-302 with the footstep switch enabled, :503-504).
+__global__ void __launch_bounds__(32, 1)
+formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,
+                          int n_ticks, double* traj, int32_t* status_out)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const FormCArgs& a = wa.base;
+    const int lane = threadIdx.x;
+    FormCWarpShared sm;
+    formc_warp_carve(smem_d, formc_warp_epl(a.model.N), sm);
+    double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
+    for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
+        ismpc_state_t st = state_io[inst];
+        ismpc_walk_t wk = walk_io[inst];
+        const ismpc_formc_inst_t in = a.inst[inst];
+        ismpc_push_t pu; pu.fs = 0; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
+        if (push) pu = push[inst];
+        int acc_status = 0;
+        const double* plan_t = a.plan + (size_t)in.plan_first_row * 4;
+#pragma unroll 1
+        for (int tick = 0; tick < n_ticks; ++tick) {
+            if (wk.footstep_counter < in.n_steps &&
+                wk.sim_time >= __ldg(plan_t + (size_t)wk.footstep_counter * 4 + 3) - 1.0) {      // Controller.cpp:297-302
+                wk.control_iter = 0; wk.mpc_iter = 0; wk.footstep_counter += 1; wk.support_foot = !wk.support_foot;
+            }
+            if (tick >= pu.ct0 && tick < pu.ct1) {              // impulsive push (quad_as_bip_bang.m:104-114)
+                st.com_vel[0] += a.model.dt * pu.ax; st.com_vel[1] += a.model.dt * pu.ay;
+            }
+            ismpc_formc_out_t r;
+            formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r, nullptr, nullptr);
+            st = r.next;
+            acc_status |= r.status;
+            if (traj && lane < 6) {
+                double v = st.com_pos[0];
+                v = lane == 1 ? st.com_pos[1] : v; v = lane == 2 ? st.com_pos[2] : v;
+                v = lane == 3 ? st.com_vel[0] : v; v = lane == 4 ? st.com_vel[1] : v; v = lane == 5 ? st.com_vel[2] : v;
+                traj[((size_t)inst * n_ticks + tick) * 6 + lane] = v;
+            }
+            wk.control_iter += 1;                                                    // Controller.cpp:503
+            wk.mpc_iter = (int)floor(wk.control_iter * a.model.dtc / a.model.dt);    // Controller.cpp:504
+            wk.sim_time += 1.0;                                                      // Controller.cpp:310 (sim frames)
+        }
+        if (lane == 0) {
+            state_io[inst] = st; walk_io[inst] = wk;
+            if (status_out) status_out[inst] = acc_status;
+        }
+    }
+}
+
+// The warp kernels cover every horizon the ABI accepts (N <= ISMPC_MAX_N).
+int formc_warp_supported(int N) { return N >= 2 && N <= ISMPC_MAX_N; }
+
+// Grid of the warp kernels for n instances: one 32-thread CTA per instance up to what the GPU keeps resident,
+// grid-stride beyond that (bounds the workspace of the general vertical path).
+int g_formc_variant = 1;
+void formc_set_variant(int v) { g_formc_variant = v; }
+int formc_warp_grid(int N, int n, int sm_count)
+{
+    const size_t smem = formc_warp_smem_bytes(N);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(formc_tick_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    int per_sm = 0;
+    cudaError_t oe = g_formc_variant == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<16>, 32, smem)
+                   : g_formc_variant == 12 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<12>, 32, smem)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<1>, 32, smem);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long cap = (long long)per_sm * sm_count;
+    return (int)((long long)n < cap ? n : cap);
+}
+
+int formc_tick_warp_launch(const FormCWarpArgs& a, int grid, cudaStream_t st)
+{
+    const size_t smem = formc_warp_smem_bytes(a.base.model.N);
+    if (g_formc_variant == 16) formc_tick_warp_kernel<16><<<grid, 32, smem, st>>>(a);
+    else if (g_formc_variant == 12) formc_tick_warp_kernel<12><<<grid, 32, smem, st>>>(a);
+    else formc_tick_warp_kernel<1><<<grid, 32, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
+                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
+                              cudaStream_t st)
+{
+    formc_rollout_warp_kernel<<<grid, 32, formc_warp_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
+                                                                                      traj, status);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ismpc

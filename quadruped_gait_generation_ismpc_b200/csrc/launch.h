@@ -8,6 +8,7 @@ namespace ismpc {
 struct FormCArgs;
 struct FormCTables;
 struct FormAArgs;
+struct FormCWarpArgs;
 
 int formc_setup_launch(const ismpc_formc_model_t& m, double* work, double* Hinv, double* G, double* M,
                        int* d_info, cudaStream_t st, long long* launches);
@@ -18,6 +19,17 @@ int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream
 int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                          const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
                          cudaStream_t st);
+
+// warp-per-instance kernels (formc_warp_kernels.cu)
+int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, double* tab, cudaStream_t st,
+                         long long* launches);
+int formc_warp_supported(int N);
+void formc_set_variant(int v);
+int formc_warp_grid(int N, int n, int sm_count);
+int formc_tick_warp_launch(const FormCWarpArgs& a, int grid, cudaStream_t st);
+int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
+                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
+                              cudaStream_t st);
 
 struct FormALaunchPlan { int R, warps_per_cta, grid, use_pdas, warm_start; size_t smem, spill_doubles; };
 void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p);

@@ -157,3 +157,57 @@ def test_prepared_gait_equals_generic_path(handle):
     i = np.nonzero(running & (walk["mpc_iter"] < 35))[0][0]
     c_lo = 35 - walk["mpc_iter"][i]
     assert (p["primal"][i, c_lo:c_lo + 10] == 0.0).all()
+
+
+@pytest.mark.parametrize("N", [50, 100, 200, 400])
+def test_warp_per_instance_equals_cta_per_instance(handle, N):
+    """The warp-per-instance tick (Riccati form of the vertical QP, register-resident) and the CTA-per-instance tick
+    (H_z^-1 tables) solve the same strictly convex QPs: same primal to 1e-9, same active sets, same status -- with the
+    prepared-gait tables, with the in-warp recursion (another step timing), and on the general vertical path."""
+    n = 96 if N <= 200 else 24
+    steps = (2 * N + 900) // 45 + 3
+    state, walk, inst, plan = synth.formc_batch(n, seed=31 + N, N=N, n_steps=steps, z_spread=0.06, running_frac=0.8)
+    inst["S"][::4] = 30; inst["F_ds"][::4] = 15
+    handle.formc_set_model(abi.formc_model(N=N))
+    handle.formc_prepare_gait(35, 10)
+    try:
+        handle.set_option("formc_kernel", 1)
+        a = handle.formc_solve_batch(state, walk, inst, plan)
+        handle.set_option("formc_kernel", 2)
+        res = [handle.formc_solve_batch(state, walk, inst, plan)]
+    finally:
+        handle.set_option("formc_kernel", 0)
+    assert (a["out"]["iters"][:, 0] > 0).any(), "test is vacuous: the general vertical path never ran"
+    for b in res:
+        assert np.array_equal(a["out"]["status"], b["out"]["status"])
+        ok = (a["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
+        assert ok.mean() > 0.7
+        # H_z loses digits with the horizon (cond ~ N^4): at N = 400 the explicit H_z^-1 table is good to ~1e-8 only
+        tol = 1e-9 if N <= 200 else 1e-7
+        assert primal_rel_err(b["primal"][ok].reshape(-1, 3, N), a["primal"][ok].reshape(-1, 3, N)).max() <= tol
+        assert np.array_equal(a["active"][ok], b["active"][ok])
+        assert np.abs(a["out"]["next"]["com_pos"][ok] - b["out"]["next"]["com_pos"][ok]).max() <= 1e-10
+        assert np.abs(a["out"]["next"]["com_vel"][ok] - b["out"]["next"]["com_vel"][ok]).max() <= 1e-9
+        assert b["out"]["kkt_res"][ok].max() < 1e-8
+
+
+def test_warp_rollout_equals_cta_rollout(handle):
+    """Closed loop with pushes: the two kernel families stay together tick by tick (1e-9 over 120 ticks)."""
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(64, seed=77)
+    walk["sim_time"] = np.minimum(walk["sim_time"], 300)
+    push = synth.push_batch(64, formc=True)
+    push["ct0"] = 20; push["ct1"] = 34
+    try:
+        handle.set_option("formc_kernel", 1)
+        a = handle.formc_rollout(state, walk, inst, plan, 120, push=push)
+        handle.set_option("formc_kernel", 2)
+        b = handle.formc_rollout(state, walk, inst, plan, 120, push=push)
+    finally:
+        handle.set_option("formc_kernel", 0)
+    ok = (a["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
+    assert ok.mean() > 0.7
+    assert np.array_equal(a["status"] & 7, b["status"] & 7)
+    assert np.abs(a["traj"][ok] - b["traj"][ok]).max() <= 1e-9
+    assert np.array_equal(a["walk"]["footstep_counter"], b["walk"]["footstep_counter"])

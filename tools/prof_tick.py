@@ -26,17 +26,25 @@ def to_dev(a):
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if which == "formc":
     h.formc_set_model(abi.formc_model())
+    if os.environ.get("ISMPC_FORMC_KERNEL"):
+        h.set_option("formc_kernel", int(os.environ["ISMPC_FORMC_KERNEL"]))
+    if os.environ.get("ISMPC_VARIANT"):
+        h.set_option("formc_variant", int(os.environ["ISMPC_VARIANT"]))
     if not os.environ.get("ISMPC_NO_GAIT"):
         h.formc_prepare_gait(35, 10)
     st, wk, ins, pl = synth.formc_batch(n)
     d = [to_dev(x) for x in (st, wk, ins, pl)]
     out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
     for r in range(reps):
+        if os.environ.get("ISMPC_DBG") and r == reps - 1:
+            binding.lib().ismpc_debug_reset_phases()
+        burst = int(os.environ.get("ISMPC_BURST", "20"))     # launches between the events: hides the host-side launch cost
         e0.record()
-        h.formc_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), pl.shape[0],
-                                out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        for _ in range(burst):
+            h.formc_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), pl.shape[0],
+                                    out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
         e1.record(); e1.synchronize()
-        print("formc tick n=%d: %.1f us" % (n, e0.elapsed_time(e1) * 1e3))
+        print("formc tick n=%d: %.1f us per launch (%d back-to-back)" % (n, e0.elapsed_time(e1) * 1e3 / burst, burst))
 else:
     h.forma_set_model(abi.forma_model())
     inst, ft, plan = synth.forma_batch(n, gait="trot")
@@ -67,6 +75,28 @@ if os.environ.get("ISMPC_DBG"):
     ph = (C.c_longlong * 64)()
     binding.lib().ismpc_debug_read_phases(ph)
     v = list(ph)[:24]
+    if which == "formc" and os.environ.get("ISMPC_FORMC_KERNEL", "0") != "1":
+        names = ["midpoints", "riccati", "rows+general", "lambda", "stab_row", "knapsack", "integrate"]
+        tot = float(sum(v[:7])) or 1.0
+        print("warp kernel, last launch: mean cycles per instance and phase (n=%d)" % n)
+        for nm, a in zip(names, v[:7]):
+            print("  %-12s %9.0f  %5.1f%%" % (nm, a / (n * burst), 100.0 * a / tot))
+        print("  total %.0f cycles/instance; newton fallbacks %d, in-warp riccati %d, general vertical %d"
+              % (tot / (n * burst), ph[29], ph[30], ph[31]))
+        m = min(n, 8192)
+        tr = (C.c_longlong * (3 * m))()
+        binding.lib().ismpc_debug_read_trace(tr, 3 * m)
+        tr = np.array(list(tr)).reshape(m, 3)
+        t0 = tr[:, 0].min()
+        st_, en_ = tr[:, 0] - t0, tr[:, 1] - t0
+        du = en_ - st_
+        print("  CTA trace of the last launch (ns): start p50 %d p90 %d max %d | duration p50 %d p90 %d p99 %d max %d | end max %d"
+              % (np.percentile(st_, 50), np.percentile(st_, 90), st_.max(), np.percentile(du, 50), np.percentile(du, 90),
+                 np.percentile(du, 99), du.max(), en_.max()))
+        sm_ids = tr[:, 2]
+        per_sm = np.bincount(sm_ids.astype(int))
+        print("  CTAs per SM: min %d max %d; slowest 5 durations at SMs %s" % (per_sm[per_sm > 0].min(), per_sm.max(), sm_ids[np.argsort(du)[-5:]]))
+        sys.exit(0)
     nz = [(i, x) for i, x in enumerate(v) if x]
     print("phase clocks (CTA 0): stamp -> cycles since the previous non-zero stamp:",
           [(nz[k][0], nz[k][1] - nz[k - 1][1]) for k in range(1, len(nz))], "total", nz[-1][1] - nz[0][1] if nz else 0)
