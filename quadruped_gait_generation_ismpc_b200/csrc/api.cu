@@ -38,7 +38,7 @@ struct ismpc_handle {
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
     DevBuf c_tables, c_work, c_info, c_ptab;
-    DevBuf c_ric_none, c_ric_gait, c_ws;   // Riccati tables (warp kernels) and the per-warp workspace of their general path
+    DevBuf c_ric_none, c_ric_gait, c_law_none, c_law_gait, c_ws;   // Riccati tables (warp kernels) and the per-warp workspace of their general path
     int gait_S = 0, gait_F = 0;            // prepared gait (projector tables in c_ptab), 0 = none
     int ric_S = 0, ric_F = 0;              // prepared gait of the Riccati tables (c_ric_gait), 0 = none
     // form A
@@ -97,7 +97,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
 {
     if (!h) return ISMPC_ERR_ARG;
     cudaSetDevice(h->device);
-    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_ws, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
@@ -152,6 +152,9 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
     if (h->c_ric_none.ensure((size_t)m->N * FORMC_RIC_W * sizeof(double))) return ISMPC_ERR_ALLOC;
     rc = formc_riccati_launch(*m, 0, 0, 1, (double*)h->c_ric_none.p, 0, &h->launches);
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_riccati_launch");
+    if (h->c_law_none.ensure(formc_law_pattern_doubles(m->N) * sizeof(double))) return ISMPC_ERR_ALLOC;
+    rc = formc_law_launch(*m, 1, (const double*)h->c_ric_none.p, (double*)h->c_law_none.p, 0, &h->launches);
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_law_launch");
     CK(cudaStreamSynchronize(0));
     h->cm = *m;
     h->gait_S = h->gait_F = 0; h->ric_S = h->ric_F = 0; h->w_resident = 0;
@@ -206,6 +209,8 @@ static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStr
     wa.base = a;
     wa.R.none = (const double*)h->c_ric_none.p;
     wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
+    wa.R.law_none = (const double*)h->c_law_none.p;
+    wa.R.law_gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_law_gait.p : nullptr;
     wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
     wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
     if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
@@ -222,6 +227,8 @@ static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismp
     wa.base = a;
     wa.R.none = (const double*)h->c_ric_none.p;
     wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
+    wa.R.law_none = (const double*)h->c_law_none.p;
+    wa.R.law_gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_law_gait.p : nullptr;
     wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
     wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
     if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
@@ -242,6 +249,9 @@ extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)
     if (h->c_ric_gait.ensure((size_t)(S + F_ds) * h->cm.N * FORMC_RIC_W * sizeof(double))) return ISMPC_ERR_ALLOC;
     int rc = formc_riccati_launch(h->cm, S, F_ds, 0, (double*)h->c_ric_gait.p, 0, &h->launches);
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_riccati_launch");
+    if (h->c_law_gait.ensure((size_t)(S + F_ds) * formc_law_pattern_doubles(h->cm.N) * sizeof(double))) return ISMPC_ERR_ALLOC;
+    rc = formc_law_launch(h->cm, S + F_ds, (const double*)h->c_ric_gait.p, (double*)h->c_law_gait.p, 0, &h->launches);
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_law_launch");
     CK(cudaStreamSynchronize(0));
     h->ric_S = S; h->ric_F = F_ds;
     // projector tables of the CTA/cluster kernels

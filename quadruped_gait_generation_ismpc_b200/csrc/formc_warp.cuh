@@ -26,20 +26,24 @@
 //    warp runs the general dual active set (das.cuh) on a per-warp GLOBAL-memory workspace (rare path).
 //  * Stage 2: cosh(s dt), sinh(s dt)/s and s sinh(s dt) are even in s = sqrt(lambda), i.e. power series in
 //    lambda dt^2 (<= 0.04 on this path): 9 terms reach 1e-17, no sqrt / exp / division.
-//  * Stage 3: x and y share the stability row, so the prefix/suffix scans of the knapsack solve (formc.cuh:
-//    knapsack_qp) are done once for both axes; a non-prefix saturation pattern falls back to Newton passes on the
-//    multiplier (both axes per pass).
+//  * Stage 3: x and y share the stability row, so one prefix and one suffix scan give both knapsack solves their
+//    starting multiplier (best prefix set, a lower bound), which semismooth Newton confirms or corrects, both axes
+//    per pass (see the comment there).
 #pragma once
 #include "formc.cuh"
 
 namespace ismpc {
 
 constexpr int FORMC_RIC_W = 4;          // doubles per (pattern, sample) in the Riccati tables
+constexpr int FORMC_LAW_W = 8;          // doubles per (pattern, sample) in the feedback-law tables
 constexpr int FORMC_WARP_VECS = 11;     // shared-memory vectors per instance (E*32 doubles each)
 
 struct FormCRiccati {
     const double* none;   // [N][4]            pattern without equalities (footstepCounter <= 1), built with the model
     const double* gait;   // [gS+gF][N][4]     one pattern per mpcIter of the prepared gait; null if none
+    // Explicit feedback law of the same patterns (FORMC_LAW_W doubles per sample), see formc_law_apply()
+    const double* law_none;   // [8][E*32]
+    const double* law_gait;   // [gS+gF][8][E*32]
     int gS, gF;
 };
 
@@ -93,24 +97,7 @@ __device__ __forceinline__ void fast_divmod(int u, int per, float rcp, int& q, i
     if (r >= per) { ++q; r -= per; }
 }
 
-// MPCSolver.cpp:167-180: (x, y, z) of ftsp_midpoint at step index i, in-step sample r.
-// (the ramp weight (r-S)/F is formed as (r-S) * (1/F): one rounding more than the reference's division, 1e-16 relative)
-template <bool WANT_Z>
-__device__ __forceinline__ void midpoint_xyz(const double* __restrict__ rows, int n_steps, int S, double invF, int i, int r,
-                                             double& x, double& y, double& z)
-{
-    x = 0.0; y = 0.0; z = 0.0;
-    if (i >= n_steps - 1) return;                                     // last step's rows stay 0
-    const double w = r < S ? 0.0 : (double)(r - S) * invF;
-    const int j = r < S ? i : i + 1;                                  // r < S: b := a, the ramp term vanishes exactly
-    const double ax = __ldg(rows + 4 * i), ay = __ldg(rows + 4 * i + 1);
-    const double bx = __ldg(rows + 4 * j), by = __ldg(rows + 4 * j + 1);
-    x = ax * 1.0 + (bx - ax) * w; y = ay * 1.0 + (by - ay) * w;
-    if (WANT_Z) {
-        const double az = __ldg(rows + 4 * i + 2), bz = __ldg(rows + 4 * j + 2);
-        z = az * 1.0 + (bz - az) * w;
-    }
-}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; x normal and finite on this path (CoM heights).
 __device__ __forceinline__ double fast_rcp(double x)
@@ -132,9 +119,12 @@ __host__ __device__ inline size_t formc_warp_ws_doubles(int N)
     return ((d + (bytes + 7) / 8) + 3) & ~(size_t)3;
 }
 __host__ __device__ inline int formc_warp_epl(int N) { return (N + 31) >> 5; }
+// Feedback-law table of one pattern: FORMC_LAW_W component vectors in the kernel's shared-memory layout
+// [component][e*32 + lane] (sample i = lane*E + e; zero padding), so that ONE bulk copy (TMA) stages a pattern.
+__host__ __device__ inline size_t formc_law_pattern_doubles(int N) { return (size_t)FORMC_LAW_W * formc_warp_epl(N) * 32; }
 __host__ __device__ inline size_t formc_warp_smem_bytes(int N)
 {
-    return (size_t)FORMC_WARP_VECS * formc_warp_epl(N) * 32 * sizeof(double);
+    return (size_t)FORMC_WARP_VECS * formc_warp_epl(N) * 32 * sizeof(double) + 16;   // + mbarrier
 }
 
 struct FormCWarpShared {     // [e*32 + lane] each
@@ -144,12 +134,14 @@ struct FormCWarpShared {     // [e*32 + lane] each
     double *om;              // omega; later s*sinh
     double *f, *p;           // forces, CoM heights
     double *av;              // stability row
+    uint64_t* bar;           // mbarrier of the bulk copies
 };
 __device__ __forceinline__ void formc_warp_carve(double* base, int E, FormCWarpShared& s)
 {
     const int L = E * 32;
     s.mx = base; s.my = base + L; s.rq = base + 2 * L; s.ta = base + 3 * L; s.tb = base + 4 * L; s.tc = base + 5 * L;
     s.td = base + 6 * L; s.om = base + 7 * L; s.f = base + 8 * L; s.p = base + 9 * L; s.av = base + 10 * L;
+    s.bar = reinterpret_cast<uint64_t*>(base + 11 * L);
 }
 
 // Vertical LQ solve with the table entries in sm.ta..td: fills sm.om, sm.f (forces), sm.p (z_pos_k).
@@ -270,6 +262,47 @@ __device__ __forceinline__ void riccati_load(const FormCWarpShared& sm, const do
     }
 }
 
+// Flat reference (mid_z is the same over the whole window -- every plan of the reference has z = 0): the tracking
+// cost then depends on the instance through three scalars only, rq = -q_p (h + mid_z) and x0 = (z0 + dt zd0, zd0),
+// and the minimiser is affine in them:
+//     f_k = fa_k + fb_k rq + fc_k x0_0 + fd_k x0_1,      z_pos_k = pa_k + pb_k rq + pc_k x0_0 + pd_k x0_1,
+// with coefficients that depend on the pattern alone (the explicit MPC law of the equality-constrained QP, built by
+// formc_build_law from four runs of the same recursion).  No scan at all: 8 loads and 6 FMAs per sample.
+// The pattern's table is staged by one 1-D bulk copy (TMA, cp.async.bulk + mbarrier) issued as soon as the records
+// are known, straight into the eight vectors ta,tb,tc,td,om,f,p,av (contiguous; the table is stored in that layout).
+// Also checks the rows 0 <= S_bar_z f <= fz_max (MPCSolver.cpp:158-160; S_bar_z f = z_pos - T_z z0 - T_g) on the way.
+__device__ __forceinline__ void formc_law_apply(const FormCWarpShared& sm, int N, int E, int lane,
+                                                double rq, double z0, double zd0, double dt, double g, double fz_max,
+                                                bool& bad, double& viol)
+{
+    const double x00 = z0 + dt * zd0, x01 = zd0;
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e, x = e * 32 + lane;
+        const double fa = sm.ta[x], fb = sm.tb[x], fc = sm.tc[x], fd = sm.td[x];
+        const double pa = sm.om[x], pb = sm.f[x], pc = sm.p[x], pd = sm.av[x];
+        double fv = 0.0, pv = 1.0;
+        if (i < N) {
+            fv = fa + fb * rq + fc * x00 + fd * x01;
+            pv = pa + pb * rq + pc * x00 + pd * x01;
+            const double base = 1.0 * z0 + ((double)(i + 1) * dt) * zd0 - g * (dt * dt) * (0.5 * (double)i * (double)(i + 1));
+            const double v = pv - base;
+            bad = bad || (fmin(v + 1e-10, (fz_max - v) + 1e-10 * (1.0 + fabs(fz_max))) < 0.0);
+            viol = fmax(viol, fmax(-v, v - fz_max));
+        }
+        sm.f[x] = fv; sm.p[x] = pv;
+    }
+}
+__device__ __forceinline__ void formc_law_stage(const FormCWarpShared& sm, const double* __restrict__ law, int N, int lane)
+{
+    if (lane == 0) {
+        const uint32_t bytes = (uint32_t)(formc_law_pattern_doubles(N) * sizeof(double));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses to these vectors
+        mbar_expect_tx(sm.bar, bytes);
+        tma_load_1d(sm.ta, law, bytes, sm.bar);
+    }
+}
+
 // General vertical path (a row of 0 <= S_bar_z f <= fz_max is violated at the equality-constrained minimiser):
 // dual active set from the unconstrained minimiser, equalities first.  ws: this warp's global workspace, with the
 // unconstrained minimiser already stored in ws[0..N).  On return ws[0..N) = f, ws[N..2N) = S_bar_z f, state bytes
@@ -311,16 +344,16 @@ static __device__ __noinline__ int formc_vertical_general(int N, FormCTables T, 
 __device__ __forceinline__ void lip_series(double lam, double dt, double& ch, double& shs, double& ssh)
 {
     const double y = lam * dt * dt;
-    // cosh = sum y^k/(2k)!,  sinh(x)/x = sum y^k/(2k+1)!   (Horner, k = 8..0)
-    double c = 1.0 / 20922789888000.0, s = 1.0 / 355687428096000.0;
-    c = c * y + 1.0 / 87178291200.0;  s = s * y + 1.0 / 1307674368000.0;
-    c = c * y + 1.0 / 479001600.0;    s = s * y + 1.0 / 6227020800.0;
-    c = c * y + 1.0 / 3628800.0;      s = s * y + 1.0 / 39916800.0;
-    c = c * y + 1.0 / 40320.0;        s = s * y + 1.0 / 362880.0;
-    c = c * y + 1.0 / 720.0;          s = s * y + 1.0 / 5040.0;
-    c = c * y + 1.0 / 24.0;           s = s * y + 1.0 / 120.0;
-    c = c * y + 0.5;                  s = s * y + 1.0 / 6.0;
-    c = c * y + 1.0;                  s = s * y + 1.0;
+    // cosh = sum y^k/(2k)!,  sinh(x)/x = sum y^k/(2k+1)!,  k = 0..8, Estrin's scheme (dependency depth 4 instead of 9)
+    const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
+    const double c01 = fma(y, 0.5, 1.0),                         s01 = fma(y, 1.0 / 6.0, 1.0);
+    const double c23 = fma(y, 1.0 / 720.0, 1.0 / 24.0),          s23 = fma(y, 1.0 / 5040.0, 1.0 / 120.0);
+    const double c45 = fma(y, 1.0 / 3628800.0, 1.0 / 40320.0),   s45 = fma(y, 1.0 / 39916800.0, 1.0 / 362880.0);
+    const double c67 = fma(y, 1.0 / 87178291200.0, 1.0 / 479001600.0), s67 = fma(y, 1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    const double c03 = fma(y2, c23, c01), s03 = fma(y2, s23, s01);
+    const double c47 = fma(y2, c67, c45), s47 = fma(y2, s67, s45);
+    const double c = fma(y8, 1.0 / 20922789888000.0, fma(y4, c47, c03));
+    const double s = fma(y8, 1.0 / 355687428096000.0, fma(y4, s47, s03));
     ch = c; shs = dt * s; ssh = lam * dt * s;
 }
 __device__ __forceinline__ void lip_matrices(double lam, double dt, double& ch, double& shs, double& ssh)
@@ -346,7 +379,8 @@ struct FormCWarpArgs {
 __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const ismpc_formc_model_t& mdl, const FormCTables& T,
                                                 const FormCRiccati& R, const ismpc_state_t& st, const ismpc_walk_t& wk,
                                                 const ismpc_formc_inst_t& in, const double* __restrict__ plan_all,
-                                                double* ws, ismpc_formc_out_t& r, double* prim, signed char* act)
+                                                double* ws, ismpc_formc_out_t& r, double* prim, signed char* act,
+                                                uint32_t& bar_parity)
 {
     const int lane = lane_id();
     const int N = mdl.N, E = formc_warp_epl(N);
@@ -367,46 +401,101 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
     }
     __syncwarp();                                          // the previous instance's shared-memory reads are done
 
+    // Which Riccati pattern stage 1 uses is known from the records alone: start pulling its table (and the plan rows
+    // of the window) into L1 now, so that the three dependent global-memory round trips of the tick -- records, plan
+    // rows, gain table -- overlap instead of queueing up behind one another.
+    const double z0 = st.com_pos[2], zd0 = st.com_vel[2];
+    const double c1 = dt * dt / mass;
+    const bool running = wk.footstep_counter > 1;
+    int ne = 0, c_lo = 0;
+    if (running) formc_flight_range(N, S, F, wk.mpc_iter, c_lo, ne);
+    const double* tab = nullptr;
+    const double* law = nullptr;
+    if (ne == 0) { tab = R.none; law = R.law_none; }
+    else if (R.gait != nullptr && S == R.gS && F == R.gF && wk.mpc_iter >= 0 && wk.mpc_iter < per) {
+        tab = R.gait + (size_t)wk.mpc_iter * N * FORMC_RIC_W;
+        law = R.law_gait + (size_t)wk.mpc_iter * formc_law_pattern_doubles(N);
+    }
+    const double* rows = plan_all + (size_t)in.plan_first_row * 4;
+    {
+        const int first = k0 / per;
+        int last = (k0 + 2 * N - 1) / per + 1;
+        if (last > in.n_steps - 1) last = in.n_steps - 1;
+        const char* pb = reinterpret_cast<const char*>(rows + 4 * first);
+        const int nbytes = (last - first + 1) * 32;
+        if (lane * 128 < nbytes) prefetch_l1(pb + lane * 128);
+    }
+    const bool staged = __any_sync(ISMPC_FULL_MASK, law != nullptr);
+    if (staged) formc_law_stage(sm, law, N, lane);
+
     // ---- midpoint window (MPCSolver.cpp:167-180): samples [k0, k0+N), and the anticipative tail (:381-383)
     //      sum_i exp(-dt eta i) mid[k0+N+i] accumulated on the fly ----
-    const double* rows = plan_all + (size_t)in.plan_first_row * 4;
     double tx = 0.0, ty = 0.0;
+    double rq_first = 0.0, rq_ref = 0.0;
+    bool flat = true;
     {
         const int q0 = k0 / per, r0 = k0 - q0 * per;
         const float rcp = 1.0f / (float)per;
         const double invF = 1.0 / (double)F;
         const double qd = exp(-dt * eta);
         double dl = exp(-dt * eta * (double)(lane * E));                             // deltas (:183-184), dl_i = qd^i
+        // (step, in-step sample) of the chunk's first sample in the window and in the tail; then they only count up,
+        // and the plan rows are re-read only when the step changes (once or twice per chunk)
+        int qi, ri, qt, rt;
+        fast_divmod(r0 + lane * E, per, rcp, qi, ri);
+        fast_divmod(r0 + N + lane * E, per, rcp, qt, rt);
+        qi += q0; qt += q0;
+        int cq = -1, ct = -1;
+        double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0, cx_ = 0.0, cy_ = 0.0, dx_ = 0.0, dy_ = 0.0;
 #pragma unroll 1
         for (int e = 0; e < E; ++e) {
             const int i = lane * E + e, x = e * 32 + lane;
             double mxv = 0.0, myv = 0.0, mzv = 0.0;
             if (i < N) {
-                int qi, ri;
-                fast_divmod(r0 + i, per, rcp, qi, ri);
-                midpoint_xyz<true>(rows, in.n_steps, S, invF, q0 + qi, ri, mxv, myv, mzv);
-                double xt, yt, zt;
-                fast_divmod(r0 + N + i, per, rcp, qi, ri);
-                midpoint_xyz<false>(rows, in.n_steps, S, invF, q0 + qi, ri, xt, yt, zt);
-                tx += dl * xt; ty += dl * yt;
+                if (qi != cq) {
+                    cq = qi;
+                    ax = ay = az = bx = by = bz = 0.0;                               // last step's rows stay 0 (:167)
+                    if (qi < in.n_steps - 1) {
+                        ax = __ldg(rows + 4 * qi); ay = __ldg(rows + 4 * qi + 1); az = __ldg(rows + 4 * qi + 2);
+                        bx = __ldg(rows + 4 * qi + 4); by = __ldg(rows + 4 * qi + 5); bz = __ldg(rows + 4 * qi + 6);
+                    }
+                }
+                if (qt != ct) {
+                    ct = qt;
+                    cx_ = cy_ = dx_ = dy_ = 0.0;
+                    if (qt < in.n_steps - 1) {
+                        cx_ = __ldg(rows + 4 * qt); cy_ = __ldg(rows + 4 * qt + 1);
+                        dx_ = __ldg(rows + 4 * qt + 4); dy_ = __ldg(rows + 4 * qt + 5);
+                    }
+                }
+                // (the ramp weight (r-S)/F is formed as (r-S) * (1/F): one rounding more than the reference's division)
+                const double w = ri < S ? 0.0 : (double)(ri - S) * invF;
+                mxv = ax * 1.0 + (bx - ax) * w; myv = ay * 1.0 + (by - ay) * w; mzv = az * 1.0 + (bz - az) * w;
+                const double wt = rt < S ? 0.0 : (double)(rt - S) * invF;
+                tx += dl * (cx_ * 1.0 + (dx_ - cx_) * wt); ty += dl * (cy_ * 1.0 + (dy_ - cy_) * wt);
             }
-            sm.mx[x] = mxv; sm.my[x] = myv; sm.rq[x] = -mdl.q_p * (h + mzv);
+            if (++ri == per) { ri = 0; ++qi; }
+            if (++rt == per) { rt = 0; ++qt; }
+            const double rqv = -mdl.q_p * (h + mzv);
+            sm.mx[x] = mxv; sm.my[x] = myv; sm.rq[x] = rqv;
+            if (e == 0) rq_first = rqv;
+            if (i < N) flat = flat && (rqv == rq_ref || e == 0);
+            if (e == 0) rq_ref = rqv;
             dl *= qd;
         }
     }
+    // flat reference: every sample of the window has the same mid_z
+    const double rq0 = __shfl_sync(ISMPC_FULL_MASK, rq_first, 0);
+    flat = __all_sync(ISMPC_FULL_MASK, flat && (rq_first == rq0 || lane * E >= N));
     ISMPC_WPHASE(0);
 
     // ================= STAGE 1: vertical QP (MPCSolver.cpp:220-269) =================
-    const double z0 = st.com_pos[2], zd0 = st.com_vel[2];
-    const double c1 = dt * dt / mass;
-    const bool running = wk.footstep_counter > 1;
-    int ne = 0, c_lo = 0;
-    if (running) formc_flight_range(N, S, F, wk.mpc_iter, c_lo, ne);
-    {
-        const double* tab = nullptr;
-        if (ne == 0) tab = R.none;
-        else if (R.gait != nullptr && S == R.gS && F == R.gF && wk.mpc_iter >= 0 && wk.mpc_iter < per)
-            tab = R.gait + (size_t)wk.mpc_iter * N * FORMC_RIC_W;
+    double viol = 0.0;
+    bool bad = false;
+    if (staged) { mbar_wait(sm.bar, bar_parity); bar_parity ^= 1u; }
+    const bool use_law = __all_sync(ISMPC_FULL_MASK, flat && law != nullptr);
+    if (use_law) formc_law_apply(sm, N, E, lane, rq0, z0, zd0, dt, g, mdl.fz_max, bad, viol);
+    else {
         if (__any_sync(ISMPC_FULL_MASK, tab != nullptr)) riccati_load(sm, tab, N, E, lane);
         else {
             // another step timing than the prepared one: every lane runs the recursion, the owner keeps the sample
@@ -422,22 +511,20 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                 if (--oe < 0) { oe = E - 1; --ol; }
             }
         }
-    }
-    riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
-    ISMPC_WPHASE(1);
-    // rows 0 <= S_bar_z f <= fz_max  (:158-160):  S_bar_z f = p - T_z z0 - T_g
-    double viol = 0.0;
-    bool bad = false;
+        riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
+        // rows 0 <= S_bar_z f <= fz_max  (:158-160):  S_bar_z f = p - T_z z0 - T_g
 #pragma unroll 1
-    for (int e = 0; e < E; ++e) {
-        const int k = lane * E + e;
-        if (k < N) {
-            const double base = 1.0 * z0 + ((double)(k + 1) * dt) * zd0 - g * (dt * dt) * (0.5 * (double)k * (double)(k + 1));
-            const double v = sm.p[e * 32 + lane] - base;
-            bad = bad || (fmin(v + 1e-10, (mdl.fz_max - v) + 1e-10 * (1.0 + fabs(mdl.fz_max))) < 0.0);
-            viol = fmax(viol, fmax(-v, v - mdl.fz_max));
+        for (int e = 0; e < E; ++e) {
+            const int k = lane * E + e;
+            if (k < N) {
+                const double base = 1.0 * z0 + ((double)(k + 1) * dt) * zd0 - g * (dt * dt) * (0.5 * (double)k * (double)(k + 1));
+                const double v = sm.p[e * 32 + lane] - base;
+                bad = bad || (fmin(v + 1e-10, (mdl.fz_max - v) + 1e-10 * (1.0 + fabs(mdl.fz_max))) < 0.0);
+                viol = fmax(viol, fmax(-v, v - mdl.fz_max));
+            }
         }
     }
+    ISMPC_WPHASE(1);
     int it_z = 0;
     const bool general = __any_sync(ISMPC_FULL_MASK, bad);
     signed char* zstate = nullptr;
@@ -445,8 +532,16 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         ISMPC_WCOUNT(31);
         // general path: unconstrained minimiser -> workspace -> dual active set -> back to shared memory
         if (ne > 0) {
-            riccati_load(sm, R.none, N, E, lane);
-            riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
+            bool b2 = false; double v2 = 0.0;
+            if (flat) {
+                __syncwarp();
+                formc_law_stage(sm, R.law_none, N, lane);
+                mbar_wait(sm.bar, bar_parity); bar_parity ^= 1u;
+                formc_law_apply(sm, N, E, lane, rq0, z0, zd0, dt, g, mdl.fz_max, b2, v2);
+            } else {
+                riccati_load(sm, R.none, N, E, lane);
+                riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
+            }
         }
         for (int e = 0; e < E; ++e) if (lane * E + e < N) ws[lane * E + e] = sm.f[e * 32 + lane];
         __syncwarp();
@@ -464,8 +559,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         }
         __syncwarp();
     }
-    viol = warp_max(viol);
-    double kkt = fmax(0.0, viol);
+    double kkt = fmax(0.0, viol);            // lane-local so far; reduced over the warp with the final sums
     if (prim) for (int e = 0; e < E; ++e) if (lane * E + e < N) prim[lane * E + e] = sm.f[e * 32 + lane];
     if (act) for (int e = 0; e < E; ++e) if (lane * E + e < N) act[lane * E + e] = zstate ? zstate[lane * E + e] : (signed char)0;
     ISMPC_WPHASE(2);
@@ -520,8 +614,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         const double cs0 = 1.0, cs1 = 1.0 / eta;                                     // C_sc (:375-377), nominal eta
         double c0 = cs0 * t00 + cs1 * t10, c1r = cs0 * t01 + cs1 * t11;
         // stability row + the lane-local sums of the knapsack solve
-        const double INF = 1e300;
-        double amx = 0.0, amy = 0.0, t1 = 0.0, t2 = 0.0, mx = 0.0, mn = INF;
+        double amx = 0.0, amy = 0.0, t1 = 0.0, t2 = 0.0, mx = 0.0;
 #pragma unroll 1
         for (int e = E - 1; e >= 0; --e) {
             const int x = e * 32 + lane;
@@ -533,20 +626,27 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
             const double ai = fabs(a);
             amx += a * sm.mx[x]; amy += a * sm.my[x];
             t1 += ai; t2 += ai * ai; mx = fmax(mx, ai);
-            if (ai > 0.0) mn = fmin(mn, ai);
         }
         const double ps0 = __shfl_sync(ISMPC_FULL_MASK, c0, 0), ps1 = __shfl_sync(ISMPC_FULL_MASK, c1r, 0);   // C_sc * phi_state
         ISMPC_WPHASE(4);
 
-        // ---- knapsack solve for both axes (formc.cuh: knapsack_qp), scans over |a| shared ----
+        // ---- both horizontal QPs:  min 1/2|u|^2 - mid'u,  a'u = b,  |u - mid| <= rho  (H = I, A = [a'; I]).
+        // u_i = mid_i + clip(nu a_i, +-rho); with t = |nu| the equality reads  g(t) := sum_i |a_i| min(t|a_i|, rho) = |r|,
+        // r = b - a'mid: g is concave, increasing and piecewise linear.  For ANY set S of rows taken as saturated,
+        //   t_S = (|r| - rho sum_S |a_i|) / sum_{not S} a_i^2  <=  t*      (g is the lower envelope of those lines),
+        // so the best prefix set S = [0,k) -- |a| decays along the horizon, the saturated rows are a prefix up to the
+        // ripples lambda puts on it -- gives a tight lower bound max_k t_k from one prefix and one suffix scan, shared by
+        // x and y.  Semismooth Newton from there (re-solve with the rows saturated at t, both axes per pass) is monotone
+        // and ends when the set repeats: one pass when the prefix guess was exact, a few otherwise (the slowest QP of a
+        // batch sets the tick time: Newton from the unsaturated start needs up to a dozen passes).
         const double rho = running ? in.box_w / 2 : in.box_w_init / 2;                // (:328-338)
-        double aa = t2;
+        double aa = t2, amax = mx;
 #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) {                                            // five sums in one butterfly
+        for (int o = 16; o > 0; o >>= 1) {                                            // six reductions in one butterfly
             const double s0 = __shfl_xor_sync(ISMPC_FULL_MASK, tx, o), s1 = __shfl_xor_sync(ISMPC_FULL_MASK, ty, o);
             const double s2 = __shfl_xor_sync(ISMPC_FULL_MASK, amx, o), s3 = __shfl_xor_sync(ISMPC_FULL_MASK, amy, o);
-            const double s4 = __shfl_xor_sync(ISMPC_FULL_MASK, aa, o);
-            tx += s0; ty += s1; amx += s2; amy += s3; aa += s4;
+            const double s4 = __shfl_xor_sync(ISMPC_FULL_MASK, aa, o), s5 = __shfl_xor_sync(ISMPC_FULL_MASK, amax, o);
+            tx += s0; ty += s1; amx += s2; amy += s3; aa += s4; amax = fmax(amax, s5);
         }
         const double bx = -(ps0 * st.com_pos[0] + ps1 * st.com_vel[0]) + eta * dt * tx;   // (:381-384)
         const double by = -(ps0 * st.com_pos[1] + ps1 * st.com_vel[1]) + eta * dt * ty;
@@ -556,58 +656,36 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         double tqx = 0.0, tqy = 0.0;
         int stx = 0, sty = 0;
         if (__any_sync(ISMPC_FULL_MASK, aa > 0.0)) {                                  // (the same in all lanes)
-            // P1 = sum |a| before k, Lm = min nonzero |a| before k, S2 = sum a^2 from k on, Mx = max |a| from k on
-            double p1 = t1, sf = t2, pm = mn, sm_ = mx;
+            const double inv_aa = 1.0 / aa;
+            tqx = rax * inv_aa; tqy = ray * inv_aa;                                   // no row saturated
+            const bool satx = tqx * amax > rho, saty = tqy * amax > rho;
+            if (__any_sync(ISMPC_FULL_MASK, satx || saty)) {
+                // prefix candidates: P1(k) = sum_{i<k} |a_i|,  S2(k) = sum_{i>=k} a_i^2
+                double p1 = t1, sf = t2;
 #pragma unroll 1
-            for (int o = 1; o < 32; o <<= 1) {
-                const double a1 = __shfl_up_sync(ISMPC_FULL_MASK, p1, o), a3 = __shfl_up_sync(ISMPC_FULL_MASK, pm, o);
-                const double a2 = __shfl_down_sync(ISMPC_FULL_MASK, sf, o), a4 = __shfl_down_sync(ISMPC_FULL_MASK, sm_, o);
-                if (lane >= o) { p1 += a1; pm = fmin(pm, a3); }
-                if (lane + o < 32) { sf += a2; sm_ = fmax(sm_, a4); }
-            }
-            double P1 = p1 - t1;
-            double Lm = __shfl_up_sync(ISMPC_FULL_MASK, pm, 1); if (lane == 0) Lm = INF;
-            double S2 = sf - t2;
-            double Mx = __shfl_down_sync(ISMPC_FULL_MASK, sm_, 1); if (lane == 31) Mx = 0.0;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double a1 = __shfl_up_sync(ISMPC_FULL_MASK, p1, o), a2 = __shfl_down_sync(ISMPC_FULL_MASK, sf, o);
+                    if (lane >= o) p1 += a1;
+                    if (lane + o < 32) sf += a2;
+                }
+                double P1 = p1 - t1, S2 = sf;                                         // at the lane's first sample
+                double cx = 0.0, cy = 0.0;
 #pragma unroll 1
-            for (int e = 0; e < E; ++e) {
-                const int x = e * 32 + lane;
-                sm.ta[x] = P1; sm.tb[x] = Lm;
-                const double ak = fabs(sm.av[x]);
-                P1 += ak; if (ak > 0.0) Lm = fmin(Lm, ak);
-            }
-            int kbx = 0x7fffffff, kby = 0x7fffffff;
-            double nbx = 0.0, dbx = 1.0, nby = 0.0, dby = 1.0;
+                for (int e = 0; e < E; ++e) {
+                    const double ak = fabs(sm.av[e * 32 + lane]);
+                    if (S2 > 1e-30 * aa) {
+                        const double ri = fast_rcp(S2);
+                        cx = fmax(cx, (rax - rho * P1) * ri); cy = fmax(cy, (ray - rho * P1) * ri);
+                    }
+                    P1 += ak; S2 -= ak * ak;
+                }
 #pragma unroll 1
-            for (int e = E - 1; e >= 0; --e) {
-                const int x = e * 32 + lane;
-                const double ak = fabs(sm.av[x]);
-                S2 += ak * ak; Mx = fmax(Mx, ak);
-                const bool vk = (lane * E + e < N) && (S2 > 0.0);
-                const double lm = sm.tb[x], rs = rho * S2, rp = rho * sm.ta[x];
-                // candidate t_k = num / S2, tested in multiplied-out form (S2 > 0): one division per axis at the end
-                const double numx = rax - rp, numy = ray - rp;
-                const bool nl = !(lm < INF);
-                if (vk && (nl || numx * lm > rs) && !(numx * Mx > rs) && numx >= 0.0) { kbx = lane * E + e; nbx = numx; dbx = S2; }
-                if (vk && (nl || numy * lm > rs) && !(numy * Mx > rs) && numy >= 0.0) { kby = lane * E + e; nby = numy; dby = S2; }
-            }
-            // the smallest valid k wins; its lane broadcasts the quotient
-            int gx = kbx, gy = kby;
-#pragma unroll 1
-            for (int o = 16; o > 0; o >>= 1) {
-                gx = min(gx, __shfl_xor_sync(ISMPC_FULL_MASK, gx, o)); gy = min(gy, __shfl_xor_sync(ISMPC_FULL_MASK, gy, o));
-            }
-            const unsigned wx = __ballot_sync(ISMPC_FULL_MASK, kbx == gx), wy = __ballot_sync(ISMPC_FULL_MASK, kby == gy);
-            tqx = __shfl_sync(ISMPC_FULL_MASK, nbx / dbx, __ffs(wx) - 1);
-            tqy = __shfl_sync(ISMPC_FULL_MASK, nby / dby, __ffs(wy) - 1);
-            const bool needx = gx == 0x7fffffff, needy = gy == 0x7fffffff;
-            if (__any_sync(ISMPC_FULL_MASK, needx || needy)) {
-                // The saturated set is not a prefix (|a| is not monotone where lambda varies): semismooth Newton on the
-                // multiplier from the unsaturated start, both axes in one pass; every pass adds all newly saturated rows,
-                // |nu| grows monotonically, so it ends after a handful of passes (<= N).
-                ISMPC_WCOUNT(29);
-                double ux_ = needx ? rax / aa : tqx, uy_ = needy ? ray / aa : tqy;
-                int prevx = needx ? -1 : -2, prevy = needy ? -1 : -2;           // -2: axis already solved
+                for (int o = 16; o > 0; o >>= 1) {
+                    cx = fmax(cx, __shfl_xor_sync(ISMPC_FULL_MASK, cx, o)); cy = fmax(cy, __shfl_xor_sync(ISMPC_FULL_MASK, cy, o));
+                }
+                if (satx) tqx = fmax(tqx, cx);
+                if (saty) tqy = fmax(tqy, cy);
+                int prevx = satx ? -1 : -2, prevy = saty ? -1 : -2;                   // -2: axis settled
 #pragma unroll 1
                 for (int it = 0; it < N + 3; ++it) {
                     double q1x = 0.0, q2x = 0.0, q1y = 0.0, q2y = 0.0;
@@ -615,7 +693,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
 #pragma unroll 1
                     for (int e = 0; e < E; ++e) {
                         const double ai = fabs(sm.av[e * 32 + lane]);
-                        const bool sx = ux_ * ai > rho, sy = uy_ * ai > rho;
+                        const bool sx = tqx * ai > rho, sy = tqy * ai > rho;
                         q1x += sx ? ai : 0.0; q2x += sx ? 0.0 : ai * ai;
                         q1y += sy ? ai : 0.0; q2y += sy ? 0.0 : ai * ai;
                         cnt += (sx ? 1 : 0) + (sy ? 1024 : 0);
@@ -627,22 +705,37 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                         cnt += __shfl_xor_sync(ISMPC_FULL_MASK, cnt, o);
                     }
                     const int nx = cnt & 1023, ny = cnt >> 10;
-                    const bool donex = prevx == -2 || nx == prevx, doney = prevy == -2 || ny == prevy;
-                    if (__all_sync(ISMPC_FULL_MASK, donex && doney)) break;
-                    if (!donex) {
-                        prevx = nx;
-                        const double rem = rax - rho * q1x;
-                        if (!(q2x > 0.0)) { if (rem > 1e-12 * fmax(1.0, rax)) stx = 1; prevx = -2; }
-                        else { const double tn = rem / q2x; if (tn >= ux_) ux_ = tn; }
+                    if (prevx != -2) {
+                        if (nx == prevx) prevx = -2;                                  // same set as the one tqx was solved for
+                        else {
+                            prevx = nx;
+                            const double rem = rax - rho * q1x;
+                            if (!(q2x > 0.0)) { if (rem > 1e-12 * fmax(1.0, rax)) stx = 1; prevx = -2; }
+                            else {
+                                const double tn = rem / q2x;
+                                const bool same = fabs(tn - tqx) <= 1e-13 * tqx;      // the guess was this set's solution
+                                tqx = (it == 0 || tn > tqx) ? tn : tqx;               // (a guess may sit a rounding above t*)
+                                if (same) prevx = -2;
+                            }
+                        }
                     }
-                    if (!doney) {
-                        prevy = ny;
-                        const double rem = ray - rho * q1y;
-                        if (!(q2y > 0.0)) { if (rem > 1e-12 * fmax(1.0, ray)) sty = 1; prevy = -2; }
-                        else { const double tn = rem / q2y; if (tn >= uy_) uy_ = tn; }
+                    if (prevy != -2) {
+                        if (ny == prevy) prevy = -2;
+                        else {
+                            prevy = ny;
+                            const double rem = ray - rho * q1y;
+                            if (!(q2y > 0.0)) { if (rem > 1e-12 * fmax(1.0, ray)) sty = 1; prevy = -2; }
+                            else {
+                                const double tn = rem / q2y;
+                                const bool same = fabs(tn - tqy) <= 1e-13 * tqy;
+                                tqy = (it == 0 || tn > tqy) ? tn : tqy;
+                                if (same) prevy = -2;
+                            }
+                        }
                     }
+                    if (__all_sync(ISMPC_FULL_MASK, prevx == -2 && prevy == -2)) break;
+                    ISMPC_WCOUNT(29);
                 }
-                tqx = ux_; tqy = uy_;
             }
         } else {
             if (rax > 1e-12) stx = 1;
@@ -673,6 +766,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         for (int o = 16; o > 0; o >>= 1) {
             aux += __shfl_xor_sync(ISMPC_FULL_MASK, aux, o); auy += __shfl_xor_sync(ISMPC_FULL_MASK, auy, o);
             nsx += __shfl_xor_sync(ISMPC_FULL_MASK, nsx, o); nsy += __shfl_xor_sync(ISMPC_FULL_MASK, nsy, o);
+            kkt = fmax(kkt, __shfl_xor_sync(ISMPC_FULL_MASK, kkt, o));
         }
         ux0 = __shfl_sync(ISMPC_FULL_MASK, ux0, 0); uy0 = __shfl_sync(ISMPC_FULL_MASK, uy0, 0);
         it_x = nsx; it_y = nsy;
@@ -682,6 +776,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         ISMPC_WPHASE(5);
     } else {
         status |= ISMPC_ST_XY_SKIPPED;
+        kkt = warp_max(kkt);
         if (prim) for (int i = lane; i < 2 * N; i += 32) prim[N + i] = 0.0;
         if (act) for (int i = lane; i < 2 * N; i += 32) act[N + i] = 0;
     }

@@ -24,6 +24,70 @@ __global__ void formc_build_riccati(ismpc_formc_model_t m, int S, int F, int n_p
     }
 }
 
+// Feedback-law tables (formc_law_apply): thread t = 4*pattern + basis runs the tracking recursion of that pattern
+// sequentially for the input (rq, x0) = 0, e_rq, e_x00, e_x01 and stores forces and heights as column `basis`;
+// formc_law_finish turns columns 1..3 into differences against column 0 (the affine part).
+__global__ void formc_build_law(ismpc_formc_model_t m, int n_pat, const double* __restrict__ ric, double* __restrict__ law)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * n_pat) return;
+    const int pat = t >> 2, basis = t & 3;
+    const int N = m.N;
+    const double dt = m.dt, B0 = dt * dt, B1 = dt, g = m.g;
+    const double rq = basis == 1 ? 1.0 : 0.0, x00 = basis == 2 ? 1.0 : 0.0, x01 = basis == 3 ? 1.0 : 0.0;
+    const double* T = ric + (size_t)pat * N * FORMC_RIC_W;
+    const int E = formc_warp_epl(N), LV = E * 32;
+    double* L = law + (size_t)pat * formc_law_pattern_doubles(N);
+#define LAW_AT(k, c) L[(size_t)(c) * LV + ((k) % E) * 32 + (k) / E]
+    double s0 = 0.0, s1 = 0.0;                       // s_{k+1}
+    for (int k = N - 1; k >= 0; --k) {
+        const double a = T[k * FORMC_RIC_W], b = T[k * FORMC_RIC_W + 1], c = T[k * FORMC_RIC_W + 2], d = T[k * FORMC_RIC_W + 3];
+        const bool fixed = d != 0.0;
+        const double K0 = fixed ? 0.0 : a, K1 = fixed ? 0.0 : b;
+        LAW_AT(k, basis) = d - c * (B0 * s0 + B1 * s1);                      // omega_k, parked in the f slot
+        const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+        const double w0 = rq + (fixed ? a : 0.0), w1 = fixed ? b : 0.0;
+        const double u0 = f00 * s0 + f10 * s1 + w0, u1 = f01 * s0 + f11 * s1 + w1;
+        s0 = u0; s1 = u1;
+    }
+    double c0 = x00, c1 = x01;
+    for (int k = 0; k < N; ++k) {
+        const double a = T[k * FORMC_RIC_W], b = T[k * FORMC_RIC_W + 1], d = T[k * FORMC_RIC_W + 3];
+        const bool fixed = d != 0.0;
+        const double K0 = fixed ? 0.0 : a, K1 = fixed ? 0.0 : b;
+        const double om = LAW_AT(k, basis);
+        const double vk = om - (K0 * c0 + K1 * c1);
+        LAW_AT(k, basis) = fixed ? 0.0 : m.mass * (vk + g);
+        LAW_AT(k, 4 + basis) = c0;
+        const double f00 = 1.0 - B0 * K0, f01 = dt - B0 * K1, f10 = -B1 * K0, f11 = 1.0 - B1 * K1;
+        const double u0 = f00 * c0 + f01 * c1 + B0 * om, u1 = f10 * c0 + f11 * c1 + B1 * om;
+        c0 = u0; c1 = u1;
+    }
+#undef LAW_AT
+}
+// columns 1..3 (and 5..7) become differences against column 0 (4): t = pattern * LV + slot
+__global__ void formc_law_finish(int n_pat, int LV, double* __restrict__ law)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pat * LV) return;
+    const int pat = t / LV, x = t - pat * LV;
+    double* L = law + (size_t)pat * FORMC_LAW_W * LV + x;
+    for (int h = 0; h < 2; ++h) {
+        const double a = L[(size_t)(4 * h) * LV];
+        L[(size_t)(4 * h + 1) * LV] -= a; L[(size_t)(4 * h + 2) * LV] -= a; L[(size_t)(4 * h + 3) * LV] -= a;
+    }
+}
+
+int formc_law_launch(const ismpc_formc_model_t& m, int n_pat, const double* ric, double* law, cudaStream_t st, long long* launches)
+{
+    const int LV = formc_warp_epl(m.N) * 32;
+    cudaMemsetAsync(law, 0, (size_t)n_pat * formc_law_pattern_doubles(m.N) * sizeof(double), st);
+    formc_build_law<<<(4 * n_pat + 63) / 64, 64, 0, st>>>(m, n_pat, ric, law);
+    formc_law_finish<<<(n_pat * LV + 127) / 128, 128, 0, st>>>(n_pat, LV, law);
+    *launches += 2;
+    return (int)cudaGetLastError();
+}
+
 int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, double* tab, cudaStream_t st,
                          long long* launches)
 {
@@ -53,6 +117,9 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
     const int N = a.model.N;
     FormCWarpShared sm;
     formc_warp_carve(smem_d, formc_warp_epl(N), sm);
+    if (lane == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t parity = 0;
     double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
 #ifdef ISMPC_PHASE_TIMING
     if (lane == 0 && blockIdx.x < 8192) { g_trace[3 * blockIdx.x] = dbg_globaltimer(); g_trace[3 * blockIdx.x + 2] = dbg_smid(); }
@@ -64,7 +131,7 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
         ismpc_formc_out_t r;
         formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
                         a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
-                        a.active ? a.active + (size_t)inst * 3 * N : nullptr);
+                        a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
         if (lane == 0) store_record(a.out + inst, r);
     }
 #ifdef ISMPC_PHASE_TIMING
@@ -83,6 +150,9 @@ formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
     const int lane = threadIdx.x;
     FormCWarpShared sm;
     formc_warp_carve(smem_d, formc_warp_epl(a.model.N), sm);
+    if (lane == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t parity = 0;
     double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         ismpc_state_t st = state_io[inst];
@@ -102,7 +172,7 @@ formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
                 st.com_vel[0] += a.model.dt * pu.ax; st.com_vel[1] += a.model.dt * pu.ay;
             }
             ismpc_formc_out_t r;
-            formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r, nullptr, nullptr);
+            formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r, nullptr, nullptr, parity);
             st = r.next;
             acc_status |= r.status;
             if (traj && lane < 6) {

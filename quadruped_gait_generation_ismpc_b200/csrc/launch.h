@@ -23,6 +23,7 @@ int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk
 // warp-per-instance kernels (formc_warp_kernels.cu)
 int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, double* tab, cudaStream_t st,
                          long long* launches);
+int formc_law_launch(const ismpc_formc_model_t& m, int n_pat, const double* ric, double* law, cudaStream_t st, long long* launches);
 int formc_warp_supported(int N);
 void formc_set_variant(int v);
 int formc_warp_grid(int N, int n, int sm_count);

@@ -195,10 +195,10 @@ def test_warp_rollout_equals_cta_rollout(handle):
     """Closed loop with pushes: the two kernel families stay together tick by tick (1e-9 over 120 ticks)."""
     model = abi.formc_model()
     handle.formc_set_model(model)
-    state, walk, inst, plan = synth.formc_batch(64, seed=77)
-    walk["sim_time"] = np.minimum(walk["sim_time"], 300)
+    state, walk, inst, plan = synth.formc_batch(64, seed=77, dcm_spread=0.01, k0_cap=300)
     push = synth.push_batch(64, formc=True)
     push["ct0"] = 20; push["ct1"] = 34
+    push["ax"] *= 0.3; push["ay"] *= 0.3           # keep most instances inside the 9 cm ZMP box for the whole run
     try:
         handle.set_option("formc_kernel", 1)
         a = handle.formc_rollout(state, walk, inst, plan, 120, push=push)
@@ -207,7 +207,37 @@ def test_warp_rollout_equals_cta_rollout(handle):
     finally:
         handle.set_option("formc_kernel", 0)
     ok = (a["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
-    assert ok.mean() > 0.7
+    assert ok.mean() > 0.5
     assert np.array_equal(a["status"] & 7, b["status"] & 7)
     assert np.abs(a["traj"][ok] - b["traj"][ok]).max() <= 1e-9
     assert np.array_equal(a["walk"]["footstep_counter"], b["walk"]["footstep_counter"])
+
+
+def test_uneven_ground(handle):
+    """Footsteps at different heights (plan z != 0): mid_z varies over the window, so stage 1 runs the two affine
+    scans instead of the flat-reference feedback law; prepared and unprepared step timings mixed."""
+    state, walk, inst, plan = synth.formc_batch(192, seed=909, z_spread=0.03)
+    rng = np.random.default_rng(3)
+    plan[:, 2] = rng.uniform(-0.02, 0.02, len(plan))
+    inst["S"][::5] = 30; inst["F_ds"][::5] = 15
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    handle.formc_prepare_gait(35, 10)
+    _compare_prepared(handle, model, state, walk, inst, plan)
+
+
+def _compare_prepared(handle, model, state, walk, inst, plan):
+    """_compare without resetting the model (keeps the prepared gait)."""
+    g = handle.formc_solve_batch(state, walk, inst, plan)
+    o = O.formc_batch(model, state, walk, inst, plan, nthreads=8)
+    N = int(model["N"][0])
+    ok = (o["ret"] == 0).all(axis=1) & (o["out"]["status"] & abi.ST_WINDOW == 0)
+    assert ok.sum() >= 0.7 * len(state)
+    gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
+    assert not gfail[ok].any()
+    err = primal_rel_err(g["primal"][ok].reshape(-1, 3, N), o["primal"][ok].reshape(-1, 3, N))
+    assert err.max() <= PRIMAL_TOL, "primal rel err %.3e" % err.max()
+    mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
+    assert mism.sum() == 0
+    for name in ("com_pos", "com_vel"):
+        assert np.abs(g["out"]["next"][name][ok] - o["out"]["next"][name][ok]).max() <= PRIMAL_TOL
