@@ -33,7 +33,7 @@ struct ismpc_handle {
     int opt_formc_cluster = 0;     // 0 = automatic
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
-    int w_resident = 0;            // CTAs of the warp kernels the GPU keeps resident at this model's N (0 = not queried yet)
+    int w_res[3] = {0, 0, 0};      // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel; 0 = not queried
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
@@ -115,7 +115,6 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     }
     if (strcmp(name, "formc_variant") == 0) {      // experiment knob: register budget of the warp tick kernel
         formc_set_variant(value);
-        h->w_resident = 0;
         return ISMPC_OK;
     }
     if (strcmp(name, "formc_kernel") == 0) {
@@ -157,7 +156,7 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_law_launch");
     CK(cudaStreamSynchronize(0));
     h->cm = *m;
-    h->gait_S = h->gait_F = 0; h->ric_S = h->ric_F = 0; h->w_resident = 0;
+    h->gait_S = h->gait_F = 0; h->ric_S = h->ric_F = 0; h->w_res[0] = 0;
     h->c_ctas_per_sm = formc_cluster_ctas_per_sm(m->N);
     h->formc_ready = true;
     return ISMPC_OK;
@@ -194,45 +193,43 @@ static bool formc_use_warp(const ismpc_handle* h)
 }
 
 // Resident CTAs of the warp kernels are queried once per model (the occupancy query costs microseconds per call).
-static int formc_warp_grid_cached(ismpc_handle* h, int n)
+static int formc_warp_prepare(ismpc_handle* h, FormCWarpArgs& wa, const FormCArgs& a, int n)
 {
-    if (h->w_resident <= 0) h->w_resident = formc_warp_grid(h->cm.N, 1 << 30, h->sm_count);
-    return n < h->w_resident ? n : h->w_resident;
+    if (h->w_res[0] <= 0) formc_warp_resident(h->cm.N, h->sm_count, h->w_res);
+    int cap = h->w_res[0] > h->w_res[1] ? h->w_res[0] : h->w_res[1];
+    if (h->w_res[2] > cap) cap = h->w_res[2];
+    if (n < cap) cap = n;
+    wa.base = a;
+    wa.R.none = (const double*)h->c_ric_none.p;
+    wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
+    wa.R.law_none = (const double*)h->c_law_none.p;
+    wa.R.law_gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_law_gait.p : nullptr;
+    wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
+    wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
+    if (h->c_ws.ensure((size_t)cap * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
+    wa.ws = (double*)h->c_ws.p;
+    return 0;
 }
 
 // One tick launch (either kernel family) on device-resident arguments.
 static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStream_t st)
 {
     if (!formc_use_warp(h)) return formc_tick_launch(a, n, formc_cluster_size(h, n), st);
-    const int grid = formc_warp_grid_cached(h, n);
     FormCWarpArgs wa;
-    wa.base = a;
-    wa.R.none = (const double*)h->c_ric_none.p;
-    wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
-    wa.R.law_none = (const double*)h->c_law_none.p;
-    wa.R.law_gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_law_gait.p : nullptr;
-    wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
-    wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
-    if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
-    wa.ws = (double*)h->c_ws.p;
-    return formc_tick_warp_launch(wa, grid, st);
+    int rc = formc_warp_prepare(h, wa, a, n);
+    if (rc) return rc;
+    int grid = 0;
+    return formc_tick_warp_launch(wa, n, h->w_res, &grid, st);
 }
 
 static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                                 const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, cudaStream_t st)
 {
     if (!formc_use_warp(h)) return formc_rollout_launch(a, state_io, walk_io, push, n_ticks, traj, status, n, st);
-    const int grid = formc_warp_grid_cached(h, n);
     FormCWarpArgs wa;
-    wa.base = a;
-    wa.R.none = (const double*)h->c_ric_none.p;
-    wa.R.gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_ric_gait.p : nullptr;
-    wa.R.law_none = (const double*)h->c_law_none.p;
-    wa.R.law_gait = (h->ric_S + h->ric_F > 0) ? (const double*)h->c_law_gait.p : nullptr;
-    wa.R.gS = h->ric_S; wa.R.gF = h->ric_F;
-    wa.ws_stride = formc_warp_ws_doubles(h->cm.N);
-    if (h->c_ws.ensure((size_t)grid * wa.ws_stride * sizeof(double))) return (int)cudaErrorMemoryAllocation;
-    wa.ws = (double*)h->c_ws.p;
+    int rc = formc_warp_prepare(h, wa, a, n);
+    if (rc) return rc;
+    const int grid = n < h->w_res[2] ? n : h->w_res[2];
     return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, grid, st);
 }
 

@@ -91,6 +91,7 @@ __host__ __device__ __forceinline__ void riccati_step(RicP& P, bool fixed, doubl
 // u / per and u % per for 0 <= u < 2^22 through a float reciprocal (exact after one correction step).
 __device__ __forceinline__ void fast_divmod(int u, int per, float rcp, int& q, int& r)
 {
+    if (u >= (1 << 22)) { q = u / per; r = u - q * per; return; }
     q = (int)((float)u * rcp);
     r = u - q * per;
     if (r < 0) { --q; r += per; }
@@ -417,12 +418,16 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         law = R.law_gait + (size_t)wk.mpc_iter * formc_law_pattern_doubles(N);
     }
     const double* rows = plan_all + (size_t)in.plan_first_row * 4;
+    const float rcp_per = 1.0f / (float)per;
+    int q0, r0;                                               // window start: step index, in-step sample
+    fast_divmod(k0, per, rcp_per, q0, r0);
     {
-        const int first = k0 / per;
-        int last = (k0 + 2 * N - 1) / per + 1;
+        int ql, rl;
+        fast_divmod(r0 + 2 * N - 1, per, rcp_per, ql, rl);
+        int last = q0 + ql + 1;
         if (last > in.n_steps - 1) last = in.n_steps - 1;
-        const char* pb = reinterpret_cast<const char*>(rows + 4 * first);
-        const int nbytes = (last - first + 1) * 32;
+        const char* pb = reinterpret_cast<const char*>(rows + 4 * q0);
+        const int nbytes = (last - q0 + 1) * 32;
         if (lane * 128 < nbytes) prefetch_l1(pb + lane * 128);
     }
     const bool staged = __any_sync(ISMPC_FULL_MASK, law != nullptr);
@@ -434,9 +439,8 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
     double rq_first = 0.0, rq_ref = 0.0;
     bool flat = true;
     {
-        const int q0 = k0 / per, r0 = k0 - q0 * per;
-        const float rcp = 1.0f / (float)per;
-        const double invF = 1.0 / (double)F;
+        const float rcp = rcp_per;
+        const double invF = fast_rcp((double)F);
         const double qd = exp(-dt * eta);
         double dl = exp(-dt * eta * (double)(lane * E));                             // deltas (:183-184), dl_i = qd^i
         // (step, in-step sample) of the chunk's first sample in the window and in the tail; then they only count up,
@@ -656,7 +660,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         double tqx = 0.0, tqy = 0.0;
         int stx = 0, sty = 0;
         if (__any_sync(ISMPC_FULL_MASK, aa > 0.0)) {                                  // (the same in all lanes)
-            const double inv_aa = 1.0 / aa;
+            const double inv_aa = fast_rcp(aa);
             tqx = rax * inv_aa; tqy = ray * inv_aa;                                   // no row saturated
             const bool satx = tqx * amax > rho, saty = tqy * amax > rho;
             if (__any_sync(ISMPC_FULL_MASK, satx || saty)) {
@@ -712,7 +716,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                             const double rem = rax - rho * q1x;
                             if (!(q2x > 0.0)) { if (rem > 1e-12 * fmax(1.0, rax)) stx = 1; prevx = -2; }
                             else {
-                                const double tn = rem / q2x;
+                                const double tn = rem * fast_rcp(q2x);
                                 const bool same = fabs(tn - tqx) <= 1e-13 * tqx;      // the guess was this set's solution
                                 tqx = (it == 0 || tn > tqx) ? tn : tqx;               // (a guess may sit a rounding above t*)
                                 if (same) prevx = -2;
@@ -726,7 +730,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                             const double rem = ray - rho * q1y;
                             if (!(q2y > 0.0)) { if (rem > 1e-12 * fmax(1.0, ray)) sty = 1; prevy = -2; }
                             else {
-                                const double tn = rem / q2y;
+                                const double tn = rem * fast_rcp(q2y);
                                 const bool same = fabs(tn - tqy) <= 1e-13 * tqy;
                                 tqy = (it == 0 || tn > tqy) ? tn : tqy;
                                 if (same) prevy = -2;

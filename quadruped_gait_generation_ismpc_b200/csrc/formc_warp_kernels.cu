@@ -197,33 +197,45 @@ int formc_warp_supported(int N) { return N >= 2 && N <= ISMPC_MAX_N; }
 
 // Grid of the warp kernels for n instances: one 32-thread CTA per instance up to what the GPU keeps resident,
 // grid-stride beyond that (bounds the workspace of the general vertical path).
-int g_formc_variant = 1;
+// Two builds of the tick kernel: <1> takes the registers it wants (fastest while every instance of the batch has a
+// resident warp: the 1,024-instance tick), <16> is held to 128 registers so that 16 warps per SM stay resident
+// (throughput of large batches: 65,536 instances run 1.25x faster).  variant 0 = pick by batch size.
+static int g_formc_variant = 0;
 void formc_set_variant(int v) { g_formc_variant = v; }
-int formc_warp_grid(int N, int n, int sm_count)
+
+static void formc_warp_configure(size_t smem)
 {
-    const size_t smem = formc_warp_smem_bytes(N);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(formc_tick_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    int per_sm = 0;
-    cudaError_t oe = g_formc_variant == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<16>, 32, smem)
-                   : g_formc_variant == 12 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<12>, 32, smem)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, formc_tick_warp_kernel<1>, 32, smem);
-    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
-    const long long cap = (long long)per_sm * sm_count;
-    return (int)((long long)n < cap ? n : cap);
 }
 
-int formc_tick_warp_launch(const FormCWarpArgs& a, int grid, cudaStream_t st)
+// CTAs (= warps = instances in flight) the GPU keeps resident: res[0] for the tick kernel <1>, res[1] for <16>,
+// res[2] for the rollout kernel.
+void formc_warp_resident(int N, int sm_count, int res[3])
+{
+    const size_t smem = formc_warp_smem_bytes(N);
+    formc_warp_configure(smem);
+    int b = 0;
+    res[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<1>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[2] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_warp_kernel, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+}
+
+// One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
+// general vertical path).
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[3], int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
-    if (g_formc_variant == 16) formc_tick_warp_kernel<16><<<grid, 32, smem, st>>>(a);
-    else if (g_formc_variant == 12) formc_tick_warp_kernel<12><<<grid, 32, smem, st>>>(a);
+    const bool big = g_formc_variant == 16 || (g_formc_variant == 0 && n > res[0]);
+    const int cap = big ? res[1] : res[0];
+    const int grid = n < cap ? n : cap;
+    *grid_out = grid;
+    if (big) formc_tick_warp_kernel<16><<<grid, 32, smem, st>>>(a);
     else formc_tick_warp_kernel<1><<<grid, 32, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
