@@ -171,9 +171,14 @@ const char* ismpc_last_cuda_error(const ismpc_handle* h);
 /* Number of kernels this handle has launched since creation (for the benchmark's launch count). */
 int64_t ismpc_kernel_launches(const ismpc_handle* h);
 
-/* Tuning knobs that do not change results.  "formc_cluster_size": CTAs per instance of the formulation-C tick
- * (1 = CTA-per-QP, 2/4/8 = thread-block-cluster-per-QP, 0 = automatic: clusters from N = 200 on while the whole
- * batch stays resident -- the latency regime). */
+/* Tuning knobs that do not change results beyond rounding (every kernel family is an exact solver of the same
+ * strictly convex QPs; tests/test_formc_gpu.py holds them to 1e-9 of each other).
+ *   "formc_kernel":       0 = automatic (the warp-per-instance kernels), 1 = CTA / cluster per instance, 2 = warp.
+ *   "formc_cluster_size": CTAs per instance of the CTA-per-instance family (1 = CTA-per-QP, 2/4/8 = thread-block-
+ *                         cluster-per-QP); setting it selects that family, 0 returns to automatic.
+ *   "formc_variant":      register budget of the warp tick kernel: 0 = by batch size, 1 = unlimited, 16 = 128
+ *                         registers (16 resident warps per SM).
+ * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);
 
 /* Measurement utility (not part of the reference seam): register-resident DFMA micro-benchmark, the FP64
@@ -186,8 +191,10 @@ int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* model);
 
 /* Optional, after ismpc_formc_set_model: declares the step timing (S single-support, F_ds double-support samples;
  * parameters.cpp:43-44) most instances use, so that the flight-phase equalities of stage 1 (MPCSolver.cpp:223-243)
- * are folded into one precomputed projector table per mpcIter.  Results do not change; instances with another
- * (S, F_ds) take the generic path.  Calls with host buffers do this by themselves from the first instance. */
+ * are folded into precomputed tables per mpcIter (Riccati gains and the explicit feedback law for the warp kernels,
+ * one projector per mpcIter for the CTA kernels).  Results do not change; instances with another (S, F_ds) take the
+ * generic path (the recursion is run in-kernel).  Calls with host buffers do this by themselves from the first
+ * instance. */
 int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds);
 
 /* One tick of MPCSolver::solve (MPCSolver.cpp:204-501) for n independent instances.

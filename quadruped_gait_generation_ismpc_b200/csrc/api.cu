@@ -113,7 +113,8 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
         h->opt_formc_cluster = value;
         return ISMPC_OK;
     }
-    if (strcmp(name, "formc_variant") == 0) {      // experiment knob: register budget of the warp tick kernel
+    if (strcmp(name, "formc_variant") == 0) {      // register budget of the warp tick kernel (process-wide)
+        if (value != 0 && value != 1 && value != 16) return ISMPC_ERR_ARG;
         formc_set_variant(value);
         return ISMPC_OK;
     }
