@@ -197,8 +197,17 @@ int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t* model);
  * instance. */
 int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds);
 
+/* Optional: hands the footstep plans to the handle once, as the reference's constructor receives them
+ * (MPCSolver::MPCSolver(ftsp_and_timings), MPCSolver.cpp:5; Controller.cpp:89-106 builds the matrix once and passes
+ * the same object to every solve()).  The table is copied into device memory owned by the handle (mem = ISMPC_MEM_HOST
+ * or ISMPC_MEM_DEVICE says where plan_xyzt lives; the call synchronises); afterwards ismpc_formc_solve_batch and
+ * ismpc_formc_rollout accept plan_xyzt = NULL (plan_rows is then ignored) and a host-memory tick moves only the
+ * per-tick records: state, walk state, instance in -- result record out.  plan_rows = 0 forgets the table. */
+int ismpc_formc_set_plan(ismpc_handle* h, const double* plan_xyzt, int plan_rows, int mem);
+
 /* One tick of MPCSolver::solve (MPCSolver.cpp:204-501) for n independent instances.
- * plan_xyzt: plan_rows x 4 doubles row-major (x, y, z, t) -- ftsp_and_timings (Controller.cpp:89-97).
+ * plan_xyzt: plan_rows x 4 doubles row-major (x, y, z, t) -- ftsp_and_timings (Controller.cpp:89-97); NULL = the
+ *            table given to ismpc_formc_set_plan.
  * primal_opt (nullable): n x 3N doubles  [f(N) | u_x(N) | u_y(N)] per instance.
  * active_opt (nullable): n x 3N int8    [S_bar_z rows | x box rows | y box rows], -1 lower / 0 / +1 upper,
  *                        the convention of QProblem::getWorkingSetConstraints (qpOASES/QProblem.cpp:809-829);

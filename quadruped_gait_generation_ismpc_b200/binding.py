@@ -18,7 +18,7 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
-           "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch"]
+           "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan"]
 
 _lib = None
 
@@ -66,6 +66,7 @@ def lib():
     L.ismpc_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ismpc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.ismpc_formc_prepare_gait.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ismpc_formc_set_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
@@ -144,16 +145,30 @@ class Handle:
     def formc_prepare_gait(self, S, F_ds):
         self._check(self._L.ismpc_formc_prepare_gait(self._h, int(S), int(F_ds)), "ismpc_formc_prepare_gait")
 
+    def formc_set_plan(self, plan, mem=abi.MEM_HOST, rows=None):
+        """Footstep plans resident in the handle (the reference's constructor argument); plan=None forgets them.
+        plan: numpy array (host) or an integer device address with rows given."""
+        if plan is None:
+            self._check(self._L.ismpc_formc_set_plan(self._h, None, 0, abi.MEM_HOST), "ismpc_formc_set_plan")
+            return
+        if isinstance(plan, np.ndarray):
+            plan = np.ascontiguousarray(plan, dtype=np.float64)
+            rows = plan.shape[0]
+        self._check(self._L.ismpc_formc_set_plan(self._h, _ptr(plan), int(rows), mem), "ismpc_formc_set_plan")
+
     def formc_solve_batch(self, state, walk, inst, plan, want_primal=True, want_active=True):
-        """Host-memory call (numpy arrays in, numpy arrays out)."""
+        """Host-memory call (numpy arrays in, numpy arrays out).  plan=None: the table given to formc_set_plan."""
         n = len(state)
         N = int(self.formc["N"][0])
-        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        rows = 0
+        if plan is not None:
+            plan = np.ascontiguousarray(plan, dtype=np.float64)
+            rows = plan.shape[0]
         out = np.zeros(n, dtype=abi.FORMC_OUT)
         primal = np.zeros((n, 3 * N)) if want_primal else None
         active = np.zeros((n, 3 * N), dtype=np.int8) if want_active else None
         rc = self._L.ismpc_formc_solve_batch(self._h, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
-                                             plan.shape[0], _ptr(out), _ptr(primal), _ptr(active), abi.MEM_HOST, None)
+                                             rows, _ptr(out), _ptr(primal), _ptr(active), abi.MEM_HOST, None)
         self._check(rc, "ismpc_formc_solve_batch")
         return dict(out=out, primal=primal, active=active)
 

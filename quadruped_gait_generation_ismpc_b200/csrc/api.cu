@@ -38,7 +38,8 @@ struct ismpc_handle {
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
     DevBuf c_tables, c_work, c_info, c_ptab;
-    DevBuf c_ric_none, c_ric_gait, c_law_none, c_law_gait, c_ws;   // Riccati tables (warp kernels) and the per-warp workspace of their general path
+    DevBuf c_ric_none, c_ric_gait, c_law_none, c_law_gait, c_ws, c_plan;
+    int plan_res_rows = 0;         // rows of the resident footstep-plan table (ismpc_formc_set_plan), 0 = none   // Riccati tables (warp kernels) and the per-warp workspace of their general path
     int gait_S = 0, gait_F = 0;            // prepared gait (projector tables in c_ptab), 0 = none
     int ric_S = 0, ric_F = 0;              // prepared gait of the Riccati tables (c_ric_gait), 0 = none
     // form A
@@ -97,7 +98,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
 {
     if (!h) return ISMPC_ERR_ARG;
     cudaSetDevice(h->device);
-    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->c_plan, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
@@ -266,6 +267,20 @@ extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)
     return ISMPC_OK;
 }
 
+extern "C" int ismpc_formc_set_plan(ismpc_handle* h, const double* plan_xyzt, int plan_rows, int mem)
+{
+    if (!h || plan_rows < 0 || (plan_rows > 0 && !plan_xyzt)) return ISMPC_ERR_ARG;
+    if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_DEVICE) return ISMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    h->plan_res_rows = 0;
+    if (plan_rows == 0) return ISMPC_OK;
+    if (h->c_plan.ensure((size_t)plan_rows * 4 * sizeof(double))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpy(h->c_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double),
+                  mem == ISMPC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    h->plan_res_rows = plan_rows;
+    return ISMPC_OK;
+}
+
 extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state_t* state, const ismpc_walk_t* walk,
                                        const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
                                        ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt, int mem,
@@ -273,7 +288,9 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
 {
     if (!h) return ISMPC_ERR_ARG;
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
-    if (n < 0 || n > h->max_batch || !state || !walk || !inst || !plan_xyzt || !out || plan_rows <= 0)
+    const bool plan_res = plan_xyzt == nullptr;
+    if (plan_res) plan_rows = h->plan_res_rows;
+    if (n < 0 || n > h->max_batch || !state || !walk || !inst || !out || plan_rows <= 0)
         return ISMPC_ERR_ARG;
     if (n == 0) return ISMPC_OK;
     CK(cudaSetDevice(h->device));
@@ -282,7 +299,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     FormCArgs a;
     formc_fill_args(h, a, n);
     if (mem == ISMPC_MEM_DEVICE) {
-        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt; a.plan_rows = plan_rows;
+        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt; a.plan_rows = plan_rows;
         a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
         int rc = formc_launch_tick(h, a, n, st);
         h->launches += 1;
@@ -298,16 +315,17 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     const size_t mb = (size_t)h->max_batch;
     if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
         h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t)) ||
-        h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double)))
+        (!plan_res && h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double))))
         return ISMPC_ERR_ALLOC;
     if (primal_opt && h->s_primal.ensure(mb * 3 * N * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (active_opt && h->s_active.ensure(mb * 3 * N)) return ISMPC_ERR_ALLOC;
     CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!plan_res) CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
-    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = (const double*)h->s_plan.p; a.plan_rows = plan_rows;
+    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
+    a.plan_rows = plan_rows;
     a.out = (ismpc_formc_out_t*)h->s_cout.p;
     a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
     a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
@@ -328,7 +346,9 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
 {
     if (!h) return ISMPC_ERR_ARG;
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
-    if (n < 0 || n > h->max_batch || n_ticks < 0 || !state || !walk || !inst || !plan_xyzt || plan_rows <= 0)
+    const bool plan_res = plan_xyzt == nullptr;
+    if (plan_res) plan_rows = h->plan_res_rows;
+    if (n < 0 || n > h->max_batch || n_ticks < 0 || !state || !walk || !inst || plan_rows <= 0)
         return ISMPC_ERR_ARG;
     if (n == 0 || n_ticks == 0) return ISMPC_OK;
     CK(cudaSetDevice(h->device));
@@ -337,7 +357,7 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     formc_fill_args(h, a, n);
     a.out = nullptr; a.primal = nullptr; a.active = nullptr; a.plan_rows = plan_rows;
     if (mem == ISMPC_MEM_DEVICE) {
-        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_xyzt;
+        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt;
         int rc = formc_launch_rollout(h, a, n, state, walk, push, n_ticks, traj_opt, status_opt, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
@@ -351,7 +371,8 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     }
     const size_t mb = (size_t)h->max_batch;
     if (h->s_state.ensure(mb * sizeof(ismpc_state_t)) || h->s_walk.ensure(mb * sizeof(ismpc_walk_t)) ||
-        h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) || h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double)))
+        h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t)) ||
+        (!plan_res && h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double))))
         return ISMPC_ERR_ALLOC;
     if (push && h->s_push.ensure(mb * sizeof(ismpc_push_t))) return ISMPC_ERR_ALLOC;
     if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
@@ -359,10 +380,10 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!plan_res) CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (push) CK(cudaMemcpyAsync(h->s_push.p, push, n * sizeof(ismpc_push_t), cudaMemcpyHostToDevice, st));
     a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
-    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = (const double*)h->s_plan.p;
+    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
     int rc = formc_launch_rollout(h, a, n, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr,

@@ -128,7 +128,7 @@ public:
             wk_[i].support_foot = walk[i].supportFoot ? 1 : 0;
             inst_[i].n_steps = plan_rows_;
         }
-        int rc = ismpc_formc_solve_batch(h_, n_, st_.data(), wk_.data(), inst_.data(), plan_.data(), plan_rows_,
+        int rc = ismpc_formc_solve_batch(h_, n_, st_.data(), wk_.data(), inst_.data(), /*plan: resident*/ nullptr, 0,
                                          out_.data(), nullptr, nullptr, ISMPC_MEM_HOST, nullptr);
         if (rc != ISMPC_OK)
             throw std::runtime_error(std::string("ismpc_formc_solve_batch: ") + ismpc_error_string(rc) + " [" +
@@ -149,6 +149,10 @@ private:
         plan_.resize((size_t)plan_rows_ * 4);
         for (int i = 0; i < plan_rows_; ++i)
             for (int c = 0; c < 4; ++c) plan_[(size_t)i * 4 + c] = f(i, c);
+        // like the reference's constructor argument, the plan lives with the solver: one upload, then every tick
+        // moves only the state / walk-state records (ismpc_formc_set_plan)
+        int rc = ismpc_formc_set_plan(h_, plan_.data(), plan_rows_, ISMPC_MEM_HOST);
+        if (rc != ISMPC_OK) throw std::runtime_error(std::string("ismpc_formc_set_plan: ") + ismpc_error_string(rc));
     }
     int n_;
     Parameters par_;

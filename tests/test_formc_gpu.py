@@ -241,3 +241,26 @@ def _compare_prepared(handle, model, state, walk, inst, plan):
     assert mism.sum() == 0
     for name in ("com_pos", "com_vel"):
         assert np.abs(g["out"]["next"][name][ok] - o["out"]["next"][name][ok]).max() <= PRIMAL_TOL
+
+
+def test_resident_plan_equals_plan_per_call(handle):
+    """ismpc_formc_set_plan (the plan as constructor data, MPCSolver.cpp:5) == passing the plan with every call;
+    tick and rollout, and the call is refused once the table is forgotten."""
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(48, seed=12, k0_cap=300)
+    a = handle.formc_solve_batch(state, walk, inst, plan)
+    ra = handle.formc_rollout(state, walk, inst, plan, 25)
+    handle.formc_set_plan(plan)
+    try:
+        b = handle.formc_solve_batch(state, walk, inst, None)
+        assert a["out"].tobytes() == b["out"].tobytes()
+        assert np.array_equal(a["primal"], b["primal"]) and np.array_equal(a["active"], b["active"])
+        st, wk = state.copy(), walk.copy()
+        traj = np.zeros((len(st), 25, 6)); status = np.zeros(len(st), dtype=np.int32)
+        handle.formc_rollout_raw(len(st), 25, st, wk, inst, None, 0, traj=traj, status=status, mem=abi.MEM_HOST)
+        assert np.array_equal(ra["traj"], traj) and np.array_equal(ra["state"], st)
+    finally:
+        handle.formc_set_plan(None)
+    with pytest.raises(Exception):
+        handle.formc_solve_batch(state, walk, inst, None)
