@@ -187,3 +187,68 @@ def test_plan_generators():
     fpw, cw = plans.walk_plan()
     assert cw.shape[0] >= 100 and np.allclose(cw[1], cw[0]) and np.allclose(cw[3], cw[2])
     assert np.all(np.diff(c[:, 0]) >= -1e-12)
+
+
+def _riccati_vertical(model, state, walk, inst, plan, i):
+    """numpy restatement of what formc_warp.cuh does in stage 1: the vertical QP (MPCSolver.cpp:220-269) as an LQ
+    tracking problem on x = (z_pos, z_vel), x+ = A x + B v, v = f/m - g, with the flight-phase inputs fixed to f = 0."""
+    N = int(model["N"][0]); dt = float(model["dt"][0]); m = float(model["mass"][0]); g = float(model["g"][0])
+    qp, qv, qu = float(model["q_p"][0]), float(model["q_v"][0]), float(model["q_u"][0])
+    S, F = int(inst["S"][i]), int(inst["F_ds"][i]); per = S + F
+    h = float(inst["com_height"][i])
+    k0 = int(walk["sim_time"][i] / (dt / float(model["dtc"][0])))
+    mi, fc = int(walk["mpc_iter"][i]), int(walk["footstep_counter"][i])
+    ne = c_lo = 0
+    if fc > 1:                                                  # MPCSolver.cpp:223-243
+        ne, c_lo = (F, S - mi) if mi < S else (S + F - mi, 0)
+        ne = max(min(ne, N - c_lo), 0)
+    fixed = np.zeros(N, bool); fixed[c_lo:c_lo + ne] = True
+    f0, ns = int(inst["plan_first_row"][i]), int(inst["n_steps"][i])
+
+    def midz(t):                                                # MPCSolver.cpp:167-180
+        a, r = divmod(t, per)
+        if a >= ns - 1:
+            return 0.0
+        za = plan[f0 + a, 2]
+        return za if r < S else za + (plan[f0 + a + 1, 2] - za) * ((r - S) / F)
+
+    ref = np.array([h + midz(k0 + k) for k in range(N)])
+    A = np.array([[1.0, dt], [0.0, 1.0]]); B = np.array([dt * dt, dt]); rho = qu * m * m; Q = np.diag([qp, qv])
+    P = np.zeros((2, 2)); s = np.zeros(2)
+    K = np.zeros((N, 2)); R = np.ones(N); s_next = np.zeros((N, 2))
+    for k in range(N - 1, -1, -1):
+        s_next[k] = s
+        q = np.array([-qp * ref[k], 0.0])
+        if fixed[k]:
+            s = q + A.T @ (s - P @ B * g); P = Q + A.T @ P @ A
+        else:
+            R[k] = rho + B @ P @ B; K[k] = (B @ P @ A) / R[k]
+            Phi = A - np.outer(B, K[k])
+            s = q + Phi.T @ s; P = Q + A.T @ P @ Phi
+    z0, zd0 = state["com_pos"][i][2], state["com_vel"][i][2]
+    x = np.array([z0 + dt * zd0, zd0]); f = np.zeros(N)
+    for k in range(N):
+        v = -g if fixed[k] else -K[k] @ x - (B @ s_next[k]) / R[k]
+        f[k] = m * (v + g)
+        x = A @ x + B * v
+    return f
+
+
+def test_vertical_qp_is_an_lq_tracking_problem():
+    """The identity the warp kernels build on: the Riccati solution of the LQ problem IS the minimiser of the condensed
+    vertical QP that the oracle solves with qpOASES (instances without an active row of 0 <= S f <= fz_max)."""
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.formc_batch(48, seed=3, running_frac=0.7, vary_height=True)
+    rng = np.random.default_rng(0)
+    plan[:, 2] = rng.uniform(-0.02, 0.02, len(plan))            # uneven ground: mid_z varies over the window
+    o = O.formc_batch(model, state, walk, inst, plan)
+    N = 100
+    checked = 0
+    for i in range(len(state)):
+        if o["ret"][i][0] != 0 or o["nwsr"][i][0] != 0 or (o["out"]["status"][i] & abi.ST_WINDOW):
+            continue
+        f = _riccati_vertical(model, state, walk, inst, plan, i)
+        ref = o["primal"][i][:N]
+        assert np.abs(f - ref).max() / max(1.0, np.abs(ref).max()) < 1e-9
+        checked += 1
+    assert checked >= 30
