@@ -170,7 +170,7 @@ extern "C" int ismpc_formc_set_model(ismpc_handle* h, const ismpc_formc_model_t*
 static int formc_cluster_size(const ismpc_handle* h, int n)
 {
     if (h->opt_formc_cluster > 0) return h->opt_formc_cluster;
-    if (h->cm.N < 200) return 1;
+    if (h->cm.N < 200) return 1;   // (only reached when the CTA family is selected: formc_kernel = 1)
     const long long resident = (long long)h->c_ctas_per_sm * h->sm_count;
     if (4LL * n <= resident) return 4;
     if (2LL * n <= resident) return 2;

@@ -1,5 +1,6 @@
-"""BASELINE.json configs[3]: horizon sweep N = 50/100/200/400, 1,024 instances, CTA-per-QP vs cluster-per-QP
-(formulation C, 3 QPs per instance-tick) and the formulation-A tick at the same horizons (C = N, P = 2N).
+"""BASELINE.json configs[3]: horizon sweep N = 50/100/200/400, 1,024 instances, warp-per-QP vs CTA-per-QP vs
+cluster-per-QP (formulation C, 3 QPs per instance-tick) and the formulation-A tick at the same horizons (C = N, P = 2N).
+Times are per launch with BURST launches back to back between the CUDA events (hides the host-side launch cost).
 usage: python tools/horizon_sweep.py [n] [out.json]"""
 import json
 import os
@@ -24,14 +25,20 @@ def to_dev(a):
     return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
 
 
-def timed(fn, reps=30, warm=5):
+BURST = int(os.environ.get("SWEEP_BURST", "10"))
+
+
+def timed(fn, reps=12, warm=3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []
     for k in range(reps + warm):
         torch.cuda.synchronize()
-        e0.record(); fn(); e1.record(); e1.synchronize()
+        e0.record()
+        for _ in range(BURST):
+            fn()
+        e1.record(); e1.synchronize()
         if k >= warm:
-            ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.append(e0.elapsed_time(e1) * 1e3 / BURST)
     return statistics.median(ts)
 
 
@@ -44,6 +51,16 @@ for N in (50, 100, 200, 400):
     d = [to_dev(x) for x in (st, wk, ins, pl)]
     out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
     ref = None
+    h.set_option("formc_cluster_size", 0); h.set_option("formc_kernel", 2)
+    for m in [n] + small:                # warp-per-QP (the default family)
+        us = timed(lambda: h.formc_solve_batch_raw(m, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                                   pl.shape[0], out.data_ptr(), stream=stream))
+        o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMC_OUT).copy()
+        rows.append({"formulation": "C", "N": N, "instances": m, "kernel": "warp_per_qp", "us_per_tick": us,
+                     "qp_per_s": 3.0 * m / (us * 1e-6),
+                     "failed": int((o["status"][:m] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL) != 0).sum())})
+        print(rows[-1])
+    h.set_option("formc_kernel", 0)
     for cs in (1, 2, 4, 8):
         h.set_option("formc_cluster_size", cs)
         us = timed(lambda: h.formc_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
