@@ -271,8 +271,8 @@ def main():
     FLOP_FORMC = float(load_ncu().get("fp64_flop_per_instance_tick", FLOP_FORMC_FALLBACK))
 
     # ---- e2e: the C ABI with HOST buffers (pinned), copies inside the timed region -------------------------
-    # Headline e2e = the serving loop a caller runs: two handles on two streams, ISMPC_MEM_HOST_ASYNC, so that
-    # step k+1's host->device copy overlaps step k's kernel and device->host copy.  Every step copies its own
+    # Headline e2e = the serving loop a caller runs: DEPTH handles on DEPTH streams, ISMPC_MEM_HOST_ASYNC, so that
+    # step k+1's host->device copies overlap step k's kernel and device->host copy.  Every step copies its own
     # inputs from pinned host memory and lands its result records in pinned host memory, where they are read.
     # The synchronous single call (ISMPC_MEM_HOST) is reported next to it as e2e_sync.
     # The footstep plans are constructor data in the reference (MPCSolver::MPCSolver(ftsp_and_timings); Controller
@@ -310,7 +310,7 @@ def main():
     barrier()
     e2e_sync_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
 
-    DEPTH = 2
+    DEPTH = int(os.environ.get("ISMPC_E2E_DEPTH", "4"))      # calls in flight: 2 -> 110, 3 -> 149, 4 -> 161, 6 -> 154 M QP/s
     pipe = []
     for s_ in range(DEPTH):
         hh = binding.Handle(device=local, max_batch=max(n, 1024)); hh.formc_set_model(model); hh.formc_prepare_gait(35, 10)
@@ -376,10 +376,10 @@ def main():
                                  % (n_slots, n_slots * per_batch / 1e6)},
                 "e2e": {"value": e2e_value, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad,
-                        "how": "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, 2 handles on 2 streams "
-                               "(double-buffered serving loop); every step copies its state / walk-state / instance records in "
+                        "how": "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d handles on %d streams "
+                               "(serving loop with that many calls in flight); every step copies its state / walk-state / instance records in "
                                "and its result records out; the footstep plans are resident in the handle "
-                               "(ismpc_formc_set_plan), as they are constructor data of the reference's MPCSolver",
+                               "(ismpc_formc_set_plan), as they are constructor data of the reference's MPCSolver" % (DEPTH, DEPTH),
                         "kernel_launches": int(e2e_launches)},
                 "e2e_with_plan": {"value": 3.0 * n * world * K / e2e_plan_s, "unit": "QP solves/s",
                                   "h2d_bytes_per_step": int(h2d_with_plan), "d2h_bytes_per_step": int(d2h),
