@@ -33,7 +33,7 @@ struct ismpc_handle {
     int opt_formc_cluster = 0;     // 0 = automatic
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
-    int w_res[3] = {0, 0, 0};      // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel; 0 = not queried
+    int w_res[4] = {0, 0, 0, 0};   // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel, pair kernel; 0 = not queried
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
@@ -115,7 +115,7 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
         return ISMPC_OK;
     }
     if (strcmp(name, "formc_variant") == 0) {      // register budget of the warp tick kernel (process-wide)
-        if (value != 0 && value != 1 && value != 16) return ISMPC_ERR_ARG;
+        if (value != 0 && value != 1 && value != 2 && value != 16) return ISMPC_ERR_ARG;
         formc_set_variant(value);
         return ISMPC_OK;
     }
@@ -200,6 +200,7 @@ static int formc_warp_prepare(ismpc_handle* h, FormCWarpArgs& wa, const FormCArg
     if (h->w_res[0] <= 0) formc_warp_resident(h->cm.N, h->sm_count, h->w_res);
     int cap = h->w_res[0] > h->w_res[1] ? h->w_res[0] : h->w_res[1];
     if (h->w_res[2] > cap) cap = h->w_res[2];
+    if (h->w_res[3] > cap) cap = h->w_res[3];
     if (n < cap) cap = n;
     wa.base = a;
     wa.R.none = (const double*)h->c_ric_none.p;

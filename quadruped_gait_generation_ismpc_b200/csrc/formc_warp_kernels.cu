@@ -1,5 +1,6 @@
 // formc_warp_kernels.cu -- formulation C, warp-per-instance kernels (see formc_warp.cuh) and the Riccati tables.
 #include "formc_warp.cuh"
+#include "formc_pair.cuh"
 #include "launch.h"
 
 namespace ismpc {
@@ -139,6 +140,38 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
 #endif
 }
 
+// Latency build of the tick: two warps (one 64-thread CTA) per instance, see formc_pair.cuh.
+__global__ void __launch_bounds__(64, 7)
+formc_tick_pair_kernel(FormCWarpArgs wa)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const FormCArgs& a = wa.base;
+    const int N = a.model.N, E = formc_warp_epl(N);
+    FormCWarpShared sm;
+    formc_warp_carve(smem_d, E, sm);
+    double* red = smem_d + (FORMC_WARP_VECS * E * 32 + 2);
+    if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t parity = 0;
+    double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
+#ifdef ISMPC_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 8192) { g_trace[3 * blockIdx.x] = dbg_globaltimer(); g_trace[3 * blockIdx.x + 2] = dbg_smid(); }
+#endif
+    for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
+        const ismpc_state_t st = a.state[inst];
+        const ismpc_walk_t wk = a.walk[inst];
+        const ismpc_formc_inst_t in = a.inst[inst];
+        ismpc_formc_out_t r;
+        formc_tick_pair(sm, red, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
+                        a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
+                        a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
+        if (threadIdx.x == 32) store_record(a.out + inst, r);
+    }
+#ifdef ISMPC_PHASE_TIMING
+    if (threadIdx.x == 32 && blockIdx.x < 8192) g_trace[3 * blockIdx.x + 1] = dbg_globaltimer();
+#endif
+}
+
 // Closed loop: the warp keeps its instance and advances it n_ticks times (Controller::update bookkeeping,
 // Controller.cpp:297-302 with the footstep switch enabled, :503-504).
 __global__ void __launch_bounds__(32, 1)
@@ -197,9 +230,10 @@ int formc_warp_supported(int N) { return N >= 2 && N <= ISMPC_MAX_N; }
 
 // Grid of the warp kernels for n instances: one 32-thread CTA per instance up to what the GPU keeps resident,
 // grid-stride beyond that (bounds the workspace of the general vertical path).
-// Two builds of the tick kernel: <1> takes the registers it wants (fastest while every instance of the batch has a
-// resident warp: the 1,024-instance tick), <16> is held to 128 registers so that 16 warps per SM stay resident
-// (throughput of large batches: 65,536 instances run 1.25x faster).  variant 0 = pick by batch size.
+// Builds of the tick kernel: the PAIR kernel (two warps per instance, formc_pair.cuh) is the latency build, used while
+// every instance of the batch has a resident CTA (the 1,024-instance tick); <1> is one warp per instance with the
+// registers it wants; <16> is held to 128 registers so that 16 warps per SM stay resident (throughput of large
+// batches: 65,536 instances run 1.25x faster than with <1>).  variant 0 = pick by batch size, 2 = pair.
 static int g_formc_variant = 0;
 void formc_set_variant(int v) { g_formc_variant = v; }
 
@@ -210,13 +244,15 @@ static void formc_warp_configure(size_t smem)
         cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(formc_tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(smem + FORMC_PAIR_RED * sizeof(double)));
         configured = smem;
     }
 }
 
 // CTAs (= warps = instances in flight) the GPU keeps resident: res[0] for the tick kernel <1>, res[1] for <16>,
-// res[2] for the rollout kernel.
-void formc_warp_resident(int N, int sm_count, int res[3])
+// res[2] for the rollout kernel, res[3] for the pair kernel.
+void formc_warp_resident(int N, int sm_count, int res[4])
 {
     const size_t smem = formc_warp_smem_bytes(N);
     formc_warp_configure(smem);
@@ -224,13 +260,20 @@ void formc_warp_resident(int N, int sm_count, int res[3])
     res[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<1>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[2] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_warp_kernel, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[3] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
 }
 
 // One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
 // general vertical path).
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[3], int* grid_out, cudaStream_t st)
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[4], int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
+    if (g_formc_variant == 2 || (g_formc_variant == 0 && n <= res[3])) {
+        const int grid = n < res[3] ? n : res[3];
+        *grid_out = grid;
+        formc_tick_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a);
+        return (int)cudaGetLastError();
+    }
     const bool big = g_formc_variant == 16 || (g_formc_variant == 0 && n > res[0]);
     const int cap = big ? res[1] : res[0];
     const int grid = n < cap ? n : cap;

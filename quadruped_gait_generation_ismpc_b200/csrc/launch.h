@@ -26,8 +26,8 @@ int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, d
 int formc_law_launch(const ismpc_formc_model_t& m, int n_pat, const double* ric, double* law, cudaStream_t st, long long* launches);
 int formc_warp_supported(int N);
 void formc_set_variant(int v);
-void formc_warp_resident(int N, int sm_count, int res[3]);
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[3], int* grid_out, cudaStream_t st);
+void formc_warp_resident(int N, int sm_count, int res[4]);
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[4], int* grid_out, cudaStream_t st);
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                               const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
                               cudaStream_t st);

@@ -174,9 +174,13 @@ def test_warp_per_instance_equals_cta_per_instance(handle, N):
         handle.set_option("formc_kernel", 1)
         a = handle.formc_solve_batch(state, walk, inst, plan)
         handle.set_option("formc_kernel", 2)
-        res = [handle.formc_solve_batch(state, walk, inst, plan)]
+        res = []
+        for variant in (1, 16, 2):       # one warp per instance (two register budgets), two warps per instance
+            handle.set_option("formc_variant", variant)
+            res.append(handle.formc_solve_batch(state, walk, inst, plan))
     finally:
         handle.set_option("formc_kernel", 0)
+        handle.set_option("formc_variant", 0)
     assert (a["out"]["iters"][:, 0] > 0).any(), "test is vacuous: the general vertical path never ran"
     for b in res:
         assert np.array_equal(a["out"]["status"], b["out"]["status"])
@@ -189,6 +193,11 @@ def test_warp_per_instance_equals_cta_per_instance(handle, N):
         assert np.abs(a["out"]["next"]["com_pos"][ok] - b["out"]["next"]["com_pos"][ok]).max() <= 1e-10
         assert np.abs(a["out"]["next"]["com_vel"][ok] - b["out"]["next"]["com_vel"][ok]).max() <= 1e-9
         assert b["out"]["kkt_res"][ok].max() < 1e-8
+    # the builds of the warp family run the same arithmetic
+    for b in res[1:]:
+        assert np.array_equal(res[0]["out"]["status"], b["out"]["status"])
+        assert primal_rel_err(b["primal"].reshape(-1, 3, N), res[0]["primal"].reshape(-1, 3, N)).max() <= 1e-12
+        assert np.array_equal(res[0]["active"], b["active"])
 
 
 def test_warp_rollout_equals_cta_rollout(handle):

@@ -83,6 +83,8 @@ if os.environ.get("ISMPC_DBG"):
             print("  %-12s %9.0f  %5.1f%%" % (nm, a / (n * burst), 100.0 * a / tot))
         print("  total %.0f cycles/instance; newton fallbacks %d, in-warp riccati %d, general vertical %d"
               % (tot / (n * burst), ph[29], ph[30], ph[31]))
+        print("  pair kernel (cycles per instance): warp0 midpoints %.0f | warp1 vertical+lambda+stab %.0f | barrier wait (both) %.0f | knapsack (both) %.0f"
+              % (ph[8] / (n * burst), ph[9] / (n * burst), ph[10] / (n * burst), ph[11] / (n * burst)))
         m = min(n, 8192)
         tr = (C.c_longlong * (3 * m))()
         binding.lib().ismpc_debug_read_trace(tr, 3 * m)
