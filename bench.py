@@ -10,7 +10,7 @@ randomised footstep plans, per GPU (weak scaling: every rank owns its own 1,024 
 communication, one NCCL gather of the result records after the timed region).
 
 Printed JSON keys beyond the base contract:
-  roofline      dominant kernel (formc_tick_warp_kernel, one launch per step) against the measured HBM copy bandwidth
+  roofline      dominant kernel (formc_tick_pair_kernel, one launch per step) against the measured HBM copy bandwidth
   roofline_fp64 same kernel against the measured FP64 FMA peak (the bound that actually applies)
   cpu_baseline  the reference's qpOASES path (oracle/_ref) timed on this box's host cores, same workload
   latency       p50/p90 per-tick device latency
@@ -37,9 +37,9 @@ L2_BYTES = 126 * 1024 * 1024
 # state 72 + walk 24 + inst 40 + 7 plan rows x 32 (the rows the 2N window touches) + out 128
 B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 # executed FP64 flops per instance-tick: counted by ncu on the committed capture (2 per DFMA, 1 per DMUL/DADD, thread
-# level, predicated-on), profiles/r1m_formc_tick_warp_ncu.json; the fallback is the hand count of DESIGN.md section 4
-FLOP_FORMC_FALLBACK = 17000
-NCU_JSON = os.path.join(ROOT, "profiles", "r1m_formc_tick_warp_ncu.json")
+# level, predicated-on), profiles/r1s_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
+FLOP_FORMC_FALLBACK = 27900
+NCU_JSON = os.path.join(ROOT, "profiles", "r1s_formc_tick_pair_ncu.json")
 
 
 def load_ncu():
@@ -391,7 +391,7 @@ def main():
                 "clocks": clk,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": load_traffic(), "peak_source": peak_src,
-                             "kernel": "formc_tick_warp_kernel", "kernel_ms": kernel_ms,
+                             "kernel": "formc_tick_pair_kernel", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_instance_tick": B_ALG_FORMC},
                 "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
                                   "peak": fp64_peak, "unit": "TFLOP/s",
