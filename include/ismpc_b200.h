@@ -176,8 +176,9 @@ int64_t ismpc_kernel_launches(const ismpc_handle* h);
  *   "formc_kernel":       0 = automatic (the warp-per-instance kernels), 1 = CTA / cluster per instance, 2 = warp.
  *   "formc_cluster_size": CTAs per instance of the CTA-per-instance family (1 = CTA-per-QP, 2/4/8 = thread-block-
  *                         cluster-per-QP); setting it selects that family, 0 returns to automatic.
- *   "formc_variant":      register budget of the warp tick kernel: 0 = by batch size, 1 = unlimited, 16 = 128
- *                         registers (16 resident warps per SM).
+ *   "formc_variant":      build of the warp family: 0 = by batch size, 2 = two warps per instance (latency build, the
+ *                         choice while every instance has a resident CTA), 1 = one warp per instance with unlimited
+ *                         registers, 16 = one warp per instance held to 128 registers (16 resident warps per SM).
  * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);
 

@@ -33,7 +33,7 @@ struct ismpc_handle {
     int opt_formc_cluster = 0;     // 0 = automatic
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
-    int w_res[4] = {0, 0, 0, 0};   // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel, pair kernel; 0 = not queried
+    int w_res[5] = {0, 0, 0, 0, 0};   // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel, pair tick / rollout kernels; 0 = not queried
     // form C
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
@@ -201,6 +201,7 @@ static int formc_warp_prepare(ismpc_handle* h, FormCWarpArgs& wa, const FormCArg
     int cap = h->w_res[0] > h->w_res[1] ? h->w_res[0] : h->w_res[1];
     if (h->w_res[2] > cap) cap = h->w_res[2];
     if (h->w_res[3] > cap) cap = h->w_res[3];
+    if (h->w_res[4] > cap) cap = h->w_res[4];
     if (n < cap) cap = n;
     wa.base = a;
     wa.R.none = (const double*)h->c_ric_none.p;
@@ -232,8 +233,7 @@ static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismp
     FormCWarpArgs wa;
     int rc = formc_warp_prepare(h, wa, a, n);
     if (rc) return rc;
-    const int grid = n < h->w_res[2] ? n : h->w_res[2];
-    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, grid, st);
+    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, n, h->w_res, st);
 }
 
 extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)

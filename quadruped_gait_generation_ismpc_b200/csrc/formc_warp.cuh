@@ -5,7 +5,7 @@
 //  * Lane l owns the E = ceil(N/32) consecutive horizon samples [l*E, l*E+E) of every length-N vector (E = 4 at
 //    N = 100).  Vectors live in the CTA's shared memory as [e][lane] (conflict-free, and private to the lane that
 //    owns the sample); every stage is a short ROLLED loop over e plus one warp scan over shuffles.  There is no
-//    CTA barrier anywhere, and the whole tick is ~1.5 k SASS instructions, so it stays in the instruction caches:
+//    CTA barrier anywhere, and the whole tick executes ~3 k SASS instructions out of loops that stay in the instruction caches:
 //    the first, fully unrolled register version of this kernel executed 5 k straight-line instructions per
 //    instance and spent half its time waiting for instruction fetch (profiles/r1h_*).  The CTA is one warp so that
 //    every branch is provably warp-uniform for the compiler (no WARPSYNC/ENDCOLLECTIVE pairs around the shuffles).

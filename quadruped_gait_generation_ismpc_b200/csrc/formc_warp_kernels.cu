@@ -172,6 +172,64 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
 #endif
 }
 
+// Closed loop, two warps per instance: warp 1 owns the result of a tick and hands the next state to warp 0 through
+// shared memory (Controller::update bookkeeping as in formc_rollout_warp_kernel).
+__global__ void __launch_bounds__(64, 7)
+formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,
+                          int n_ticks, double* traj, int32_t* status_out)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const FormCArgs& a = wa.base;
+    const int N = a.model.N, E = formc_warp_epl(N);
+    FormCWarpShared sm;
+    formc_warp_carve(smem_d, E, sm);
+    double* red = smem_d + (FORMC_WARP_VECS * E * 32 + 2);
+    double* hand = red + 16;
+    if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t parity = 0;
+    double* ws = wa.ws + (size_t)blockIdx.x * wa.ws_stride;
+    for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
+        ismpc_state_t st = state_io[inst];
+        ismpc_walk_t wk = walk_io[inst];
+        const ismpc_formc_inst_t in = a.inst[inst];
+        ismpc_push_t pu; pu.fs = 0; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
+        if (push) pu = push[inst];
+        int acc_status = 0;
+        const double* plan_t = a.plan + (size_t)in.plan_first_row * 4;
+#pragma unroll 1
+        for (int tick = 0; tick < n_ticks; ++tick) {
+            if (wk.footstep_counter < in.n_steps &&
+                wk.sim_time >= __ldg(plan_t + (size_t)wk.footstep_counter * 4 + 3) - 1.0) {      // Controller.cpp:297-302
+                wk.control_iter = 0; wk.mpc_iter = 0; wk.footstep_counter += 1; wk.support_foot = !wk.support_foot;
+            }
+            if (tick >= pu.ct0 && tick < pu.ct1) {              // impulsive push (quad_as_bip_bang.m:104-114)
+                st.com_vel[0] += a.model.dt * pu.ax; st.com_vel[1] += a.model.dt * pu.ay;
+            }
+            ismpc_formc_out_t r;
+            formc_tick_pair(sm, red, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r, nullptr, nullptr, parity);
+            if (threadIdx.x == 32) {
+                hand[0] = r.next.com_pos[0]; hand[1] = r.next.com_pos[1]; hand[2] = r.next.com_pos[2];
+                hand[3] = r.next.com_vel[0]; hand[4] = r.next.com_vel[1]; hand[5] = r.next.com_vel[2];
+                hand[6] = (double)r.status;
+            }
+            pair_barrier();
+            st.com_pos[0] = hand[0]; st.com_pos[1] = hand[1]; st.com_pos[2] = hand[2];
+            st.com_vel[0] = hand[3]; st.com_vel[1] = hand[4]; st.com_vel[2] = hand[5];
+            acc_status |= (int)hand[6];
+            if (traj && threadIdx.x < 6) traj[((size_t)inst * n_ticks + tick) * 6 + threadIdx.x] = hand[threadIdx.x];
+            pair_barrier();                                      // everyone has read the hand-over before it is rewritten
+            wk.control_iter += 1;                                                    // Controller.cpp:503
+            wk.mpc_iter = (int)floor(wk.control_iter * a.model.dtc / a.model.dt);    // Controller.cpp:504
+            wk.sim_time += 1.0;                                                      // Controller.cpp:310 (sim frames)
+        }
+        if (threadIdx.x == 0) {
+            state_io[inst] = st; walk_io[inst] = wk;
+            if (status_out) status_out[inst] = acc_status;
+        }
+    }
+}
+
 // Closed loop: the warp keeps its instance and advances it n_ticks times (Controller::update bookkeeping,
 // Controller.cpp:297-302 with the footstep switch enabled, :503-504).
 __global__ void __launch_bounds__(32, 1)
@@ -246,13 +304,15 @@ static void formc_warp_configure(size_t smem)
         cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(smem + FORMC_PAIR_RED * sizeof(double)));
+        cudaFuncSetAttribute(formc_rollout_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(smem + FORMC_PAIR_RED * sizeof(double)));
         configured = smem;
     }
 }
 
 // CTAs (= warps = instances in flight) the GPU keeps resident: res[0] for the tick kernel <1>, res[1] for <16>,
-// res[2] for the rollout kernel, res[3] for the pair kernel.
-void formc_warp_resident(int N, int sm_count, int res[4])
+// res[2] for the rollout kernel, res[3] for the pair tick kernel, res[4] for the pair rollout kernel.
+void formc_warp_resident(int N, int sm_count, int res[5])
 {
     const size_t smem = formc_warp_smem_bytes(N);
     formc_warp_configure(smem);
@@ -261,11 +321,12 @@ void formc_warp_resident(int N, int sm_count, int res[4])
     res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[2] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_warp_kernel, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[3] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[4] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
 }
 
 // One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
 // general vertical path).
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[4], int* grid_out, cudaStream_t st)
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
     if (g_formc_variant == 2 || (g_formc_variant == 0 && n <= res[3])) {
@@ -284,9 +345,16 @@ int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[4], int*
 }
 
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
-                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int grid,
+                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int n, const int res[5],
                               cudaStream_t st)
 {
+    if (g_formc_variant == 2 || (g_formc_variant == 0 && n <= res[4])) {
+        const int grid = n < res[4] ? n : res[4];
+        formc_rollout_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
+                                                                                           traj, status);
+        return (int)cudaGetLastError();
+    }
+    const int grid = n < res[2] ? n : res[2];
     formc_rollout_warp_kernel<<<grid, 32, formc_warp_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
                                                                                       traj, status);
     return (int)cudaGetLastError();

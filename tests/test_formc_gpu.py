@@ -212,14 +212,20 @@ def test_warp_rollout_equals_cta_rollout(handle):
         handle.set_option("formc_kernel", 1)
         a = handle.formc_rollout(state, walk, inst, plan, 120, push=push)
         handle.set_option("formc_kernel", 2)
-        b = handle.formc_rollout(state, walk, inst, plan, 120, push=push)
+        bs = []
+        for variant in (1, 2):           # one warp per instance, two warps per instance
+            handle.set_option("formc_variant", variant)
+            bs.append(handle.formc_rollout(state, walk, inst, plan, 120, push=push))
     finally:
         handle.set_option("formc_kernel", 0)
+        handle.set_option("formc_variant", 0)
     ok = (a["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
     assert ok.mean() > 0.5
-    assert np.array_equal(a["status"] & 7, b["status"] & 7)
-    assert np.abs(a["traj"][ok] - b["traj"][ok]).max() <= 1e-9
-    assert np.array_equal(a["walk"]["footstep_counter"], b["walk"]["footstep_counter"])
+    for b in bs:
+        assert np.array_equal(a["status"] & 7, b["status"] & 7)
+        assert np.abs(a["traj"][ok] - b["traj"][ok]).max() <= 1e-9
+        assert np.array_equal(a["walk"]["footstep_counter"], b["walk"]["footstep_counter"])
+    assert np.abs(bs[0]["traj"][ok] - bs[1]["traj"][ok]).max() <= 1e-11
 
 
 def test_uneven_ground(handle):
