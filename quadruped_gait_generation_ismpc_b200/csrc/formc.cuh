@@ -34,6 +34,20 @@ struct FormCTables {      // device pointers, N x N row-major each (built once p
     int gS, gF;
 };
 
+// Flight-phase samples [c_lo, c_lo+ne) of the horizon at mpcIter m (MPCSolver.cpp:223-243, indices as written there).
+// The reference fills Aeq_z inside `for (i = 0; i < N; i++)`: with a horizon shorter than S + F only the rows with
+// i < N get an entry, the others stay all-zero rows (0 = 0).
+__host__ __device__ inline void formc_flight_range(int N, int S, int F, int mpc_iter, int& c_lo, int& ne)
+{
+    if (mpc_iter < S) {                                      // Aeq_z(i-S, i-mpcIter), i in [S, min(S+F, N))
+        const int i_hi = S + F < N ? S + F : N;
+        ne = i_hi - S; c_lo = S - mpc_iter;
+    } else { ne = S + F - mpc_iter; c_lo = 0; }              // Aeq_z(i,i), i < min(S+F-mpcIter, N)
+    if (c_lo < 0) { ne += c_lo; c_lo = 0; }
+    if (c_lo + ne > N) ne = N - c_lo;
+    if (ne < 0) ne = 0;
+}
+
 struct FormCShared {      // per-CTA shared memory carve-up (all pointers into dynamic smem)
     double *midx, *midy, *midz;            // [2N], [2N], [N]
     double *Fz, *f, *rv, *zdir, *scr;      // [N] each
@@ -379,11 +393,7 @@ __device__ inline void formc_tick(const FormCShared& sm, const ismpc_formc_model
     // equalities f_k = 0 on the flight-phase columns (:223-243), active only when running (:262-269)
     int ne = 0, c_lo = 0;
     if (wk.footstep_counter > 1) {
-        if (wk.mpc_iter < S) { ne = F; c_lo = S - wk.mpc_iter; }     // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
-        else { ne = S + F - wk.mpc_iter; c_lo = 0; }                 // Aeq_z(i,i), i < S+F-mpcIter
-        if (c_lo < 0) { ne += c_lo; c_lo = 0; }
-        if (c_lo + ne > N) ne = N - c_lo;
-        if (ne < 0) ne = 0;
+        formc_flight_range(N, S, F, wk.mpc_iter, c_lo, ne);
     }
     // Prepared gait: the projector table of this mpcIter folds the equalities into the mat-vec.
     const bool use_P = T.P != nullptr && ne > 0 && S == T.gS && F == T.gF && wk.mpc_iter >= 0 && wk.mpc_iter < S + F;

@@ -103,10 +103,7 @@ __global__ void formc_build_P(int N, int S, int F, const double* __restrict__ Hi
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = blockIdx.x;
     int ne, c_lo;
-    if (m < S) { ne = F; c_lo = S - m; } else { ne = S + F - m; c_lo = 0; }
-    if (c_lo < 0) { ne += c_lo; c_lo = 0; }
-    if (c_lo + ne > N) ne = N - c_lo;
-    if (ne < 0) ne = 0;
+    formc_flight_range(N, S, F, m, c_lo, ne);
     double* Pm = P + (size_t)m * N * N;
     const int tid = threadIdx.x, nt = blockDim.x;
     if (ne == 0) {

@@ -62,7 +62,9 @@ __device__ __forceinline__ void formc_knapsack_axis(const FormCWarpShared& sm, c
 #pragma unroll 1
             for (int e = 0; e < E; ++e) {
                 const double ak = fabs(sm.av[e * 32 + lane]);
-                if (S2 > 1e-30 * aa) cb = fmax(cb, (ra - rho * P1) * fast_rcp(S2));
+                // (S2 is a running difference: rounding residue after the last non-zero row, and the padding beyond the
+                //  horizon, are not candidates)
+                if (lane * E + e < N && S2 > 1e-12 * aa) cb = fmax(cb, (ra - rho * P1) * fast_rcp(S2));
                 P1 += ak; S2 -= ak * ak;
             }
 #pragma unroll 1

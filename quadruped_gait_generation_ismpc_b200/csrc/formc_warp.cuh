@@ -47,16 +47,6 @@ struct FormCRiccati {
     int gS, gF;
 };
 
-// Flight-phase samples [c_lo, c_lo+ne) of the horizon at mpcIter m (MPCSolver.cpp:223-243, indices as written there).
-__host__ __device__ inline void formc_flight_range(int N, int S, int F, int mpc_iter, int& c_lo, int& ne)
-{
-    if (mpc_iter < S) { ne = F; c_lo = S - mpc_iter; }       // Aeq_z(i-S, i-mpcIter), i in [S,S+F)
-    else { ne = S + F - mpc_iter; c_lo = 0; }                // Aeq_z(i,i), i < S+F-mpcIter
-    if (c_lo < 0) { ne += c_lo; c_lo = 0; }
-    if (c_lo + ne > N) ne = N - c_lo;
-    if (ne < 0) ne = 0;
-}
-
 // One backward step of the Riccati recursion for sample k, given P = P_{k+1} (symmetric 2x2).
 // Table entry: free sample  -> (K0, K1, 1/R, 0)      v_k = -K x_k - (B's_{k+1})/R
 //              fixed sample -> (e0, e1, 0, -g)       v_k = -g,  s_k = q_k + A's_{k+1} + e,  e = -g A'P_{k+1}B
@@ -677,7 +667,9 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
 #pragma unroll 1
                 for (int e = 0; e < E; ++e) {
                     const double ak = fabs(sm.av[e * 32 + lane]);
-                    if (S2 > 1e-30 * aa) {
+                    // (S2 is a running difference: what is left once the last non-zero row is taken out is rounding
+                    //  residue, not a candidate; neither is the padding beyond the horizon)
+                    if (lane * E + e < N && S2 > 1e-12 * aa) {
                         const double ri = fast_rcp(S2);
                         cx = fmax(cx, (rax - rho * P1) * ri); cy = fmax(cy, (ray - rho * P1) * ri);
                     }

@@ -29,7 +29,9 @@ def _compare(handle, model, state, walk, inst, plan, nthreads=8):
     assert (np.abs(g["out"]["fz0"][ok] - o["out"]["fz0"][ok]) / fscale).max() <= PRIMAL_TOL
     mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
     assert mism.sum() == 0, "active set differs on %d rows (%d weak rows ignored)" % (mism.sum(), weak.sum())
-    assert g["out"]["kkt_res"][ok].max() < 1e-8
+    # the self-check is an absolute residual of a'u = b, and |a| grows like exp(eta dt N): 1e-8 up to N = 400
+    kkt_tol = 1e-8 * max(1.0, float(np.exp(np.sqrt(9.81 / 0.69) * 0.01 * (N - 400))))
+    assert g["out"]["kkt_res"][ok].max() < kkt_tol
     return g, o, ok
 
 
@@ -279,3 +281,13 @@ def test_resident_plan_equals_plan_per_call(handle):
         handle.formc_set_plan(None)
     with pytest.raises(Exception):
         handle.formc_solve_batch(state, walk, inst, None)
+
+
+@pytest.mark.parametrize("N", [37, 101, 512])
+def test_ragged_and_maximum_horizons(handle, N):
+    """Horizons that do not fill the lanes evenly (37 = 32 + 5 with two samples per lane, 101 = 25 full lanes + 1) and the
+    largest horizon the ABI accepts (ISMPC_MAX_N = 512, sixteen samples per lane), against the oracle."""
+    n = 24 if N < 512 else 6
+    steps = (2 * N + 900) // 45 + 3
+    state, walk, inst, plan = synth.formc_batch(n, seed=7 * N, N=N, n_steps=steps)
+    _compare(handle, abi.formc_model(N=N), state, walk, inst, plan)
