@@ -291,3 +291,64 @@ def test_ragged_and_maximum_horizons(handle, N):
     steps = (2 * N + 900) // 45 + 3
     state, walk, inst, plan = synth.formc_batch(n, seed=7 * N, N=N, n_steps=steps)
     _compare(handle, abi.formc_model(N=N), state, walk, inst, plan)
+
+
+def test_other_step_timing_and_raised_ground(handle):
+    """A gait with another period (S=25, F_ds=8: 33-tick steps) that no table was prepared for (the recursion runs in the
+    kernel), and footsteps on a raised but level floor (z = 0.05: flat reference with a non-zero mid_z)."""
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.formc_batch(96, seed=515, S=25, F_ds=8, n_steps=50)
+    plan[:, 2] = 0.05
+    state["com_pos"][:, 2] += 0.05
+    handle.formc_set_model(model)
+    handle.formc_prepare_gait(35, 10)          # not the timing of this batch
+    _compare_prepared(handle, model, state, walk, inst, plan)
+    handle.formc_prepare_gait(25, 8)           # now with tables: same answers
+    _compare_prepared(handle, model, state, walk, inst, plan)
+
+
+def test_window_reaching_the_last_step(handle):
+    """Windows that run into the last step of the plan, whose midpoint rows stay zero (MPCSolver.cpp:167-180): the GPU
+    and the oracle must agree wherever the oracle solves, and fail together elsewhere."""
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.formc_batch(64, seed=99)
+    per = 45
+    for i in range(len(state)):
+        k0 = int(inst["n_steps"][i]) * per - 200 - (i % 40)          # k0 + 2N within 0..39 ticks of the end of the sequence
+        walk["sim_time"][i] = k0; walk["mpc_iter"][i] = k0 % per; walk["control_iter"][i] = k0 % per
+        walk["footstep_counter"][i] = 2 + k0 // per
+        row = plan[inst["plan_first_row"][i] + k0 // per]
+        state["com_pos"][i][:2] = row[:2]; state["com_vel"][i][:2] = 0.0
+    handle.formc_set_model(model)
+    g = handle.formc_solve_batch(state, walk, inst, plan)
+    o = O.formc_batch(model, state, walk, inst, plan, nthreads=8)
+    assert (g["out"]["status"] & abi.ST_WINDOW == 0).all() and (o["out"]["status"] & abi.ST_WINDOW == 0).all()
+    ok = (o["ret"] == 0).all(axis=1)
+    gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
+    assert not gfail[ok].any()
+    assert ok.sum() >= 8, "test is vacuous: the oracle solved %d instances" % ok.sum()
+    err = primal_rel_err(g["primal"][ok].reshape(-1, 3, 100), o["primal"][ok].reshape(-1, 3, 100))
+    assert err.max() <= PRIMAL_TOL
+    mism, _ = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
+    assert mism.sum() == 0
+
+
+def test_batch_beyond_residency_grid_stride(handle):
+    """3,000 instances: more than the GPU keeps resident, so the one-warp kernel walks the batch with a grid stride and
+    reuses its shared memory; same records as the two-warp kernel run on 1,000-instance slices."""
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    handle.formc_prepare_gait(35, 10)
+    state, walk, inst, plan = synth.formc_batch(3000, seed=2024)
+    big = handle.formc_solve_batch(state, walk, inst, plan, want_primal=False, want_active=False)
+    try:
+        handle.set_option("formc_variant", 2)
+        for a in range(0, 3000, 1000):
+            sl = slice(a, a + 1000)
+            part = handle.formc_solve_batch(state[sl], walk[sl], inst[sl], plan, want_primal=False, want_active=False)
+            assert np.array_equal(part["out"]["status"], big["out"]["status"][sl])
+            for name in ("com_pos", "com_vel"):
+                assert np.abs(part["out"]["next"][name] - big["out"]["next"][name][sl]).max() <= 1e-12
+            assert np.abs(part["out"]["zmp_in"] - big["out"]["zmp_in"][sl]).max() <= 1e-12
+    finally:
+        handle.set_option("formc_variant", 0)
