@@ -59,6 +59,16 @@ __device__ __forceinline__ int warp_sum_int(int v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ISMPC_FULL_MASK, v, o);
     return v;
 }
+// max over the warp of NON-NEGATIVE doubles in two integer reductions (redux.sync): for v >= 0 the bit patterns order
+// like the values, so the maximum is the largest high word and, among its holders, the largest low word.
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    v = fabs(v);                                          // (-0.0 would compare as huge)
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(ISMPC_FULL_MASK, hi);
+    const unsigned ml = __reduce_max_sync(ISMPC_FULL_MASK, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
 // argmin over the warp: returns the (value,index) with the smallest value; ties -> smallest index.
 __device__ __forceinline__ void warp_argmin(double& v, int& idx)
 {

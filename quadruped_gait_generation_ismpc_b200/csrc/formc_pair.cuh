@@ -37,11 +37,11 @@ __device__ __forceinline__ void formc_knapsack_axis(const FormCWarpShared& sm, c
         am += a * mid[x];
         t1 += ai; t2 += ai * ai; mx = fmax(mx, ai);
     }
-    double aa = t2, amax = mx;
+    double aa = t2;
+    const double amax = warp_max_nonneg(mx);
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
         am += __shfl_xor_sync(ISMPC_FULL_MASK, am, o); aa += __shfl_xor_sync(ISMPC_FULL_MASK, aa, o);
-        amax = fmax(amax, __shfl_xor_sync(ISMPC_FULL_MASK, amax, o));
     }
     const double rr = bq - am;
     const double sg = rr >= 0.0 ? 1.0 : -1.0, ra = fabs(rr);
@@ -67,9 +67,7 @@ __device__ __forceinline__ void formc_knapsack_axis(const FormCWarpShared& sm, c
                 if (lane * E + e < N && S2 > 1e-12 * aa) cb = fmax(cb, (ra - rho * P1) * fast_rcp(S2));
                 P1 += ak; S2 -= ak * ak;
             }
-#pragma unroll 1
-            for (int o = 16; o > 0; o >>= 1) cb = fmax(cb, __shfl_xor_sync(ISMPC_FULL_MASK, cb, o));
-            tq = fmax(tq, cb);
+            tq = fmax(tq, warp_max_nonneg(cb));
             int prev = -1;
 #pragma unroll 1
             for (int it = 0; it < N + 3; ++it) {
@@ -85,8 +83,8 @@ __device__ __forceinline__ void formc_knapsack_axis(const FormCWarpShared& sm, c
 #pragma unroll 1
                 for (int o = 16; o > 0; o >>= 1) {
                     q1 += __shfl_xor_sync(ISMPC_FULL_MASK, q1, o); q2 += __shfl_xor_sync(ISMPC_FULL_MASK, q2, o);
-                    cnt += __shfl_xor_sync(ISMPC_FULL_MASK, cnt, o);
                 }
+                cnt = __reduce_add_sync(ISMPC_FULL_MASK, cnt);
                 bool done = cnt == prev;                                              // same set as the one tq was solved for
                 if (!done) {
                     prev = cnt;
@@ -121,9 +119,8 @@ __device__ __forceinline__ void formc_knapsack_axis(const FormCWarpShared& sm, c
         }
     }
 #pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
-        au += __shfl_xor_sync(ISMPC_FULL_MASK, au, o); ns += __shfl_xor_sync(ISMPC_FULL_MASK, ns, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) au += __shfl_xor_sync(ISMPC_FULL_MASK, au, o);
+    ns = __reduce_add_sync(ISMPC_FULL_MASK, ns);
     u0_out = __shfl_sync(ISMPC_FULL_MASK, u0, 0);
     nsat_out = ns; fail_out = fail; resid_out = fabs(au - bq);
 }
@@ -381,13 +378,13 @@ __device__ __forceinline__ void formc_tick_pair(const FormCWarpShared& sm, doubl
             const double ux0 = red[8], uy0 = u0;
             if ((int)red[10]) status |= ISMPC_ST_X_FAIL;
             if (fail) status |= ISMPC_ST_Y_FAIL;
-            kkt = fmax(warp_max(kkt), fmax(resid, red[11]));
+            kkt = fmax(warp_max_nonneg(kkt), fmax(resid, red[11]));
             r.zmp_in[0] = ux0; r.zmp_in[1] = uy0;
             r.iters[1] = (int)red[9]; r.iters[2] = ns;
         }
     } else {
         status |= ISMPC_ST_XY_SKIPPED;
-        kkt = warp_max(kkt);
+        kkt = warp_max_nonneg(kkt);
         if (prim) for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) prim[N + i] = 0.0;
         if (act) for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) act[N + i] = 0;
         pair_barrier();

@@ -634,13 +634,14 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         // and ends when the set repeats: one pass when the prefix guess was exact, a few otherwise (the slowest QP of a
         // batch sets the tick time: Newton from the unsaturated start needs up to a dozen passes).
         const double rho = running ? in.box_w / 2 : in.box_w_init / 2;                // (:328-338)
-        double aa = t2, amax = mx;
+        double aa = t2;
+        const double amax = warp_max_nonneg(mx);
 #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) {                                            // six reductions in one butterfly
+        for (int o = 16; o > 0; o >>= 1) {                                            // five sums in one butterfly
             const double s0 = __shfl_xor_sync(ISMPC_FULL_MASK, tx, o), s1 = __shfl_xor_sync(ISMPC_FULL_MASK, ty, o);
             const double s2 = __shfl_xor_sync(ISMPC_FULL_MASK, amx, o), s3 = __shfl_xor_sync(ISMPC_FULL_MASK, amy, o);
-            const double s4 = __shfl_xor_sync(ISMPC_FULL_MASK, aa, o), s5 = __shfl_xor_sync(ISMPC_FULL_MASK, amax, o);
-            tx += s0; ty += s1; amx += s2; amy += s3; aa += s4; amax = fmax(amax, s5);
+            const double s4 = __shfl_xor_sync(ISMPC_FULL_MASK, aa, o);
+            tx += s0; ty += s1; amx += s2; amy += s3; aa += s4;
         }
         const double bx = -(ps0 * st.com_pos[0] + ps1 * st.com_vel[0]) + eta * dt * tx;   // (:381-384)
         const double by = -(ps0 * st.com_pos[1] + ps1 * st.com_vel[1]) + eta * dt * ty;
@@ -675,12 +676,9 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                     }
                     P1 += ak; S2 -= ak * ak;
                 }
-#pragma unroll 1
-                for (int o = 16; o > 0; o >>= 1) {
-                    cx = fmax(cx, __shfl_xor_sync(ISMPC_FULL_MASK, cx, o)); cy = fmax(cy, __shfl_xor_sync(ISMPC_FULL_MASK, cy, o));
-                }
-                if (satx) tqx = fmax(tqx, cx);
-                if (saty) tqy = fmax(tqy, cy);
+                const double mcx = warp_max_nonneg(cx), mcy = warp_max_nonneg(cy);
+                if (satx) tqx = fmax(tqx, mcx);
+                if (saty) tqy = fmax(tqy, mcy);
                 int prevx = satx ? -1 : -2, prevy = saty ? -1 : -2;                   // -2: axis settled
 #pragma unroll 1
                 for (int it = 0; it < N + 3; ++it) {
@@ -698,8 +696,8 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
                     for (int o = 16; o > 0; o >>= 1) {
                         q1x += __shfl_xor_sync(ISMPC_FULL_MASK, q1x, o); q2x += __shfl_xor_sync(ISMPC_FULL_MASK, q2x, o);
                         q1y += __shfl_xor_sync(ISMPC_FULL_MASK, q1y, o); q2y += __shfl_xor_sync(ISMPC_FULL_MASK, q2y, o);
-                        cnt += __shfl_xor_sync(ISMPC_FULL_MASK, cnt, o);
                     }
+                    cnt = __reduce_add_sync(ISMPC_FULL_MASK, cnt);
                     const int nx = cnt & 1023, ny = cnt >> 10;
                     if (prevx != -2) {
                         if (nx == prevx) prevx = -2;                                  // same set as the one tqx was solved for
@@ -761,9 +759,9 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
 #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
             aux += __shfl_xor_sync(ISMPC_FULL_MASK, aux, o); auy += __shfl_xor_sync(ISMPC_FULL_MASK, auy, o);
-            nsx += __shfl_xor_sync(ISMPC_FULL_MASK, nsx, o); nsy += __shfl_xor_sync(ISMPC_FULL_MASK, nsy, o);
-            kkt = fmax(kkt, __shfl_xor_sync(ISMPC_FULL_MASK, kkt, o));
         }
+        nsx = __reduce_add_sync(ISMPC_FULL_MASK, nsx); nsy = __reduce_add_sync(ISMPC_FULL_MASK, nsy);
+        kkt = warp_max_nonneg(kkt);
         ux0 = __shfl_sync(ISMPC_FULL_MASK, ux0, 0); uy0 = __shfl_sync(ISMPC_FULL_MASK, uy0, 0);
         it_x = nsx; it_y = nsy;
         if (stx) status |= ISMPC_ST_X_FAIL;
@@ -772,7 +770,7 @@ __device__ __forceinline__ void formc_tick_warp(const FormCWarpShared& sm, const
         ISMPC_WPHASE(5);
     } else {
         status |= ISMPC_ST_XY_SKIPPED;
-        kkt = warp_max(kkt);
+        kkt = warp_max_nonneg(kkt);
         if (prim) for (int i = lane; i < 2 * N; i += 32) prim[N + i] = 0.0;
         if (act) for (int i = lane; i < 2 * N; i += 32) act[N + i] = 0;
     }

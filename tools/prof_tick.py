@@ -98,6 +98,14 @@ if os.environ.get("ISMPC_DBG"):
         sm_ids = tr[:, 2]
         per_sm = np.bincount(sm_ids.astype(int))
         print("  CTAs per SM: min %d max %d; slowest 5 durations at SMs %s" % (per_sm[per_sm > 0].min(), per_sm.max(), sm_ids[np.argsort(du)[-5:]]))
+        o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMC_OUT)
+        order = np.argsort(du)
+        print("  slowest 8 CTAs: duration ns / saturated rows x,y / status:", [(int(du[i]), o["iters"][i][1:].tolist(), int(o["status"][i])) for i in order[-8:]])
+        print("  median 8 CTAs:", [(int(du[i]), o["iters"][i][1:].tolist(), int(o["status"][i])) for i in order[m // 2 - 4:m // 2 + 4]])
+        sat = (o["iters"][:m, 1] + o["iters"][:m, 2]) > 0
+        skipped = (o["status"][:m] & abi.ST_XY_SKIPPED) != 0
+        print("  mean duration: unsaturated %.0f ns (%d), saturated %.0f ns (%d), horizontal skipped %.0f ns (%d)"
+              % (du[~sat & ~skipped].mean(), (~sat & ~skipped).sum(), du[sat].mean(), sat.sum(), du[skipped].mean() if skipped.any() else 0, skipped.sum()))
         sys.exit(0)
     nz = [(i, x) for i, x in enumerate(v) if x]
     print("phase clocks (CTA 0): stamp -> cycles since the previous non-zero stamp:",
