@@ -458,7 +458,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
         // Rows whose multiplier has the wrong sign leave.  From iteration PDAS_DAMP_AFTER on, only those at an end of
         // a run of equally-signed active rows leave (if there is one): an over-long run can flip the sign of nu,
         // which would release the whole run at once and make the iteration cycle.
-        int changed = 0, wrong_end = 0;
+        int changed = 0, wrong_end = 0, viol = 0, wrong_in = 0;
         for (int i = r0; i < r1; ++i) {
             const int s0 = st[i];
             int s1 = 0;
@@ -466,6 +466,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
                 const double lo = pb.lo_[i], hi = pb.hi_[i], r = sm.rv[i];
                 if (lo - r > 1e-10 * (1.0 + fabs(lo))) s1 = -1;
                 else if (r - hi > 1e-10 * (1.0 + fabs(hi))) s1 = +1;
+                viol |= s1 != 0;
             } else {
                 const double y = cseg[i] - (i + 1 < C ? cseg[i + 1] : 0.0);     // dt * multiplier
                 if (s0 < 0 ? y > 0.0 : y < 0.0) s1 = s0;
@@ -473,18 +474,10 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
                     const int sl = i > 0 ? st[i - 1] : 0, sr = i + 1 < C ? st[i + 1] : 0;
                     s1 = (sl != s0 || sr != s0) ? 0 : 2;          // 2: wrong sign, interior of a run
                     wrong_end |= s1 == 0;
+                    wrong_in |= s1 == 2;
                 }
             }
             nxt[i] = s1;                                      // staged: cseg[i+1] of a neighbour lane may still be read
-        }
-        {
-            const bool damp = it >= PDAS_DAMP_AFTER && __any_sync(ISMPC_FULL_MASK, wrong_end);
-            for (int i = r0; i < r1; ++i) {
-                int s1 = nxt[i];
-                if (s1 == 2) s1 = damp ? st[i] : 0;
-                changed |= s1 != st[i];
-                nxt[i] = s1;
-            }
         }
         if (lane < F) {
             const int f = lane, s0 = st[C + f];
@@ -497,11 +490,88 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
             if (s0 == 0) {
                 if (lo - r > 1e-10 * (1.0 + fabs(lo))) s1 = -1;
                 else if (r - hi > 1e-10 * (1.0 + fabs(hi))) s1 = +1;
+                viol |= s1 != 0;
             } else if (s0 < 0 ? kap > 0.0 : kap < 0.0) s1 = s0;
             changed |= s1 != s0;
             sm.rv[C + f] = r;
             sm.x[C + f] = xme + shift;
             st[C + f] = (signed char)s1;
+        }
+        __syncwarp();
+        const unsigned end_mask = __ballot_sync(ISMPC_FULL_MASK, wrong_end);
+        // ---- peeling step ----
+        // When nothing is violated and the only rows with a wrong-sign multiplier are ends of runs, the plain rule peels
+        // the runs one row per iteration (the next end row turns wrong once its neighbour is gone: a third of the
+        // cold mid-gait QPs spent 20-45 iterations that way).  With nu and the footsteps frozen, the multiplier a run
+        // would have at its end if it stopped at row e is closed form (segment constant of the new free stretch against
+        // the one-row segment before e), so the run is cut back in one step to the first row whose multiplier keeps
+        // its sign.  The next solve corrects nu; overshoot shows up as violated rows and is re-added wholesale.
+        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, viol | wrong_in)) {
+            auto tgt = [&](int k) -> double { return beta(k) + mx(k); };
+            unsigned todo = end_mask;
+            while (todo) {
+                const int L = __ffs(todo) - 1; todo &= todo - 1;
+                int a0, a1; lane_chunk(C, L, a0, a1);
+                for (int i = a0; i < a1; ++i) {
+                    const int sg = st[i];
+                    if (sg == 0 || nxt[i] != 0) continue;             // not a wrong end row (3 = cut by an earlier end)
+                    const bool right = i + 1 >= C || st[i + 1] != sg, left = i == 0 || st[i - 1] != sg;
+                    if (right) {
+                        int lb = -1, kn = C;                           // last row before i outside the run, next active row after i
+                        for (int k = r0; k < r1; ++k) {
+                            if (k < i && st[k] != sg) lb = k;
+                            if (k > i && st[k] != 0 && kn == C) kn = k;
+                        }
+                        lb = __reduce_max_sync(ISMPC_FULL_MASK, lb); kn = __reduce_min_sync(ISMPC_FULL_MASK, kn);
+                        const int s = lb + 1;
+                        const double tkn = kn < C ? tgt(kn) : 0.0, PAkn = kn < C ? pb.PA[kn] : 0.0;
+                        int best = -1;
+                        for (int e = r0 > s ? r0 : s; e < r1 && e <= i; ++e) {
+                            const double te = tgt(e);
+                            const double c_new = kn < C ? (qz_dt * (tkn - te) - nu * (PAkn - pb.PA[e])) * rg[kn - e] : 0.0;
+                            const double c_prev = e > s ? qz_dt * (te - tgt(e - 1)) - nu * pb.a[e] : cseg[s];
+                            const double y = c_prev - c_new;
+                            if (sg < 0 ? y > 0.0 : y < 0.0) best = e;
+                        }
+                        best = __reduce_max_sync(ISMPC_FULL_MASK, best);
+                        const int from = best >= s ? best + 1 : s;
+                        for (int k = r0 > from ? r0 : from; k < r1 && k <= i; ++k) nxt[k] = 3;
+                    }
+                    if (left) {
+                        int ub = C, kp = -1;                           // first row after i outside the run, last active row before i
+                        for (int k = r0; k < r1; ++k) {
+                            if (k > i && st[k] != sg && ub == C) ub = k;
+                            if (k < i && st[k] != 0) kp = k;
+                        }
+                        ub = __reduce_min_sync(ISMPC_FULL_MASK, ub); kp = __reduce_max_sync(ISMPC_FULL_MASK, kp);
+                        const int e = ub - 1;
+                        const double tkp = kp >= 0 ? tgt(kp) : 0.0, PAkp = kp >= 0 ? pb.PA[kp] : 0.0;
+                        const double c_after = e + 1 < C ? cseg[e + 1] : 0.0;
+                        int best = C;
+                        for (int s2 = r1 - 1 < e ? r1 - 1 : e; s2 >= r0 && s2 >= i; --s2) {
+                            const double ts = tgt(s2);
+                            const double c_new = (qz_dt * (ts - tkp) - nu * (pb.PA[s2] - PAkp)) * rg[s2 - kp];
+                            const double c_next = s2 < e ? qz_dt * (tgt(s2 + 1) - ts) - nu * pb.a[s2 + 1] : c_after;
+                            const double y = c_new - c_next;
+                            if (sg < 0 ? y > 0.0 : y < 0.0) best = s2;
+                        }
+                        best = __reduce_min_sync(ISMPC_FULL_MASK, best);
+                        const int to = best <= e ? best - 1 : e;
+                        for (int k = r0 > i ? r0 : i; k < r1 && k <= to; ++k) nxt[k] = 3;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        {
+            const bool damp = it >= PDAS_DAMP_AFTER && end_mask != 0u;
+            for (int i = r0; i < r1; ++i) {
+                int s1 = nxt[i];
+                if (s1 == 2) s1 = damp ? st[i] : 0;
+                if (s1 == 3) s1 = 0;
+                changed |= s1 != st[i];
+                nxt[i] = s1;
+            }
         }
         __syncwarp();
         for (int i = r0; i < r1; ++i) st[i] = (signed char)nxt[i];
