@@ -212,7 +212,10 @@ int ismpc_formc_set_plan(ismpc_handle* h, const double* plan_xyzt, int plan_rows
  * primal_opt (nullable): n x 3N doubles  [f(N) | u_x(N) | u_y(N)] per instance.
  * active_opt (nullable): n x 3N int8    [S_bar_z rows | x box rows | y box rows], -1 lower / 0 / +1 upper,
  *                        the convention of QProblem::getWorkingSetConstraints (qpOASES/QProblem.cpp:809-829);
- *                        equality rows are always active and not reported. */
+ *                        equality rows are always active and not reported.
+ * Host-memory modes: if the three input arrays lie back to back in one allocation (walk == state + n records,
+ * inst == walk + n records, e.g. one pinned staging buffer per tick) they are moved in ONE host->device copy instead
+ * of three; results are identical either way. */
 int ismpc_formc_solve_batch(ismpc_handle* h, int n,
                             const ismpc_state_t* state, const ismpc_walk_t* walk,
                             const ismpc_formc_inst_t* inst,

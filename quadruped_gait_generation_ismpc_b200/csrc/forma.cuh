@@ -293,7 +293,9 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
 #pragma unroll
     for (int f = 0; f < FT; ++f) pl[f] = f < F ? planf[f] : 0.0;
     int it = 0, rc = 1;
+    DasTimer tmr;
     for (; it < maxit; ++it) {
+        tmr.start();
         // ---- predecessor / successor active rows of this lane's chunk (ballot + one shuffle each) ----
         int la = -1, fa = C, nk = 0;
         for (int i = r0; i < r1; ++i) if (st[i]) { la = i; if (fa == C) fa = i; }
@@ -338,6 +340,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
                 kp = i; bp = bk; PAp = PAk;
             }
         }
+        tmr.lap(13);
         double nu, xf[FT], kap = 0.0;
         bool fast = false;
         if constexpr (FT <= 3) fast = nk == 0;
@@ -429,6 +432,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
             for (int f = 0; f < FT; ++f) s += ((p == f + 1 ? w : 0.0) + (p == f ? 1.0 - w : 0.0)) * xf[f];
             return s;
         };
+        tmr.lap(14);
         // ---- pass B: successor rows, segment constants, zd, row values ----
         { int kn = kn0; for (int i = r1 - 1; i >= r0; --i) { if (st[i]) kn = i; nxt[i] = kn; } }
         {
@@ -454,6 +458,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
             }
         }
         __syncwarp();
+        tmr.lap(15);
         // ---- re-guess the working set ----
         // Rows whose multiplier has the wrong sign leave.  From iteration PDAS_DAMP_AFTER on, only those at an end of
         // a run of equally-signed active rows leave (if there is one): an over-long run can flip the sign of nu,
@@ -577,6 +582,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
         for (int i = r0; i < r1; ++i) st[i] = (signed char)nxt[i];
         changed = __any_sync(ISMPC_FULL_MASK, changed);
         __syncwarp();
+        tmr.lap(16);
         if (!changed) { rc = 0; ++it; break; }
     }
     *iters_out = it;
@@ -600,6 +606,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     const double w_box = axis == 0 ? in.wx : in.wy;
     const int ds = in.ds, n_timing = in.n_timing, n_fs = in.n_fs;
     const int step = ft[1] - ft[0];
+    DasTimer tmt; tmt.start();
     // ---- stability row coefficients (bang.m:200-207) ----
     const double lam = exp(-eta * dt);
     const double k1 = (1.0 / eta) * (1.0 - lam) / (1.0 - pow(lam, (double)C));
@@ -653,6 +660,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     if (!warm) for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
     __syncwarp();
     FormAProb pb{C, F, dt, 1.0 / mdl.q_zdot, 1.0 / mdl.q_foot, saa, sm.a, sm.PA, sm.mw, sm.lo, sm.hi, sm.mp, sm.scr};
+    tmt.lap(10);
     int status = 0, iters = 0;
     bool solved = false;
     double eqv = 0.0, viol = 0.0;
@@ -674,6 +682,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
             rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
             iters += it2;
         }
+        tmt.lap(11);
         if (rc == 0) {
             for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
             eqv = warp_sum(eqv);
@@ -717,6 +726,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     }
     *iters_out = iters;
     *kkt_out = fmax(fabs(eqv - beq), fmax(viol, 0.0));
+    tmt.lap(12);
     return status;
 }
 

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
         int iters; double kkt;
         int status = forma_tick_axis<FT>(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
                                          in.cl_first_ramp, plan, ft, axis, 0, a.use_pdas, rg, &iters, &kkt);
+        DasTimer tme; tme.start();
         const double eta = sqrt(a.model.g_eta / in.height);
         const double zd0 = sm.x[0];
         forma_integrate(eta, a.model.dt, s3, zd0);
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
             for (int f = lane; f < F; f += 32) act[2 * C + axis * F + f] = sm.das.state[C + f];
         }
         __syncwarp();
+        tme.lap(17);
     }
 }
 
@@ -180,7 +182,12 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, For
 {
     const int C = m.C, F = m.F, q = C + F + 1;
     const size_t lim = 227 * 1024;
-    int R = env_int("ISMPC_FORMA_R", 32);
+    // Rows of the dual active set's inverse factor kept in shared memory: the fallback is rare (0 of 16,384 cold mid-gait
+    // instances), so R is only what the structured solver needs as scratch ((1+2F)(2+2F) doubles), at least 12 --
+    // a smaller footprint keeps every (instance, axis) item of a 1,024-instance tick resident (R = 32: 153 us, 12: 128 us)
+    int R_dflt = 12;
+    while (R_dflt < q && (size_t)tri(R_dflt, 0) < (size_t)(1 + 2 * F) * (2 + 2 * F)) ++R_dflt;
+    int R = env_int("ISMPC_FORMA_R", R_dflt);
     if (R > q) R = q;
     if (R < 1) R = 1;
     int wpc = env_int("ISMPC_FORMA_WPC", 4);

@@ -60,6 +60,8 @@ else:
     d = [to_dev(x) for x in (inst, ft, plan)]
     out = torch.zeros(n * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
     for r in range(reps):
+        if os.environ.get("ISMPC_DBG") and r == reps - 1:
+            torch.cuda.synchronize(); binding.lib().ismpc_debug_reset_phases()
         e0.record()
         h.forma_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), len(ft), d[2].data_ptr(), plan.shape[0],
                                 out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
@@ -110,7 +112,8 @@ if os.environ.get("ISMPC_DBG"):
     nz = [(i, x) for i, x in enumerate(v) if x]
     print("phase clocks (CTA 0): stamp -> cycles since the previous non-zero stamp:",
           [(nz[k][0], nz[k][1] - nz[k - 1][1]) for k in range(1, len(nz))], "total", nz[-1][1] - nz[0][1] if nz else 0)
-    names = ["eval", "viol_scan", "schur_col", "apply_J", "apply_Jt", "ratio", "step_dir", "x_mu_update", "append", "drop"]
+    names = ["eval", "viol_scan", "schur_col", "apply_J", "apply_Jt", "ratio", "step_dir", "x_mu_update", "append", "drop",
+             "A:build", "A:pdas_total", "A:selfcheck", "A:it_passA", "A:it_solve", "A:it_passB", "A:it_reguess", "A:epilogue"]
     acc = list(ph)[32:32 + len(names)]
     tot = float(sum(acc)) or 1.0
     print("das sections (cycles summed over all warps and launches):")
