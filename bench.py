@@ -39,6 +39,7 @@ B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 # executed FP64 flops per instance-tick: counted by ncu on the committed capture (2 per DFMA, 1 per DMUL/DADD, thread
 # level, predicated-on), profiles/r1x_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
 FLOP_FORMC_FALLBACK = 28000
+F_REF_FORMC = 2 * 0.96e6 + 0.49e6
 NCU_JSON = os.path.join(ROOT, "profiles", "r1x_formc_tick_pair_ncu.json")
 
 
@@ -449,7 +450,13 @@ def main():
                                   "peak": fp64_peak, "unit": "TFLOP/s",
                                   "frac": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
                                   "executed_flop_per_instance_tick": FLOP_FORMC,
-                                  "peak_source": "ismpc_measure_fp64_peak (DFMA micro-benchmark, this run)"},
+                                  "peak_source": "ismpc_measure_fp64_peak (DFMA micro-benchmark, this run)",
+                                  # the dense null-space active-set model of the reference algorithm,
+                                  # F_ref = (k+1)(14 nV^2 + 2 nC nV): 2 x 0.96 Mflop (x, y; k = 5) + 0.49 Mflop (z) per
+                                  # instance-tick.  NOT work this kernel executes (it exploits the structure);
+                                  # reported beside the executed figure as the survey asks.
+                                  "reference_algorithm_flop_per_instance_tick": F_REF_FORMC,
+                                  "reference_algorithm_equivalent_tflops": F_REF_FORMC * n / (kernel_ms * 1e-3) / 1e12},
                 "eager": {"value": 3.0 * n * world * K / (eager_ms_max * 1e-3), "unit": "QP solves/s",
                           "ms_per_step": eager_ms_max / K, "how": "K separate C-ABI calls from Python, CUDA events around the loop"},
                 "two_streams": (None if overlap_ms is None else
@@ -481,6 +488,9 @@ def main():
                                     "sample": "%d instances x %d passes of the same workload, all %d host threads, "
                                               "cold qpOASES QProblem per solve (utils.cpp:121-130)" % (ns, reps, threads),
                                     "failed_instances": nfail}
+            q1, _, _, _, n1, _ = cpu_reference_run(1, 0, sample_n=128, threads=1)
+            line["cpu_baseline"]["single_thread"] = {"value": q1, "unit": "QP solves/s", "cores": 1,
+                                                     "sample": "%d instances x 1 pass, one host thread" % n1}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
