@@ -398,6 +398,58 @@ def main():
     last_copy = pipe[(K - 1) % DEPTH]["out_np"].copy()
     e2e_mapped_s = e2e_loop(2)
     mapped_equal = bool(np.array_equal(last_copy, pipe[(K - 1) % DEPTH]["out_np"]))
+
+    # ---- the same serving loop from C++ (host/FormCPipeline.hpp over the C ABI): the reference's host language ----
+    # W warm-up steps, barrier, K timed steps ending with every stream waited for, barrier.  Same pinned input blocks,
+    # same rotation, its own DEPTH handles / streams / pinned result buffers; the loop reads every step's result.
+    import ctypes as C
+    hostlib = C.CDLL(os.path.join(os.path.dirname(binding.LIB_PATH), "libismpc_host.so"))
+    hostlib.ismpc_host_pipeline_create.restype = C.c_void_p
+    hostlib.ismpc_host_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    hostlib.ismpc_host_pipeline_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hostlib.ismpc_host_pipeline_destroy.argtypes = [C.c_void_p]
+    hostlib.ismpc_host_pipeline_launches.restype = C.c_longlong
+    hostlib.ismpc_host_pipeline_launches.argtypes = [C.c_void_p]
+    hostlib.ismpc_host_last_error.restype = C.c_char_p
+    hostlib.ismpc_host_pipelines_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
+    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "2"))        # host threads, one pipeline each (1x4: 249, 1x6: 267, 2x3: 296, 2x4: 303, 3x3: 310 M QP/s)
+    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4"))      # calls in flight per thread
+    pps = []
+    for _ in range(T_HOST):
+        pp = hostlib.ismpc_host_pipeline_create(local, n, D_HOST, model.ctypes.data, 35, 10, plans_c.ctypes.data, plans_c.shape[0])
+        if not pp:
+            raise RuntimeError("ismpc_host_pipeline_create: " + hostlib.ismpc_host_last_error().decode())
+        pps.append(pp)
+    pp_arr = (C.c_void_p * T_HOST)(*pps)
+    blocks = (C.c_void_p * len(pinned))(*[d["pack_res"].data_ptr() for d in pinned])
+    csum = C.c_longlong(0)
+    out_cpp = np.zeros((T_HOST, D_HOST, n), dtype=abi.FORMC_OUT)
+    l_before = sum(hostlib.ismpc_host_pipeline_launches(pp) for pp in pps)
+    WC = -(-W // T_HOST) * T_HOST                                  # warm-up rounded up to whole rounds of the threads
+    if hostlib.ismpc_host_pipelines_run(pp_arr, T_HOST, 0, WC, blocks, len(pinned), C.byref(csum), None) != 0:
+        raise RuntimeError("ismpc_host_pipelines_run: " + hostlib.ismpc_host_last_error().decode())
+    barrier()
+    t0 = time.perf_counter()
+    rc_cpp = hostlib.ismpc_host_pipelines_run(pp_arr, T_HOST, WC, K, blocks, len(pinned), C.byref(csum), out_cpp.ctypes.data)
+    barrier()
+    e2e_cpp_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
+    if rc_cpp != 0:
+        raise RuntimeError("ismpc_host_pipelines_run: " + hostlib.ismpc_host_last_error().decode())
+    e2e_cpp_launches = sum(hostlib.ismpc_host_pipeline_launches(pp) for pp in pps) - l_before
+    for pp in pps:
+        hostlib.ismpc_host_pipeline_destroy(pp)
+    # where the last step's records are: thread t takes steps WC+t, WC+t+T, ...; its slots go round-robin from the
+    # number of steps it has submitted since creation
+    k_last = WC + K - 1
+    t_last = (k_last - WC) % T_HOST
+    done_before = WC // T_HOST + (k_last - WC - t_last) // T_HOST   # steps thread t_last submitted before this one
+    slot_last = done_before % D_HOST
+    # its last step against a synchronous call on the same pinned block
+    e2e_sync_step(k_last, out_sync)
+    ref_last = np.frombuffer(out_sync.numpy().tobytes(), dtype=abi.FORMC_OUT)
+    cpp_equal = bool(out_cpp[t_last, slot_last].tobytes() == ref_last.tobytes())
+    bad_cpp = int(((out_cpp[t_last, slot_last]["status"] & 7) != 0).sum())
     # sanity: the e2e result equals the device-resident result for the same batch
     chk = np.frombuffer(pipe[(K - 1) % DEPTH]["out"].numpy().tobytes(), dtype=abi.FORMC_OUT)
     bad = int(((chk["status"] & 7) != 0).sum())
@@ -421,13 +473,20 @@ def main():
                            "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)", "launch": launch_mode,
                            "l2": "inputs rotate over %d distinct device batches (%.0f MB > L2 126 MB)"
                                  % (n_slots, n_slots * per_batch / 1e6)},
-                "e2e": {"value": e2e_value, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad,
-                        "how": "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d handles on %d streams "
-                               "(serving loop with that many calls in flight); every step copies its state / walk-state / instance records in "
-                               "and its result records out; the footstep plans are resident in the handle "
-                               "(ismpc_formc_set_plan), as they are constructor data of the reference's MPCSolver" % (DEPTH, DEPTH),
-                        "kernel_launches": int(e2e_launches)},
+                "e2e": {"value": 3.0 * n * world * K / e2e_cpp_s, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad_cpp,
+                        "last_step_equals_synchronous_call": cpp_equal,
+                        "how": "C++ host loop (host/FormCPipeline.hpp, the reference's host language) over the C ABI: "
+                               "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d host threads x %d handles / streams "
+                               "(that many calls in flight); every step copies its state / walk-state / instance records in "
+                               "(one pinned block, one copy) and its result records out, and the loop reads each result; the "
+                               "footstep plans are resident in the handles (ismpc_formc_set_plan), as they are constructor "
+                               "data of the reference's MPCSolver" % (T_HOST, D_HOST),
+                        "kernel_launches": int(e2e_cpp_launches)},
+                "e2e_python": {"value": e2e_value, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
+                               "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad,
+                               "how": "the same loop written in Python over ctypes (~13 us of interpreter and call overhead per step)",
+                               "kernel_launches": int(e2e_launches)},
                 "e2e_with_plan": {"value": 3.0 * n * world * K / e2e_plan_s, "unit": "QP solves/s",
                                   "h2d_bytes_per_step": int(h2d_with_plan), "d2h_bytes_per_step": int(d2h),
                                   "how": "the same loop with the whole footstep-plan table passed and copied in every step"},

@@ -33,6 +33,7 @@
 #ifndef ISMPC_B200_H
 #define ISMPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -170,6 +171,15 @@ int ismpc_destroy(ismpc_handle* h);
 const char* ismpc_last_cuda_error(const ismpc_handle* h);
 /* Number of kernels this handle has launched since creation (for the benchmark's launch count). */
 int64_t ismpc_kernel_launches(const ismpc_handle* h);
+
+/* For hosts without the CUDA headers (plain C, C++, FFI): a non-blocking stream owned by the handle (created on first
+ * use, destroyed with the handle; NULL on failure), a wait for everything enqueued on a stream by calls on this handle
+ * (what ISMPC_MEM_HOST_ASYNC asks the caller to do before touching the buffers again), and pinned host memory for the
+ * buffers of the host-memory modes (NULL on failure). */
+void* ismpc_handle_stream(ismpc_handle* h);
+int ismpc_wait(ismpc_handle* h, void* stream);
+void* ismpc_host_alloc(size_t bytes);
+void ismpc_host_free(void* p);
 
 /* Tuning knobs that do not change results beyond rounding (every kernel family is an exact solver of the same
  * strictly convex QPs; tests/test_formc_gpu.py holds them to 1e-9 of each other).

@@ -18,7 +18,8 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_forma_set_model", "ismpc_forma_solve_batch", "ismpc_forma_rollout", "ismpc_qp_solve_batch",
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
-           "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan"]
+           "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan",
+           "ismpc_handle_stream", "ismpc_wait", "ismpc_host_alloc", "ismpc_host_free"]
 
 _lib = None
 
@@ -82,6 +83,12 @@ def lib():
     L.ismpc_kf_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_kf_filter_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
+    L.ismpc_handle_stream.restype = C.c_void_p
+    L.ismpc_handle_stream.argtypes = [C.c_void_p]
+    L.ismpc_wait.argtypes = [C.c_void_p, C.c_void_p]
+    L.ismpc_host_alloc.restype = C.c_void_p
+    L.ismpc_host_alloc.argtypes = [C.c_size_t]
+    L.ismpc_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 

@@ -51,6 +51,7 @@ struct ismpc_handle {
     DevBuf s_ainst, s_aout, s_timing, a_Lwork, a_queue;
     DevBuf q_in, q_out, q_work;
     DevBuf s_pred, f_inst, f_plan, f_out;
+    cudaStream_t own_stream = nullptr;     // ismpc_handle_stream: created on first use, destroyed with the handle
 };
 
 static int fail_cuda(ismpc_handle* h, cudaError_t e, const char* where)
@@ -103,9 +104,39 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
     for (DevBuf* b : all) b->release();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ISMPC_OK;
 }
+
+// Plumbing for callers without the CUDA headers (plain C / C++ / FFI hosts): a stream owned by the handle, a wait on
+// it, and pinned host memory for the ISMPC_MEM_HOST_ASYNC buffers.
+extern "C" void* ismpc_handle_stream(ismpc_handle* h)
+{
+    if (!h) return nullptr;
+    if (!h->own_stream) {
+        if (cudaSetDevice(h->device) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->own_stream = nullptr; return nullptr; }
+    }
+    return (void*)h->own_stream;
+}
+
+extern "C" int ismpc_wait(ismpc_handle* h, void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return ISMPC_OK;
+}
+
+extern "C" void* ismpc_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" void ismpc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
 {

@@ -51,3 +51,84 @@ def test_shim_closed_loop_matches_oracle():
         state["com_pos"][0] = traj[k, :3]; state["com_vel"][0] = traj[k, 3:6]
         walk["control_iter"] += 1
         walk["mpc_iter"] = int(np.floor(walk["control_iter"][0] * 0.01 / 0.01))
+
+
+def _hostlib():
+    import ctypes as C
+    L = C.CDLL(os.path.join(os.path.dirname(binding.LIB_PATH), "libismpc_host.so"))
+    L.ismpc_host_pipeline_create.restype = C.c_void_p
+    L.ismpc_host_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ismpc_host_pipeline_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ismpc_host_pipelines_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ismpc_host_pipeline_destroy.argtypes = [C.c_void_p]
+    L.ismpc_host_last_error.restype = C.c_char_p
+    return L
+
+
+def test_host_library_loads_and_fails_loudly_without_gpu():
+    """lib/libismpc_host.so (the C++ serving loop, g++ only) exports its entry points; without a GPU the pipeline
+    cannot be created and says why."""
+    import torch
+    L = _hostlib()
+    for name in ("ismpc_host_pipeline_create", "ismpc_host_pipeline_run", "ismpc_host_pipeline_destroy",
+                 "ismpc_host_pipeline_launches", "ismpc_host_last_error"):
+        assert hasattr(L, name)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model = abi.formc_model()
+    plan = np.zeros((4, 4))
+    assert not L.ismpc_host_pipeline_create(0, 8, 2, model.ctypes.data, 35, 10, plan.ctypes.data, 4)
+    assert b"ismpc_create" in L.ismpc_host_last_error()
+
+
+@pytest.mark.gpu
+def test_cpp_serving_loop_equals_direct_calls(handle):
+    """host/FormCPipeline.hpp: several ticks in flight on several handles give the records of one synchronous call each."""
+    import ctypes as C
+    L = _hostlib()
+    n, depth, nb = 256, 3, 5
+    model = abi.formc_model()
+    batches = [synth.formc_batch(n, seed=60 + b, n_steps=40) for b in range(nb)]
+    plans = np.concatenate([b[3] for b in batches])
+    blocks, keep = [], []
+    for b, (st, wk, ins, pl) in enumerate(batches):
+        ins = ins.copy(); ins["plan_first_row"] += b * pl.shape[0]
+        raw = np.concatenate([x.view(np.uint8).reshape(-1) for x in (st, wk, ins)]).copy()
+        keep.append((st, wk, ins, raw)); blocks.append(raw.ctypes.data)
+    arr = (C.c_void_p * nb)(*blocks)
+    p = L.ismpc_host_pipeline_create(0, n, depth, model.ctypes.data, 35, 10, plans.ctypes.data, plans.shape[0])
+    assert p, L.ismpc_host_last_error()
+    try:
+        steps = 2 * depth + 2
+        out = np.zeros((depth, n), dtype=abi.FORMC_OUT)
+        csum = C.c_longlong(0)
+        assert L.ismpc_host_pipeline_run(p, 0, steps, arr, nb, C.byref(csum), out.ctypes.data) == 0, L.ismpc_host_last_error()
+    finally:
+        L.ismpc_host_pipeline_destroy(p)
+    # two host threads, one pipeline each: thread t takes steps t, t+2, ...
+    T = 2
+    ps = [L.ismpc_host_pipeline_create(0, n, depth, model.ctypes.data, 35, 10, plans.ctypes.data, plans.shape[0]) for _ in range(T)]
+    assert all(ps), L.ismpc_host_last_error()
+    try:
+        steps_t = 2 * T * depth + 1
+        out_t = np.zeros((T, depth, n), dtype=abi.FORMC_OUT)
+        assert L.ismpc_host_pipelines_run((C.c_void_p * T)(*ps), T, 0, steps_t, arr, nb, C.byref(csum), out_t.ctypes.data) == 0, \
+            L.ismpc_host_last_error()
+    finally:
+        for q in ps:
+            L.ismpc_host_pipeline_destroy(q)
+    handle.formc_set_model(model)
+    handle.formc_set_plan(plans)
+    try:
+        for k in range(steps - depth, steps):
+            st, wk, ins, _ = keep[k % nb]
+            ref = handle.formc_solve_batch(st, wk, ins, None, want_primal=False, want_active=False)
+            assert out[k % depth].tobytes() == ref["out"].tobytes(), "step %d" % k
+        for t in range(T):
+            mine = list(range(t, steps_t, T))
+            for j in range(len(mine) - depth, len(mine)):       # the last `depth` steps of thread t sit in slots j % depth
+                st, wk, ins, _ = keep[mine[j] % nb]
+                ref = handle.formc_solve_batch(st, wk, ins, None, want_primal=False, want_active=False)
+                assert out_t[t, j % depth].tobytes() == ref["out"].tobytes(), "thread %d step %d" % (t, mine[j])
+    finally:
+        handle.formc_set_plan(None)
