@@ -413,8 +413,10 @@ def main():
     hostlib.ismpc_host_last_error.restype = C.c_char_p
     hostlib.ismpc_host_pipelines_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
-    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "2"))        # host threads, one pipeline each (1x4: 249, 1x6: 267, 2x3: 296, 2x4: 303, 3x3: 310 M QP/s)
-    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4"))      # calls in flight per thread
+    # a second host thread pays off only where the rank has cores to itself (8 ranks on a 32-thread box: 1 thread each)
+    T_DEFAULT = 2 if (os.cpu_count() or 1) // world >= 8 else 1
+    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", str(T_DEFAULT)))        # host threads, one pipeline each (1x4: 249, 1x6: 267, 2x3: 296, 2x4: 303, 3x3: 310 M QP/s)
+    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4" if T_HOST > 1 else "6"))      # calls in flight per thread
     pps = []
     for _ in range(T_HOST):
         pp = hostlib.ismpc_host_pipeline_create(local, n, D_HOST, model.ctypes.data, 35, 10, plans_c.ctypes.data, plans_c.shape[0])
