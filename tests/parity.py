@@ -26,3 +26,21 @@ def active_set_mismatch(as_gpu, as_ora, duals_ora, weak_tol=1e-9):
     # a weak row may legitimately be reported active by one side only; but it must not be active on opposite sides
     opp = (as_gpu * as_ora == -1)
     return (diff | opp).sum(axis=-1), (weak & (as_gpu != as_ora)).sum(axis=-1)
+
+
+def kkt_certificate(Hd, g, A, lb, ub, x, active, n_eq=2):
+    """Solver-independent optimality check of x for  min 1/2 x'diag(Hd)x + g'x,  lb <= Ax <= ub  (first n_eq rows are
+    equalities), given the claimed working set `active` (-1 lower / 0 / +1 upper per inequality row).
+    Returns (feasibility violation, stationarity residual per variable relative to max(1, |H_jj x_j| + |g_j|), worst
+    wrong-signed multiplier relative to the largest multiplier): all three ~0 certify the minimiser of a strictly convex
+    QP."""
+    r = A @ x
+    scale = np.maximum(1.0, np.maximum(np.abs(lb), np.abs(ub)))
+    feas = max(((lb - r) / scale).max(), ((r - ub) / scale).max(), 0.0)
+    W = np.concatenate([np.arange(n_eq), n_eq + np.nonzero(active)[0]])
+    grad = Hd * x + g
+    y, *_ = np.linalg.lstsq(A[W].T, grad, rcond=None)                 # grad = A_W' y: y >= 0 at lower, <= 0 at upper bounds
+    stat = (np.abs(A[W].T @ y - grad) / np.maximum(1.0, np.abs(Hd * x) + np.abs(g))).max()
+    yi = y[n_eq:] * np.where(active[np.nonzero(active)[0]] < 0, 1.0, -1.0)   # must be >= 0
+    wrong = max(0.0, -yi.min()) / max(1e-300, np.abs(y).max()) if len(yi) else 0.0
+    return feas, stat, wrong

@@ -4,7 +4,7 @@ import pytest
 
 from quadruped_gait_generation_ismpc_b200 import abi, synth
 from oracle import oracle as O
-from parity import PRIMAL_TOL, primal_rel_err, active_set_mismatch
+from parity import PRIMAL_TOL, primal_rel_err, active_set_mismatch, kkt_certificate
 
 pytestmark = pytest.mark.gpu
 
@@ -183,3 +183,47 @@ def test_warm_started_rollout_equals_cold(handle, monkeypatch):
     assert (w["status"] & abi.ST_FAIL_MASK == 0).all() and (c["status"] & abi.ST_FAIL_MASK == 0).all()
     assert np.abs(w["traj"] - c["traj"]).max() <= 1e-7
     assert np.array_equal(w["inst"]["fs_counter"], c["inst"]["fs_counter"])
+
+
+@pytest.mark.parametrize("C,F,step", [(50, 3, 25), (37, 2, 20), (100, 5, 50), (100, 8, 50), (200, 3, 100), (400, 3, 200)])
+def test_horizons_and_footstep_counts(handle, C, F, step):
+    """configs[3] for formulation A (C = 50/100/200/400, ragged 37) and footstep counts other than the scripts' F = 3
+    (F > 3 runs the kernel instantiation with the general saddle solve): mid-gait instances against the oracle.  The
+    oracle's working-set budget is raised for the long horizons (nWSR = 300 is hit at C = 200)."""
+    model = abi.forma_model(C=C, P=2 * C, F=F)
+    handle.forma_set_model(model)
+    n = 24 if C <= 200 else 8
+    inst, ft, plan = synth.forma_batch(n, gait="trot", C=C, step=step, ds=max(2, step * 2 // 5), sim_ticks=24 * step,
+                                       seed=70 + C + F)
+    rng = np.random.default_rng(C + F)
+    ticks = rng.choice([0, step // 3, step + 3, 2 * step + step // 2, 4 * step - 1], size=n)
+    inst, plan = _advance(handle, inst, ft, plan, ticks)
+    g = handle.forma_solve_batch(inst, ft, plan)
+    o = O.forma_batch(model, inst, ft, plan, nthreads=8, nwsr_cap=4000)
+    ok = o["ret"] == 0
+    assert ok.mean() > 0.9
+    assert (g["out"]["status"][ok] & abi.ST_FAIL_MASK == 0).all()
+    # an optimality certificate that does not involve the oracle's SOLVER (only its dense builder): feasible,
+    # stationary on the reported working set, multipliers of the right sign
+    for i in np.nonzero(ok)[0]:
+        it = inst[i]
+        p = O.FormAParams(float(model["dt"][0]), float(np.sqrt(model["g_eta"][0] / it["height"])), float(it["wx"]), float(it["wy"]),
+                          float(model["disp_forw"][0]), float(model["disp_forw_dummy"][0]), float(model["disp_L"][0]),
+                          float(model["q_zdot"][0]), float(model["q_foot"][0]), C, 2 * C, F)
+        tf, nt, a, nf = int(it["timing_first"]), int(it["n_timing"]), int(it["plan_first_row"]), int(it["n_fs"])
+        Hd, gq, A, lb, ub = O.forma_build(p, it["st"], it["cur_fs"], it["fs_store"], int(it["j"]), int(it["fs_counter"]),
+                                          ft[tf:tf + nt], int(it["ds"]), plan[a:a + nf], int(it["cl_first_ramp"]))
+        feas, stat, wrong = kkt_certificate(Hd, gq, A, lb, ub, g["primal"][i], g["active"][i])
+        assert feas <= 1e-9 and stat <= 1e-7 and wrong <= 1e-7, (i, feas, stat, wrong)
+    err = primal_rel_err(g["primal"][ok], o["primal"][ok])
+    if C >= 400:
+        # At C = 400 qpOASES (Options::setToMPC, 200-350 working-set changes) stops with bound violations of ~2e-7 on
+        # some instances (measured: its own A x leaves [lb, ub] by that much, this library's by 1e-16), which moves
+        # its primal by up to 2.4e-6: the comparison is held to 1e-5 there and the certificate above carries the claim.
+        assert err.max() <= 1e-5, "primal rel err %.3e" % err.max()
+        return
+    assert err.max() <= PRIMAL_TOL, "primal rel err %.3e" % err.max()
+    assert np.abs(g["out"]["st"][ok] - o["out"]["st"][ok]).max() <= PRIMAL_TOL
+    assert np.abs(g["out"]["pred_fs"][ok][:, :2 * F] - o["out"]["pred_fs"][ok][:, :2 * F]).max() <= PRIMAL_TOL
+    mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
+    assert mism.sum() == 0, "active set differs on %d rows (%d weak ignored)" % (mism.sum(), weak.sum())
