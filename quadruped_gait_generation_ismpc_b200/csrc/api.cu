@@ -31,6 +31,7 @@ struct ismpc_handle {
     long long launches = 0;
     char err[256] = {0};
     int opt_formc_cluster = 0;     // 0 = automatic
+    int opt_formc_variant = 0;     // 0 = by batch size, 2 = two warps per instance, 1 / 16 = one warp (register budgets)
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
     int w_res[5] = {0, 0, 0, 0, 0};   // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel, pair tick / rollout kernels; 0 = not queried
@@ -146,9 +147,9 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
         h->opt_formc_cluster = value;
         return ISMPC_OK;
     }
-    if (strcmp(name, "formc_variant") == 0) {      // register budget of the warp tick kernel (process-wide)
+    if (strcmp(name, "formc_variant") == 0) {      // build of the warp kernel family used by this handle
         if (value != 0 && value != 1 && value != 2 && value != 16) return ISMPC_ERR_ARG;
-        formc_set_variant(value);
+        h->opt_formc_variant = value;
         return ISMPC_OK;
     }
     if (strcmp(name, "formc_kernel") == 0) {
@@ -255,7 +256,7 @@ static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStr
     int rc = formc_warp_prepare(h, wa, a, n);
     if (rc) return rc;
     int grid = 0;
-    return formc_tick_warp_launch(wa, n, h->w_res, &grid, st);
+    return formc_tick_warp_launch(wa, n, h->w_res, h->opt_formc_variant, &grid, st);
 }
 
 static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
@@ -265,7 +266,7 @@ static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismp
     FormCWarpArgs wa;
     int rc = formc_warp_prepare(h, wa, a, n);
     if (rc) return rc;
-    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, n, h->w_res, st);
+    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, n, h->w_res, h->opt_formc_variant, st);
 }
 
 extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)

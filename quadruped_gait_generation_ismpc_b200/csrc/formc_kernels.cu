@@ -311,12 +311,9 @@ int formc_cluster_ctas_per_sm(int N)
 int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream_t st)
 {
     size_t smem = formc_smem_bytes(a.model.N);
-    static size_t configured = 0;
-    if (smem > configured) {
+    if (smem > 48 * 1024) {     // per-device function attribute, needed only beyond the default limit (N > ~330); no process-wide cache
         cudaFuncSetAttribute(formc_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_tick_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(formc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
     }
     if (cluster_size <= 1) {
         formc_tick_kernel<<<grid, FORMC_THREADS, smem, st>>>(a);

@@ -292,13 +292,13 @@ int formc_warp_supported(int N) { return N >= 2 && N <= ISMPC_MAX_N; }
 // every instance of the batch has a resident CTA (the 1,024-instance tick); <1> is one warp per instance with the
 // registers it wants; <16> is held to 128 registers so that 16 warps per SM stay resident (throughput of large
 // batches: 65,536 instances run 1.25x faster than with <1>).  variant 0 = pick by batch size, 2 = pair.
-static int g_formc_variant = 0;
-void formc_set_variant(int v) { g_formc_variant = v; }
+// (the variant is per handle: ismpc_set_option("formc_variant"), passed down with every launch)
 
+// The dynamic shared-memory limit is a per-device function attribute: set it whenever a handle queries residency (once
+// per handle and model), on that handle's device -- no process-wide cache, handles on several devices or threads are fine.
 static void formc_warp_configure(size_t smem)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
+    {
         cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -306,7 +306,6 @@ static void formc_warp_configure(size_t smem)
                              (int)(smem + FORMC_PAIR_RED * sizeof(double)));
         cudaFuncSetAttribute(formc_rollout_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(smem + FORMC_PAIR_RED * sizeof(double)));
-        configured = smem;
     }
 }
 
@@ -326,16 +325,16 @@ void formc_warp_resident(int N, int sm_count, int res[5])
 
 // One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
 // general vertical path).
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int* grid_out, cudaStream_t st)
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
-    if (g_formc_variant == 2 || (g_formc_variant == 0 && n <= res[3])) {
+    if (variant == 2 || (variant == 0 && n <= res[3])) {
         const int grid = n < res[3] ? n : res[3];
         *grid_out = grid;
         formc_tick_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a);
         return (int)cudaGetLastError();
     }
-    const bool big = g_formc_variant == 16 || (g_formc_variant == 0 && n > res[0]);
+    const bool big = variant == 16 || (variant == 0 && n > res[0]);
     const int cap = big ? res[1] : res[0];
     const int grid = n < cap ? n : cap;
     *grid_out = grid;
@@ -346,9 +345,9 @@ int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int*
 
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                               const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int n, const int res[5],
-                              cudaStream_t st)
+                              int variant, cudaStream_t st)
 {
-    if (g_formc_variant == 2 || (g_formc_variant == 0 && n <= res[4])) {
+    if (variant == 2 || (variant == 0 && n <= res[4])) {
         const int grid = n < res[4] ? n : res[4];
         formc_rollout_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
                                                                                            traj, status);

@@ -25,12 +25,11 @@ int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, d
                          long long* launches);
 int formc_law_launch(const ismpc_formc_model_t& m, int n_pat, const double* ric, double* law, cudaStream_t st, long long* launches);
 int formc_warp_supported(int N);
-void formc_set_variant(int v);
 void formc_warp_resident(int N, int sm_count, int res[5]);
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int* grid_out, cudaStream_t st);
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int* grid_out, cudaStream_t st);
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                               const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int n, const int res[5],
-                              cudaStream_t st);
+                              int variant, cudaStream_t st);
 
 struct FormALaunchPlan { int R, warps_per_cta, grid, use_pdas, warm_start; size_t smem, spill_doubles; };
 void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p);

@@ -1,5 +1,5 @@
 """Exercises every kernel of the library once on small batches, for compute-sanitizer:
-    compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python tools/sanitize_run.py
+    compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python tools/sanitize_run.py   (where the pool allows it: compute-sanitizer is closed on the B200 pool this round was measured on, so it ran as a plain kernel tour there)
 (no torch: host-memory calls through ctypes only, so the report holds this library's kernels and nothing else)."""
 import os
 import sys
