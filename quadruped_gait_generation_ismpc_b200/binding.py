@@ -140,6 +140,16 @@ class Handle:
         self._check(self._L.ismpc_measure_fp64_peak(self._h, reps, C.byref(v)), "ismpc_measure_fp64_peak")
         return v.value
 
+    def stream(self):
+        """The handle's own non-blocking stream (ismpc_handle_stream) as an integer address."""
+        v = self._L.ismpc_handle_stream(self._h)
+        if not v:
+            raise IsmpcError("ismpc_handle_stream failed")
+        return int(v)
+
+    def wait(self, stream=None):
+        self._check(self._L.ismpc_wait(self._h, C.c_void_p(stream) if stream else None), "ismpc_wait")
+
     @property
     def kernel_launches(self):
         return int(self._L.ismpc_kernel_launches(self._h))

@@ -487,7 +487,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
         if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
         return ISMPC_OK;
     }
-    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
     const size_t mb = (size_t)h->max_batch;
     if (h->s_ainst.ensure(mb * sizeof(ismpc_forma_inst_t)) || h->s_aout.ensure(mb * sizeof(ismpc_forma_out_t)) ||
         h->s_timing.ensure((size_t)timing_len * sizeof(int32_t)) || h->s_plan.ensure((size_t)plan_rows * 2 * sizeof(double)))
@@ -527,7 +527,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
         if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * nV, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
+    if (mem == ISMPC_MEM_HOST) CK(cudaStreamSynchronize(st));
     return ISMPC_OK;
 }
 

@@ -227,3 +227,35 @@ def test_horizons_and_footstep_counts(handle, C, F, step):
     assert np.abs(g["out"]["pred_fs"][ok][:, :2 * F] - o["out"]["pred_fs"][ok][:, :2 * F]).max() <= PRIMAL_TOL
     mism, weak = active_set_mismatch(g["active"][ok], o["active"][ok], o["duals"][ok])
     assert mism.sum() == 0, "active set differs on %d rows (%d weak ignored)" % (mism.sum(), weak.sum())
+
+
+def test_host_async_call_on_the_handles_stream(handle):
+    """ISMPC_MEM_HOST_ASYNC + ismpc_handle_stream + ismpc_wait (the plumbing a host without CUDA headers uses) == the
+    synchronous host-memory call; the buffers come from ismpc_host_alloc (pinned)."""
+    import ctypes as C
+    from quadruped_gait_generation_ismpc_b200 import binding
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    n = 64
+    inst, ft, plan = synth.forma_batch(n, gait="trot", seed=91)
+    ref = handle.forma_solve_batch(inst, ft, plan)
+    L = binding.lib()
+    nV = 2 * (int(model["C"][0]) + int(model["F"][0]))
+    ft = np.ascontiguousarray(ft, dtype=np.int32)
+    sizes = [inst.nbytes, ft.nbytes, plan.nbytes, n * abi.FORMA_OUT.itemsize, n * nV * 8]
+    ptrs = [L.ismpc_host_alloc(s) for s in sizes]
+    assert all(ptrs)
+    try:
+        for p, a in zip(ptrs[:3], (inst, ft, plan)):
+            C.memmove(p, a.ctypes.data, a.nbytes)
+        st = handle.stream()
+        handle.forma_solve_batch_raw(n, ptrs[0], ptrs[1], len(ft), ptrs[2], plan.shape[0], ptrs[3], primal=ptrs[4],
+                                     mem=abi.MEM_HOST_ASYNC, stream=st)
+        handle.wait(st)
+        out = np.frombuffer(C.string_at(ptrs[3], sizes[3]), dtype=abi.FORMA_OUT)
+        primal = np.frombuffer(C.string_at(ptrs[4], sizes[4]), dtype=np.float64).reshape(n, nV)
+        assert out.tobytes() == ref["out"].tobytes()
+        assert np.array_equal(primal, ref["primal"])
+    finally:
+        for p in ptrs:
+            L.ismpc_host_free(p)
