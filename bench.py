@@ -531,16 +531,41 @@ def main():
                 "gathered_records": int(len(full))}
 
     # ---- formulation A (canonical ISMPC with footsteps), rank 0 extra measurement -------------------------
-    if rank == 0 and not args.no_form_a:
+    # (configs[2] -- 65,536 walking instances over 8 GPUs -- is the walking tick of every rank's 8,192-instance shard)
+    if not args.no_form_a:
         try:
-            line["form_a"] = bench_form_a(h, torch, dev, n, stream)
+            fa = bench_form_a(h, torch, dev, n, stream, rank=rank)
         except Exception as e:  # noqa: BLE001
-            line["form_a"] = {"error": repr(e)}
+            fa = {"error": repr(e)}
+        walk_ms = fa.get("tick_cold_walk", {}).get("ms_per_tick", -1.0)
+        if world > 1:
+            walk_ms_all = sharding.max_over_ranks(walk_ms, device=dev)
+            bad_all = sharding.max_over_ranks(float("error" in fa), device=dev)
+            if rank == 0 and bad_all == 0.0:
+                fa["tick_cold_walk_all_gpus"] = {
+                    "workload": "formA_tick_walk_%dxC100F3_midgait_cold: 8,192 instances on each of %d GPUs (configs[2])"
+                                % (8192 * world, world),
+                    "qp_solves_per_s": 8192 * world / (walk_ms_all * 1e-3), "ms_per_tick": walk_ms_all}
+        if rank == 0:
+            line["form_a"] = fa
+    # ---- configs[4]: closed loop on every rank (its own 1,000 instances), aggregated like the headline value ---------
+    if not args.no_form_a:
         try:
             h.formc_set_model(model); h.formc_prepare_gait(35, 10)
-            line["closed_loop_form_c"] = bench_formc_rollout(h, torch, dev, stream)
+            cl = bench_formc_rollout(h, torch, dev, stream, rank)
         except Exception as e:  # noqa: BLE001
-            line["closed_loop_form_c"] = {"error": repr(e)}
+            cl = {"error": repr(e), "ms_total": -1.0}
+        ms_all = sharding.max_over_ranks(cl["ms_total"], device=dev) if world > 1 else cl["ms_total"]
+        ok_all = sharding.max_over_ranks(1.0 if "error" in cl else 0.0, device=dev) if world > 1 else float("error" in cl)
+        if rank == 0:
+            if ok_all == 0.0 and world > 1:
+                per_rank = cl["instance_ticks_per_s"] * cl["ms_total"] * 1e-3          # instance-ticks of one rank
+                cl["workload"] += " on each of %d GPUs" % world
+                cl["ms_total"] = ms_all
+                cl["instance_ticks_per_s"] = world * per_rank / (ms_all * 1e-3)
+                cl["qp_solves_per_s"] = 3.0 * cl["instance_ticks_per_s"]
+                cl["instances_with_a_failed_tick"] = "rank 0: %d" % cl["instances_with_a_failed_tick"]
+            line["closed_loop_form_c"] = cl
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             reps = 3
@@ -576,7 +601,7 @@ def _midgait(h, inst, ft, plan, seed=5):
     return inst, plan
 
 
-def bench_form_a(h, torch, dev, n, stream, steps=20):
+def bench_form_a(h, torch, dev, n, stream, steps=20, rank=0):
     """Formulation A (canonical ISMPC with footsteps, 1 QP of nV=206/nC=208 per instance-tick):
     cold single ticks on mid-gait trot (configs[1]) and walking (configs[2], per-GPU share) batches, and the
     closed loop with pushes, warm-started (configs[4])."""
@@ -609,12 +634,14 @@ def bench_form_a(h, torch, dev, n, stream, steps=20):
                 "dual_active_set_fallbacks": int((out["status"] & abi.ST_GI_FALLBACK != 0).sum())}
 
     res = {"note": "1 QP per instance-tick (x and y stacked: nV=206, nC=208); cold = empty working set"}
-    inst, ft, plan = synth.forma_batch(n, gait="trot")
-    res["tick_cold_trot"] = tick_bench(abi.forma_model(), inst, ft, plan, "formA_tick_trot_%dxC100F3_midgait_cold" % n)
     nw = 8192
-    inst, ft, plan = synth.forma_batch(nw, gait="walk", vary=True, ds=30, N_gait=108)
+    inst, ft, plan = synth.forma_batch(nw, gait="walk", vary=True, ds=30, N_gait=108, seed=(synth.SEED0 ^ 3) + 7919 * rank)
     res["tick_cold_walk"] = tick_bench(abi.forma_model(q_foot=1e9), inst, ft, plan,
                                        "formA_tick_walk_%dxC100F3_midgait_cold (configs[2] per-GPU share)" % nw)
+    if rank != 0:
+        return res          # the other ranks only take part in the walking tick (configs[2]: 8,192 instances per GPU)
+    inst, ft, plan = synth.forma_batch(n, gait="trot")
+    res["tick_cold_trot"] = tick_bench(abi.forma_model(), inst, ft, plan, "formA_tick_trot_%dxC100F3_midgait_cold" % n)
     # closed loop: 1,000 instances x 250 ticks with pushes, state resident on the device, warm-started
     nr, T = 1000, 250
     h.forma_set_model(abi.forma_model())
@@ -641,13 +668,14 @@ def bench_form_a(h, torch, dev, n, stream, steps=20):
     return res
 
 
-def bench_formc_rollout(h, torch, dev, stream):
-    """configs[4] on formulation C: 1,000 instances x 1,000 closed-loop ticks (3 QPs each) with pushes, on the device."""
+def bench_formc_rollout(h, torch, dev, stream, rank=0):
+    """configs[4] on formulation C: 1,000 instances x 1,000 closed-loop ticks (3 QPs each) with pushes, on the device
+    (every rank draws its own instances)."""
     from quadruped_gait_generation_ismpc_b200 import abi, synth
     nr, T = 1000, 1000
     steps_plan = (T + 2 * HORIZON + 900) // 45 + 3
-    state, walk, inst, plan = synth.formc_batch(nr, seed=synth.SEED0 ^ 11, n_steps=steps_plan, k0_cap=100)
-    push = synth.push_batch(nr, formc=True)
+    state, walk, inst, plan = synth.formc_batch(nr, seed=(synth.SEED0 ^ 11) + 7919 * rank, n_steps=steps_plan, k0_cap=100)
+    push = synth.push_batch(nr, seed=(synth.SEED0 ^ 5) + 7919 * rank, formc=True)
 
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
