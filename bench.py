@@ -377,7 +377,7 @@ def main():
                                           stream=p_["cu_stream"])
 
     def e2e_loop(with_plan):
-        for k in range(W):
+        for k in range(max(W, DEPTH)):                      # at least one call on every handle before the clock starts
             e2e_pipe_step(k, with_plan)
         for p_ in pipe:
             p_["stream"].synchronize()
@@ -414,7 +414,7 @@ def main():
     hostlib.ismpc_host_pipelines_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
     # a second host thread pays off only where the rank has cores to itself (8 ranks on a 32-thread box: 1 thread each)
-    T_DEFAULT = 2 if (os.cpu_count() or 1) // world >= 8 else 1
+    T_DEFAULT = 2 if (os.cpu_count() or 1) // world >= 8 and K >= 64 else 1      # (a handful of steps: not worth a thread)
     T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", str(T_DEFAULT)))        # host threads, one pipeline each (1x4: 249, 1x6: 267, 2x3: 296, 2x4: 303, 3x3: 310 M QP/s)
     D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4" if T_HOST > 1 else "6"))      # calls in flight per thread
     pps = []
@@ -428,7 +428,9 @@ def main():
     csum = C.c_longlong(0)
     out_cpp = np.zeros((T_HOST, D_HOST, n), dtype=abi.FORMC_OUT)
     l_before = sum(hostlib.ismpc_host_pipeline_launches(pp) for pp in pps)
-    WC = -(-W // T_HOST) * T_HOST                                  # warm-up rounded up to whole rounds of the threads
+    # warm-up rounded up to whole rounds of the threads, and at least one call on every handle (a handle's first call
+    # allocates its staging and workspace and queries occupancy: milliseconds that do not belong in the timed region)
+    WC = max(-(-W // T_HOST) * T_HOST, T_HOST * D_HOST)
     if hostlib.ismpc_host_pipelines_run(pp_arr, T_HOST, 0, WC, blocks, len(pinned), C.byref(csum), None) != 0:
         raise RuntimeError("ismpc_host_pipelines_run: " + hostlib.ismpc_host_last_error().decode())
     barrier()

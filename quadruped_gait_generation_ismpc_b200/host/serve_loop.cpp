@@ -68,8 +68,8 @@ extern "C" int ismpc_host_pipelines_run(void* const* pipes, int T, int k0, int s
     std::vector<std::thread> th;
     std::vector<long long> sums((size_t)T, 0);
     std::vector<std::string> errs((size_t)T);
-    for (int t = 0; t < T; ++t) {
-        th.emplace_back([&, t] {
+    auto work = [&](int t) {
+        {
             FormCPipeline& p = *static_cast<FormCPipeline*>(pipes[t]);
             const size_t n = (size_t)p.n();
             try {
@@ -89,9 +89,13 @@ extern "C" int ismpc_host_pipelines_run(void* const* pipes, int T, int k0, int s
             } catch (const std::exception& e) {
                 errs[t] = e.what();
             }
-        });
+        }
+    };
+    if (T == 1) work(0);                                   // no thread for a single pipeline
+    else {
+        for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (std::thread& x : th) x.join();
     }
-    for (std::thread& x : th) x.join();
     long long sum = 0;
     for (int t = 0; t < T; ++t) {
         if (!errs[t].empty()) { g_err = errs[t]; return -1; }
