@@ -33,6 +33,18 @@ struct DasTimer {
 #endif
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; for x normal and finite (callers check their pivots).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 __device__ __forceinline__ double warp_sum(double v)

@@ -362,11 +362,11 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
                 }
             }
             // M = L D L'
-            const double d0 = M[0][0], i0 = 1.0 / d0;
+            const double d0 = M[0][0], i0 = fast_rcp(d0);
             const double l10 = M[1][0] * i0, l20 = M[2][0] * i0;
-            const double d1 = M[1][1] - l10 * l10 * d0, i1 = 1.0 / d1;
+            const double d1 = M[1][1] - l10 * l10 * d0, i1 = fast_rcp(d1);
             const double l21 = (M[2][1] - l20 * l10 * d0) * i1;
-            const double d2 = M[2][2] - l20 * l20 * d0 - l21 * l21 * d1, i2 = 1.0 / d2;
+            const double d2 = M[2][2] - l20 * l20 * d0 - l21 * l21 * d1, i2 = fast_rcp(d2);
             auto msolve = [&](const double (&b)[3], double (&z)[3]) {
                 const double y0 = b[0], y1 = b[1] - l10 * y0, y2 = b[2] - l20 * y0 - l21 * y1;
                 z[2] = y2 * i2; z[1] = y1 * i1 - l21 * z[2]; z[0] = y0 * i0 - l10 * z[1] - l20 * z[2];
@@ -375,7 +375,7 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
             msolve(rf, zr); msolve(v, zv);
             const double S = k00 - (v[0] * zv[0] + v[1] * zv[1] + v[2] * zv[2]);
             if (!(d0 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0) || !(fabs(S) > 1e-200)) { rc = 2; break; }
-            nu = (rr0 - (v[0] * zr[0] + v[1] * zr[1] + v[2] * zr[2])) / S;
+            nu = (rr0 - (v[0] * zr[0] + v[1] * zr[1] + v[2] * zr[2])) * fast_rcp(S);
 #pragma unroll
             for (int f = 0; f < FT; ++f) xf[f] = f < 3 ? zr[f < 3 ? f : 0] - zv[f < 3 ? f : 0] * nu : 0.0;
         }

@@ -90,17 +90,6 @@ __device__ __forceinline__ void fast_divmod(int u, int per, float rcp, int& q, i
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; x normal and finite on this path (CoM heights).
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
 
 // Per-warp global workspace of the general vertical path (doubles).
 __host__ __device__ inline size_t formc_warp_ws_doubles(int N)
