@@ -259,3 +259,18 @@ def test_host_async_call_on_the_handles_stream(handle):
     finally:
         for p in ptrs:
             L.ismpc_host_free(p)
+
+
+@pytest.mark.parametrize("gait", ["trot", "walk"])
+def test_recorded_midgait_instances(handle, gait):
+    """tests/golden/forma_midgait.npz: the kernel reproduces what it did when the fixture was recorded (same minimiser,
+    same number of working-set iterations) -- the numbers tests/test_pdas_restatement.py reproduces in numpy on the CPU."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forma_midgait.npz"))
+    model, inst = gold[gait + "_model"], gold[gait + "_inst"]
+    handle.forma_set_model(model)
+    g = handle.forma_solve_batch(inst, gold[gait + "_fs_timing"], gold[gait + "_fs_plan"])
+    assert (g["out"]["status"] & abi.ST_FAIL_MASK == 0).all()
+    assert np.abs(g["primal"] - gold[gait + "_kernel_primal"]).max() <= 1e-9
+    assert np.array_equal(g["active"], gold[gait + "_kernel_active"])
+    assert np.array_equal(g["out"]["iters"], gold[gait + "_kernel_iters"])
