@@ -252,3 +252,72 @@ def test_vertical_qp_is_an_lq_tracking_problem():
         assert np.abs(f - ref).max() / max(1.0, np.abs(ref).max()) < 1e-9
         checked += 1
     assert checked >= 30
+
+
+def _knapsack(a, b, mid, rho):
+    """The horizontal QP  min 1/2|u|^2 - mid'u,  a'u = b,  |u - mid| <= rho  as the kernels solve it (formc_pair.cuh:
+    formc_knapsack_axis): u = mid + clip(nu a, +-rho); t = |nu| from the best PREFIX saturation set (a lower bound of the
+    root of the concave piecewise-linear g(t) = sum |a_i| min(t |a_i|, rho)), then semismooth Newton until the set repeats.
+    Returns u, the lower-bound start, the root, and the number of Newton passes."""
+    r = b - a @ mid
+    sg, ra = (1.0 if r >= 0 else -1.0), abs(r)
+    ab = np.abs(a)
+    t = ra / (ab @ ab)
+    t0 = t
+    passes = 0
+    if t * ab.max() > rho:
+        P1 = np.concatenate([[0.0], np.cumsum(ab)[:-1]])                # sum_{i<k} |a_i|
+        S2 = np.cumsum((ab * ab)[::-1])[::-1]                           # sum_{i>=k} a_i^2
+        ok = S2 > 1e-12 * (ab @ ab)
+        t0 = t = max(t, ((ra - rho * P1[ok]) / S2[ok]).max())
+        prev = -1
+        while True:
+            sat = t * ab > rho
+            passes += 1
+            if sat.sum() == prev:
+                break
+            prev = sat.sum()
+            q2 = (ab[~sat] ** 2).sum()
+            assert q2 > 0, "infeasible instance in the test set"
+            tn = (ra - rho * ab[sat].sum()) / q2
+            if abs(tn - t) <= 1e-13 * t:
+                break
+            t = max(t, tn) if passes > 1 else tn
+    return mid + np.clip(sg * t * a, -rho, rho), t0, t, passes
+
+
+def test_horizontal_qp_is_a_knapsack_problem():
+    """The other identity the warp kernels build on: the stage-3 QPs (MPCSolver.cpp:325-398, H = I, one
+    stability row, a box) are solved exactly by clipping along the stability row; the best prefix set is a lower bound
+    of the multiplier and Newton from there needs a pass or two.  Checked against qpOASES on the literal stage-3 build."""
+    p = O.formc_default_params()
+    N = p.N
+    rng = np.random.default_rng(4)
+    eta2 = 9.81 / 0.69
+    n_sat = 0
+    worst_passes = 0
+    for trial in range(60):
+        lam = eta2 * (1.0 + rng.uniform(-0.15, 0.15) * np.sin(np.arange(N) * rng.uniform(0.05, 0.3) + rng.uniform(0, 6)))
+        L = rng.uniform(0.05, 0.25)
+        k0 = int(rng.integers(0, 45))
+        t = k0 + np.arange(2 * N)
+        step, ph = t // 45, t % 45
+        mid = L * (step + np.where(ph < 35, 0.0, (ph - 35) / 10.0))
+        eta = np.sqrt(eta2)
+        cs = np.array([mid[0] + rng.uniform(-0.03, 0.12), rng.uniform(-0.1, 0.3)])     # from comfortable to hard against the box
+        a, b, lo, hi, g, _ = O.formc_horizontal_qp(p, lam, cs, mid, 3)
+        m, rho = -g, 0.5 * (hi - lo)
+        assert np.allclose(rho, rho[0]) and np.allclose(0.5 * (lo + hi), m)
+        if abs(b - a @ m) > rho[0] * np.abs(a).sum() * 0.999:
+            continue                                                    # infeasible: the kernels flag it, qpOASES fails
+        u, t0, troot, passes = _knapsack(a, b, m, rho[0])
+        A = np.vstack([a[None, :], np.eye(N)])
+        ref = O.qp_solve(np.eye(N), g, A, np.concatenate([[b], lo]), np.concatenate([[b], hi]))
+        assert ref["ret"] == 0
+        assert np.abs(u - ref["x"]).max() <= 1e-8 * max(1.0, np.abs(ref["x"]).max()), trial
+        assert t0 <= troot * (1 + 1e-12)                                # the prefix start never overshoots the root
+        if passes:
+            n_sat += 1
+            worst_passes = max(worst_passes, passes)
+    assert n_sat >= 10, "vacuous: no saturated instance"
+    assert worst_passes <= 6
