@@ -71,3 +71,27 @@ def test_product_never_touches_the_oracle():
                 assert bad is None, "%s uses the oracle: %s" % (f, bad.group(0))
     libs = subprocess.check_output(["ldd", binding.LIB_PATH], text=True) if os.path.exists(binding.LIB_PATH) else ""
     assert "oracle" not in libs
+
+
+def test_plumbing_entry_points_reject_bad_arguments():
+    """ismpc_handle_stream / ismpc_wait / ismpc_host_alloc (hosts without CUDA headers): NULL handle and empty
+    allocations are refused without touching the device; without a GPU the pinned allocation fails with NULL."""
+    L = binding.lib()
+    assert L.ismpc_handle_stream(None) is None
+    assert L.ismpc_wait(None, None) != 0
+    assert L.ismpc_host_alloc(0) is None
+    L.ismpc_host_free(None)                                  # a no-op, like free(NULL)
+    import torch
+    if not torch.cuda.is_available():
+        assert L.ismpc_host_alloc(4096) is None
+
+
+def test_host_library_uses_only_the_c_abi():
+    """lib/libismpc_host.so (the C++ serving loop) links against the product library and the C++ runtime only: no CUDA
+    runtime, no torch -- it is what a C++ caller of the reference's class would compile with plain g++."""
+    host = os.path.join(os.path.dirname(binding.LIB_PATH), "libismpc_host.so")
+    assert os.path.exists(host)
+    needed = subprocess.check_output(["readelf", "-d", host], text=True)
+    libs = re.findall(r"NEEDED.*\[(.*?)\]", needed)
+    assert "libismpc_b200.so" in libs
+    assert not [x for x in libs if "cuda" in x.lower() or "torch" in x.lower()], libs
