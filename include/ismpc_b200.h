@@ -189,6 +189,11 @@ void ismpc_host_free(void* p);
  *   "formc_variant":      build of the warp family: 0 = by batch size, 2 = two warps per instance (latency build, the
  *                         choice while every instance has a resident CTA), 1 = one warp per instance with unlimited
  *                         registers, 16 = one warp per instance held to 128 registers (16 resident warps per SM).
+ *   "forma_pdas":         1 = structured primal-dual active set with the dual active set as fallback (default), 0 = dual
+ *                         active set only.   "forma_warm": 1 = rollouts start each tick from the previous working set
+ *                         (default), 0 = every tick cold.   "forma_R", "forma_warps_per_cta": shared-memory rows of
+ *                         the fallback's factor and warps per CTA of the form-A kernels (0 = default).
+ *                         The ISMPC_FORMA_{PDAS,WARM,R,WPC} environment variables set these defaults when a handle is created.
  * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);
 

@@ -1,5 +1,6 @@
 // api.cu -- the C ABI (include/ismpc_b200.h): handle, staging for host-memory calls, kernel launches.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "formc.cuh"
@@ -46,6 +47,7 @@ struct ismpc_handle {
     // form A
     bool forma_ready = false;
     ismpc_forma_model_t am{};
+    FormATuning a_tune;            // ismpc_set_option("forma_*"); the ISMPC_FORMA_* environment variables set the defaults at creation
     // staging (host-memory calls)
     DevBuf s_state, s_walk, s_cinst, s_cout, s_plan, s_primal, s_active, s_push, s_traj, s_status;
     DevBuf s_in;                   // [state | walk | inst] of one form-C tick call
@@ -93,6 +95,9 @@ extern "C" int ismpc_create(ismpc_handle** out, int device, int max_batch)
     ismpc_handle* h = new (std::nothrow) ismpc_handle();
     if (!h) return ISMPC_ERR_ALLOC;
     h->device = device; h->max_batch = max_batch; h->sm_count = prop.multiProcessorCount;
+    auto env_int = [](const char* nm, int dflt) { const char* v = getenv(nm); return (v && *v) ? atoi(v) : dflt; };
+    h->a_tune.R = env_int("ISMPC_FORMA_R", 0); h->a_tune.warps_per_cta = env_int("ISMPC_FORMA_WPC", 0);
+    h->a_tune.pdas = env_int("ISMPC_FORMA_PDAS", 1) != 0; h->a_tune.warm = env_int("ISMPC_FORMA_WARM", 1) != 0;
     *out = h;
     return ISMPC_OK;
 }
@@ -152,6 +157,10 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
         h->opt_formc_variant = value;
         return ISMPC_OK;
     }
+    if (strcmp(name, "forma_pdas") == 0) { h->a_tune.pdas = value != 0; return ISMPC_OK; }
+    if (strcmp(name, "forma_warm") == 0) { h->a_tune.warm = value != 0; return ISMPC_OK; }
+    if (strcmp(name, "forma_R") == 0) { if (value < 0) return ISMPC_ERR_ARG; h->a_tune.R = value; return ISMPC_OK; }
+    if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 4) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
     if (strcmp(name, "formc_kernel") == 0) {
         if (value < 0 || value > 2) return ISMPC_ERR_ARG;
         h->opt_formc_kernel = value;
@@ -473,7 +482,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     FormAArgs a;
     a.n = n; a.model = h->am; a.timing_len = timing_len; a.plan_rows = plan_rows; a.sm_count = h->sm_count;
     FormALaunchPlan lp;
-    forma_plan(h->am, h->sm_count, 2LL * n, &lp);
+    forma_plan(h->am, h->sm_count, 2LL * n, h->a_tune, &lp);
     if (h->a_Lwork.ensure((lp.spill_doubles + 2) * sizeof(double)) || h->a_queue.ensure(sizeof(int))) return ISMPC_ERR_ALLOC;
     a.Jspill = lp.spill_doubles ? (double*)h->a_Lwork.p : nullptr;
     a.queue = (int*)h->a_queue.p;

@@ -171,14 +171,8 @@ __global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_
     io->j = j; io->fs_counter = fsc; io->cl_first_ramp = first_ramp;
 }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 // Shared-memory / residency plan for a model: R rows of the inverse factor in shared memory, the rest spilled.
-void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, FormALaunchPlan* p)
+void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, const FormATuning& tune, FormALaunchPlan* p)
 {
     const int C = m.C, F = m.F, q = C + F + 1;
     const size_t lim = 227 * 1024;
@@ -187,10 +181,10 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, For
     // a smaller footprint keeps every (instance, axis) item of a 1,024-instance tick resident (R = 32: 153 us, 12: 128 us)
     int R_dflt = 12;
     while (R_dflt < q && (size_t)tri(R_dflt, 0) < (size_t)(1 + 2 * F) * (2 + 2 * F)) ++R_dflt;
-    int R = env_int("ISMPC_FORMA_R", R_dflt);
+    int R = tune.R > 0 ? tune.R : R_dflt;
     if (R > q) R = q;
     if (R < 1) R = 1;
-    int wpc = env_int("ISMPC_FORMA_WPC", 4);
+    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     if (wpc < 1) wpc = 1;
     if (wpc > FORMA_MAX_THREADS / 32) wpc = FORMA_MAX_THREADS / 32;
     const size_t hdr = forma_cta_smem_header(C);
@@ -206,8 +200,8 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, For
     p->grid = (int)(ctas < resident ? ctas : resident);
     if (p->grid < 1) p->grid = 1;
     p->spill_doubles = forma_spill_doubles(C, F, R) * (size_t)p->grid * wpc;
-    p->use_pdas = env_int("ISMPC_FORMA_PDAS", 1) && (size_t)tri(R, 0) >= (size_t)(1 + 2 * F) * (2 + 2 * F);
-    p->warm_start = env_int("ISMPC_FORMA_WARM", 1);
+    p->use_pdas = tune.pdas && (size_t)tri(R, 0) >= (size_t)(1 + 2 * F) * (2 + 2 * F);
+    p->warm_start = tune.warm;
 }
 
 int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStream_t st)

@@ -159,9 +159,11 @@ def test_structured_solver_equals_dual_active_set(handle, monkeypatch):
     ticks = rng.choice([0, 9, 33, 49, 50, 77, 99, 100, 150, 222], size=n)
     inst, plan = _advance(handle, inst, ft, plan, ticks)
     a = handle.forma_solve_batch(inst, ft, plan)
-    monkeypatch.setenv("ISMPC_FORMA_PDAS", "0")
-    b = handle.forma_solve_batch(inst, ft, plan)
-    monkeypatch.delenv("ISMPC_FORMA_PDAS")
+    handle.set_option("forma_pdas", 0)
+    try:
+        b = handle.forma_solve_batch(inst, ft, plan)
+    finally:
+        handle.set_option("forma_pdas", 1)
     assert (b["out"]["status"] & abi.ST_GI_FALLBACK == 0).all()
     assert (a["out"]["status"] & abi.ST_FAIL_MASK == 0).all() and (b["out"]["status"] & abi.ST_FAIL_MASK == 0).all()
     assert (a["out"]["status"] & abi.ST_GI_FALLBACK != 0).mean() < 0.05, "fast path falls back too often"
@@ -177,9 +179,11 @@ def test_warm_started_rollout_equals_cold(handle, monkeypatch):
     push = synth.push_batch(16, seed=52)
     push["fs"] = 2
     w = handle.forma_rollout(inst, ft, plan, 160, push=push)
-    monkeypatch.setenv("ISMPC_FORMA_WARM", "0")
-    c = handle.forma_rollout(inst, ft, plan, 160, push=push)
-    monkeypatch.delenv("ISMPC_FORMA_WARM")
+    handle.set_option("forma_warm", 0)
+    try:
+        c = handle.forma_rollout(inst, ft, plan, 160, push=push)
+    finally:
+        handle.set_option("forma_warm", 1)
     assert (w["status"] & abi.ST_FAIL_MASK == 0).all() and (c["status"] & abi.ST_FAIL_MASK == 0).all()
     assert np.abs(w["traj"] - c["traj"]).max() <= 1e-7
     assert np.array_equal(w["inst"]["fs_counter"], c["inst"]["fs_counter"])

@@ -254,7 +254,7 @@ def test_vertical_qp_is_an_lq_tracking_problem():
     assert checked >= 30
 
 
-def _knapsack(a, b, mid, rho):
+def _knapsack_prefix_newton(a, b, mid, rho):
     """The horizontal QP  min 1/2|u|^2 - mid'u,  a'u = b,  |u - mid| <= rho  as the kernels solve it (formc_pair.cuh:
     formc_knapsack_axis): u = mid + clip(nu a, +-rho); t = |nu| from the best PREFIX saturation set (a lower bound of the
     root of the concave piecewise-linear g(t) = sum |a_i| min(t |a_i|, rho)), then semismooth Newton until the set repeats.
@@ -316,7 +316,7 @@ def test_horizontal_qp_is_a_knapsack_problem():
         m, rho = -g, 0.5 * (hi - lo)
         assert np.allclose(rho, rho[0]) and np.allclose(0.5 * (lo + hi), m)
         assert abs(b - a @ m) <= rho[0] * np.abs(a).sum()
-        u, t0, troot, passes = _knapsack(a, b, m, rho[0])
+        u, t0, troot, passes = _knapsack_prefix_newton(a, b, m, rho[0])
         A = np.vstack([a[None, :], np.eye(N)])
         ref = O.qp_solve(np.eye(N), g, A, np.concatenate([[b], lo]), np.concatenate([[b], hi]))
         assert ref["ret"] == 0

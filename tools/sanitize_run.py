@@ -41,11 +41,9 @@ ai, ft, fp = synth.forma_batch(64, gait="trot")
 r = h.forma_rollout(ai, ft, fp, 60, push=synth.push_batch(64))
 g = h.forma_solve_batch(r["inst"], ft, r["fs_plan"])
 print("forma tick: failed", int((g["out"]["status"] & abi.ST_FAIL_MASK != 0).sum()), "iters max", int(g["out"]["iters"].max()))
-os.environ["ISMPC_FORMA_PDAS"] = "0"
-try:
-    g = h.forma_solve_batch(r["inst"][:16], ft, r["fs_plan"])
-finally:
-    os.environ.pop("ISMPC_FORMA_PDAS")
+h.set_option("forma_pdas", 0)
+g = h.forma_solve_batch(r["inst"][:16], ft, r["fs_plan"])
+h.set_option("forma_pdas", 1)
 # dense seam
 rng = np.random.default_rng(0)
 nV, nC, nq = 12, 9, 8
