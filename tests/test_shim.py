@@ -132,3 +132,35 @@ def test_cpp_serving_loop_equals_direct_calls(handle):
                 assert out_t[t, j % depth].tobytes() == ref["out"].tobytes(), "thread %d step %d" % (t, mine[j])
     finally:
         handle.formc_set_plan(None)
+
+
+def _build_pipeline_example(d):
+    exe = os.path.join(d, "pipeline_example")
+    libdir = os.path.dirname(binding.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-O1", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "pipeline_example.cpp"),
+                           "-L" + libdir, "-lismpc_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_pipeline_example_compiles_with_plain_gpp():
+    """host/FormCPipeline.hpp needs nothing but g++ and the C ABI (-Wall -Wextra -Werror); no GPU: loud failure."""
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_pipeline_example(d)
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+        r = subprocess.run([exe, "2"], capture_output=True, text=True)
+        assert r.returncode == 2 and "ismpc_create" in r.stderr
+
+
+@pytest.mark.gpu
+def test_pipeline_example_runs():
+    """The C++ example steps 64 copies of the DART app's robot for a few ticks: the CoM stays at its height and starts
+    moving along the plan like the single-instance closed loop of tests/test_formc_gpu.py."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_pipeline_example(d)
+        out = subprocess.check_output([exe, "5"], text=True)
+    rows = np.array([[float(x) for x in ln.split()] for ln in out.strip().splitlines()])
+    assert rows.shape == (5, 4) and np.array_equal(rows[:, 0], np.arange(5))
+    assert np.abs(rows[:, 3] - 0.69).max() < 1e-3 and np.isfinite(rows).all()
