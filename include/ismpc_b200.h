@@ -58,10 +58,12 @@ enum {
     ISMPC_ST_Z_FAIL = 1,        /* vertical QP infeasible / iteration cap */
     ISMPC_ST_X_FAIL = 2,        /* x QP infeasible / iteration cap */
     ISMPC_ST_Y_FAIL = 4,        /* y QP infeasible / iteration cap */
-    ISMPC_ST_WINDOW = 8,        /* k0+2N exceeds the midpoint sequence: instance left untouched */
+    ISMPC_ST_WINDOW = 8,        /* k0+2N exceeds the midpoint sequence, or the record's plan rows lie outside the plan
+                                   table: instance left untouched */
     ISMPC_ST_XY_SKIPPED = 16,   /* lambda_0 <= 2: horizontal QPs skipped, u = 0 (MPCSolver.cpp:322) */
     ISMPC_ST_NAN_GUARD = 32,    /* vertical state was NaN and was patched (MPCSolver.cpp:277-278) */
-    ISMPC_ST_QP_FAIL = 64,      /* form A / generic QP infeasible or iteration cap */
+    ISMPC_ST_QP_FAIL = 64,      /* form A / generic QP infeasible or iteration cap; form A: record points outside the
+                                   plan / timing tables (instance skipped) */
     ISMPC_ST_GI_FALLBACK = 128  /* informational (form A): the structured primal-dual active-set solve did not settle;
                                    the result comes from the dual active-set fallback and is equally exact */
 };

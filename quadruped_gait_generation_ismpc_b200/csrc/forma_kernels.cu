@@ -24,6 +24,13 @@ __device__ __forceinline__ long long forma_next_item(int* queue)
     return (long long)__shfl_sync(ISMPC_FULL_MASK, v, 0);
 }
 
+// plan rows / timing entries of an instance record inside the tables handed to the call (a step needs two timing entries)
+__device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in, int plan_rows, int timing_len)
+{
+    return in.plan_first_row >= 0 && in.n_fs >= 2 && (long long)in.plan_first_row + in.n_fs <= (long long)plan_rows &&
+           in.timing_first >= 0 && in.n_timing >= 2 && (long long)in.timing_first + in.n_timing <= (long long)timing_len;
+}
+
 template <int FT>
 __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick_kernel(FormAArgs a)
 {
@@ -43,6 +50,10 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
         if (item >= 2LL * a.n) break;
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
         const ismpc_forma_inst_t in = a.inst[inst];
+        if (!forma_inst_in_range(in, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
+            if (lane == 0) atomicOr(&a.out[inst].status, (int)ISMPC_ST_QP_FAIL);
+            continue;
+        }
         const double* plan = a.fs_plan + (size_t)in.plan_first_row * 2;
         const int32_t* ft = a.fs_timing + in.timing_first;
         double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
@@ -103,6 +114,10 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_roll
         if (item >= 2LL * a.n) break;
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
         const ismpc_forma_inst_t in = ra.inst_io[inst];
+        if (!forma_inst_in_range(in, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
+            if (lane == 0 && ra.status) atomicOr(&ra.status[inst], (int)ISMPC_ST_QP_FAIL);
+            continue;
+        }
         double* plan = ra.plan_io + (size_t)in.plan_first_row * 2;
         const int32_t* ft = a.fs_timing + in.timing_first;
         const double eta = sqrt(a.model.g_eta / in.height);
@@ -154,11 +169,13 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_roll
 
 // Advance the fields both axes share (j, fs_counter, cl_first_ramp) after every warp of the rollout is done.
 // They evolve identically on both axes and depend only on the timing table, so they are recomputed here.
-__global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_io, const int32_t* fs_timing)
+__global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_io, const int32_t* fs_timing, int plan_rows,
+                                   int timing_len)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ismpc_forma_inst_t* io = inst_io + i;
+    if (!forma_inst_in_range(*io, plan_rows, timing_len)) return;     // the rollout kernel flagged and skipped it
     const int32_t* ft = fs_timing + io->timing_first;
     int j = io->j, fsc = io->fs_counter, first_ramp = io->cl_first_ramp;
     for (int tick = 0; tick < n_ticks; ++tick) {
@@ -230,7 +247,7 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
     FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status};
     kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
-    forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing);
+    forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing, a.plan_rows, a.timing_len);
     return (int)cudaGetLastError();
 }
 

@@ -48,6 +48,17 @@ __host__ __device__ inline void formc_flight_range(int N, int S, int F, int mpc_
     if (ne < 0) ne = 0;
 }
 
+// A record whose plan rows fall outside the plan table is treated like a window beyond the plan: n_steps = 0 makes the
+// tick return ISMPC_ST_WINDOW with the instance untouched (and the rollouts never look a step time up), instead of
+// reading out of bounds.
+__device__ __forceinline__ ismpc_formc_inst_t formc_checked_inst(ismpc_formc_inst_t in, int plan_rows)
+{
+    if (in.plan_first_row < 0 || in.n_steps < 0 || (long long)in.plan_first_row + in.n_steps > (long long)plan_rows) {
+        in.n_steps = 0; in.plan_first_row = 0;
+    }
+    return in;
+}
+
 struct FormCShared {      // per-CTA shared memory carve-up (all pointers into dynamic smem)
     double *midx, *midy, *midz;            // [2N], [2N], [N]
     double *Fz, *f, *rv, *zdir, *scr;      // [N] each

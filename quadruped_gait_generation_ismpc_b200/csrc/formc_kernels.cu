@@ -202,7 +202,7 @@ formc_tick_kernel(FormCArgs a)
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         const ismpc_state_t st = a.state[inst];
         const ismpc_walk_t wk = a.walk[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         formc_tick<false>(sm, a.model, a.T, st, wk, in, a.plan, a.out + inst,
                    a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
                    a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
@@ -228,7 +228,7 @@ formc_tick_cluster_kernel(FormCArgs a)
     for (int inst = cluster_id; inst < a.n; inst += n_clusters) {
         const ismpc_state_t st = a.state[inst];
         const ismpc_walk_t wk = a.walk[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         const bool lead = cr == 0;
         formc_tick<true>(sm, a.model, a.T, st, wk, in, a.plan, lead ? a.out + inst : nullptr,
                          lead && a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
@@ -263,7 +263,7 @@ formc_rollout_kernel(FormCRolloutArgs ra)
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         ismpc_state_t st = ra.state_io[inst];
         ismpc_walk_t wk = ra.walk_io[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_push_t pu; pu.fs = 0; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
         if (ra.push) pu = ra.push[inst];
         int acc_status = 0;

@@ -128,7 +128,7 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         const ismpc_state_t st = a.state[inst];
         const ismpc_walk_t wk = a.walk[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_formc_out_t r;
         formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
                         a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
@@ -160,7 +160,7 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         const ismpc_state_t st = a.state[inst];
         const ismpc_walk_t wk = a.walk[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_formc_out_t r;
         formc_tick_pair(sm, red, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
                         a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
@@ -192,7 +192,7 @@ formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         ismpc_state_t st = state_io[inst];
         ismpc_walk_t wk = walk_io[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_push_t pu; pu.fs = 0; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
         if (push) pu = push[inst];
         int acc_status = 0;
@@ -248,7 +248,7 @@ formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
         ismpc_state_t st = state_io[inst];
         ismpc_walk_t wk = walk_io[inst];
-        const ismpc_formc_inst_t in = a.inst[inst];
+        const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_push_t pu; pu.fs = 0; pu.ct0 = 0; pu.ct1 = 0; pu.ax = 0.0; pu.ay = 0.0; pu.reserved = 0;
         if (push) pu = push[inst];
         int acc_status = 0;

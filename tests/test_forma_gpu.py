@@ -278,3 +278,25 @@ def test_recorded_midgait_instances(handle, gait):
     assert np.abs(g["primal"] - gold[gait + "_kernel_primal"]).max() <= 1e-9
     assert np.array_equal(g["active"], gold[gait + "_kernel_active"])
     assert np.array_equal(g["out"]["iters"], gold[gait + "_kernel_iters"])
+
+
+def test_out_of_range_tables_are_flagged_not_read(handle):
+    """Formulation A: records pointing outside the footstep-plan or timing tables get ISMPC_ST_QP_FAIL (tick and rollout)
+    and leave the other instances' results as they are."""
+    model = abi.forma_model()
+    handle.forma_set_model(model)
+    inst, ft, plan = synth.forma_batch(32, gait="trot", seed=93)
+    ref = handle.forma_solve_batch(inst, ft, plan)
+    bad = inst.copy()
+    bad["plan_first_row"][2] = plan.shape[0] - 3
+    bad["timing_first"][7] = len(ft) - 1
+    bad["n_fs"][11] = 1 << 28
+    g = handle.forma_solve_batch(bad, ft, plan)
+    for i in (2, 7, 11):
+        assert g["out"]["status"][i] & abi.ST_QP_FAIL
+    ok = np.ones(32, bool); ok[[2, 7, 11]] = False
+    assert np.array_equal(g["primal"][ok], ref["primal"][ok])
+    r = handle.forma_rollout(bad, ft, plan, 12)
+    for i in (2, 7, 11):
+        assert r["status"][i] & abi.ST_QP_FAIL
+    assert (r["status"][ok] & abi.ST_FAIL_MASK == 0).all()

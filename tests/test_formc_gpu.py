@@ -352,3 +352,34 @@ def test_batch_beyond_residency_grid_stride(handle):
             assert np.abs(part["out"]["zmp_in"] - big["out"]["zmp_in"][sl]).max() <= 1e-12
     finally:
         handle.set_option("formc_variant", 0)
+
+
+def test_out_of_range_plan_rows_are_flagged_not_read(handle):
+    """An instance record whose plan rows lie outside the plan table comes back with ISMPC_ST_WINDOW and its state
+    untouched (tick, both kernel builds) or unmoved (rollout); its neighbours are unaffected."""
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(64, seed=77, k0_cap=300)
+    ref = handle.formc_solve_batch(state, walk, inst, plan)
+    bad = inst.copy()
+    bad["plan_first_row"][3] = plan.shape[0] - 5          # runs off the end of the table
+    bad["plan_first_row"][10] = -40                        # negative
+    bad["n_steps"][20] = 1 << 28                           # absurd length
+    ok = np.ones(64, bool); ok[[3, 10, 20]] = False
+    for name, value in (("formc_variant", 0), ("formc_variant", 1), ("formc_kernel", 1)):    # pair, one-warp, CTA kernels
+        handle.set_option(name, value)
+        try:
+            g = handle.formc_solve_batch(state, walk, bad, plan)
+        finally:
+            handle.set_option(name, 0)
+        for i in (3, 10, 20):
+            assert g["out"]["status"][i] == abi.ST_WINDOW
+            assert np.array_equal(g["out"]["next"]["com_pos"][i], state["com_pos"][i])
+        if name == "formc_variant" and value == 0:
+            assert g["out"][ok].tobytes() == ref["out"][ok].tobytes()
+        else:
+            assert np.abs(g["out"]["next"]["com_pos"][ok] - ref["out"]["next"]["com_pos"][ok]).max() < 1e-9
+    r = handle.formc_rollout(state, walk, bad, plan, 20)
+    for i in (3, 10, 20):
+        assert r["status"][i] & abi.ST_WINDOW
+        assert np.array_equal(r["state"]["com_pos"][i], state["com_pos"][i])
