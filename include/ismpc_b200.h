@@ -250,6 +250,14 @@ int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks,
                         const double* plan_xyzt, int plan_rows, const ismpc_push_t* push,
                         double* traj_opt, int32_t* status_opt, int mem, void* stream);
 
+/* ismpc_formc_rollout plus a per-tick status trace: status_trace_opt (nullable) n x n_ticks int32, the ISMPC_ST_* bits of
+ * every tick, so that a caller knows WHEN an instance failed (the reference drops the solver's return code,
+ * utils.cpp:128; after a failed tick the rollout integrates the clipped input it has and goes on). */
+int ismpc_formc_rollout_ex(ismpc_handle* h, int n, int n_ticks,
+                           ismpc_state_t* state, ismpc_walk_t* walk, const ismpc_formc_inst_t* inst,
+                           const double* plan_xyzt, int plan_rows, const ismpc_push_t* push,
+                           double* traj_opt, int32_t* status_opt, int32_t* status_trace_opt, int mem, void* stream);
+
 int ismpc_forma_set_model(ismpc_handle* h, const ismpc_forma_model_t* model);
 
 /* One tick of the MATLAB loop body (build QP-1, solve, integrate) for n independent instances.
@@ -278,6 +286,13 @@ int ismpc_forma_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst
                            const int32_t* fs_timing, int timing_len,
                            double* fs_plan, int plan_rows, const ismpc_push_t* push,
                            double* traj_opt, double* pred_traj_opt, int32_t* status_opt, int mem, void* stream);
+
+/* ... plus the per-tick status trace: status_trace_opt (nullable) n x n_ticks x 2 int32 (x axis, y axis). */
+int ismpc_forma_rollout_ex2(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                            const int32_t* fs_timing, int timing_len,
+                            double* fs_plan, int plan_rows, const ismpc_push_t* push,
+                            double* traj_opt, double* pred_traj_opt, int32_t* status_opt, int32_t* status_trace_opt,
+                            int mem, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Real-foot placement (the scripts' "SECOND QUAD_PROG") and trajectory export -- the stage     */

@@ -19,7 +19,8 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_measure_fp64_peak", "ismpc_set_option", "ismpc_forma_rollout_ex", "ismpc_feet_place_rollout",
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
            "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan",
-           "ismpc_handle_stream", "ismpc_wait", "ismpc_host_alloc", "ismpc_host_free"]
+           "ismpc_handle_stream", "ismpc_wait", "ismpc_host_alloc", "ismpc_host_free", "ismpc_formc_rollout_ex",
+           "ismpc_forma_rollout_ex2"]
 
 _lib = None
 
@@ -71,6 +72,8 @@ def lib():
     L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_formc_rollout_ex.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    L.ismpc_forma_rollout_ex2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     L.ismpc_forma_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_forma_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_forma_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
@@ -197,16 +200,19 @@ class Handle:
                                              C.c_void_p(stream) if stream else None)
         self._check(rc, "ismpc_formc_solve_batch")
 
-    def formc_rollout(self, state, walk, inst, plan, n_ticks, push=None, want_traj=True):
+    def formc_rollout(self, state, walk, inst, plan, n_ticks, push=None, want_traj=True, want_trace=False):
+        """want_trace: also return the per-tick status words (n x n_ticks int32, ismpc_formc_rollout_ex)."""
         n = len(state)
         plan = np.ascontiguousarray(plan, dtype=np.float64)
         state = state.copy(); walk = walk.copy()
         traj = np.zeros((n, n_ticks, 6)) if want_traj else None
         status = np.zeros(n, dtype=np.int32)
-        rc = self._L.ismpc_formc_rollout(self._h, n, n_ticks, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
-                                         plan.shape[0], _ptr(push), _ptr(traj), _ptr(status), abi.MEM_HOST, None)
-        self._check(rc, "ismpc_formc_rollout")
-        return dict(state=state, walk=walk, traj=traj, status=status)
+        trace = np.zeros((n, n_ticks), dtype=np.int32) if want_trace else None
+        rc = self._L.ismpc_formc_rollout_ex(self._h, n, n_ticks, _ptr(state), _ptr(walk), _ptr(inst), _ptr(plan),
+                                            plan.shape[0], _ptr(push), _ptr(traj), _ptr(status), _ptr(trace),
+                                            abi.MEM_HOST, None)
+        self._check(rc, "ismpc_formc_rollout_ex")
+        return dict(state=state, walk=walk, traj=traj, status=status, trace=trace)
 
     def formc_rollout_raw(self, n, n_ticks, state, walk, inst, plan, plan_rows, push=None, traj=None, status=None,
                           mem=abi.MEM_DEVICE, stream=None):
@@ -253,19 +259,21 @@ class Handle:
         self._check(rc, "ismpc_forma_rollout")
         return dict(inst=inst, fs_plan=fs_plan, traj=traj, status=status)
 
-    def forma_rollout_pred(self, inst, fs_timing, fs_plan, n_ticks, push=None):
-        """forma_rollout that also returns the per-tick predicted footstep (n x n_ticks x 2) for the feet stage."""
+    def forma_rollout_pred(self, inst, fs_timing, fs_plan, n_ticks, push=None, want_trace=False):
+        """forma_rollout that also returns the per-tick predicted footstep (n x n_ticks x 2) for the feet stage and,
+        with want_trace, the per-tick status words (n x n_ticks x 2 int32: x axis, y axis)."""
         n = len(inst)
         inst = inst.copy()
         fs_timing = np.ascontiguousarray(fs_timing, dtype=np.int32)
         fs_plan = np.array(fs_plan, dtype=np.float64)
         traj = np.zeros((n, n_ticks, 6)); pred = np.zeros((n, n_ticks, 2))
         status = np.zeros(n, dtype=np.int32)
-        rc = self._L.ismpc_forma_rollout_ex(self._h, n, n_ticks, _ptr(inst), _ptr(fs_timing), len(fs_timing),
-                                            _ptr(fs_plan), fs_plan.shape[0], _ptr(push), _ptr(traj), _ptr(pred),
-                                            _ptr(status), abi.MEM_HOST, None)
-        self._check(rc, "ismpc_forma_rollout_ex")
-        return dict(inst=inst, fs_plan=fs_plan, traj=traj, pred=pred, status=status)
+        trace = np.zeros((n, n_ticks, 2), dtype=np.int32) if want_trace else None
+        rc = self._L.ismpc_forma_rollout_ex2(self._h, n, n_ticks, _ptr(inst), _ptr(fs_timing), len(fs_timing),
+                                             _ptr(fs_plan), fs_plan.shape[0], _ptr(push), _ptr(traj), _ptr(pred),
+                                             _ptr(status), _ptr(trace), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_forma_rollout_ex2")
+        return dict(inst=inst, fs_plan=fs_plan, traj=traj, pred=pred, status=status, trace=trace)
 
     # ---- batched LIP Kalman filter ------------------------------------------------------------------
     def kf_filter_batch(self, model, state, samples, want_zmp=True):

@@ -53,7 +53,7 @@ struct ismpc_handle {
     DevBuf s_in;                   // [state | walk | inst] of one form-C tick call
     DevBuf s_ainst, s_aout, s_timing, a_Lwork, a_queue;
     DevBuf q_in, q_out, q_work;
-    DevBuf s_pred, f_inst, f_plan, f_out;
+    DevBuf s_pred, f_inst, f_plan, f_out, s_trace;
     cudaStream_t own_stream = nullptr;     // ismpc_handle_stream: created on first use, destroyed with the handle
 };
 
@@ -108,7 +108,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
     cudaSetDevice(h->device);
     DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->c_plan, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout, &h->s_in,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
-                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out};
+                     &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out, &h->s_trace};
     for (DevBuf* b : all) b->release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -239,7 +239,7 @@ static bool formc_use_warp(const ismpc_handle* h)
 // Resident CTAs of the warp kernels are queried once per model (the occupancy query costs microseconds per call).
 static int formc_warp_prepare(ismpc_handle* h, FormCWarpArgs& wa, const FormCArgs& a, int n)
 {
-    if (h->w_res[0] <= 0) formc_warp_resident(h->cm.N, h->sm_count, h->w_res);
+    if (h->w_res[0] <= 0) { const int rrc = formc_warp_resident(h->cm.N, h->sm_count, h->w_res); if (rrc) { h->w_res[0] = 0; return rrc; } }
     int cap = h->w_res[0] > h->w_res[1] ? h->w_res[0] : h->w_res[1];
     if (h->w_res[2] > cap) cap = h->w_res[2];
     if (h->w_res[3] > cap) cap = h->w_res[3];
@@ -269,13 +269,14 @@ static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStr
 }
 
 static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
-                                const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, cudaStream_t st)
+                                const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int32_t* trace,
+                                cudaStream_t st)
 {
-    if (!formc_use_warp(h)) return formc_rollout_launch(a, state_io, walk_io, push, n_ticks, traj, status, n, st);
+    if (!formc_use_warp(h)) return formc_rollout_launch(a, state_io, walk_io, push, n_ticks, traj, status, trace, n, st);
     FormCWarpArgs wa;
     int rc = formc_warp_prepare(h, wa, a, n);
     if (rc) return rc;
-    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, n, h->w_res, h->opt_formc_variant, st);
+    return formc_rollout_warp_launch(wa, state_io, walk_io, push, n_ticks, traj, status, trace, n, h->w_res, h->opt_formc_variant, st);
 }
 
 extern "C" int ismpc_formc_prepare_gait(ismpc_handle* h, int S, int F_ds)
@@ -397,6 +398,15 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
                                    const ismpc_push_t* push, double* traj_opt, int32_t* status_opt, int mem,
                                    void* stream)
 {
+    return ismpc_formc_rollout_ex(h, n, n_ticks, state, walk, inst, plan_xyzt, plan_rows, push, traj_opt, status_opt,
+                                  nullptr, mem, stream);
+}
+
+extern "C" int ismpc_formc_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc_state_t* state, ismpc_walk_t* walk,
+                                      const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
+                                      const ismpc_push_t* push, double* traj_opt, int32_t* status_opt,
+                                      int32_t* status_trace_opt, int mem, void* stream)
+{
     if (!h) return ISMPC_ERR_ARG;
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
     const bool plan_res = plan_xyzt == nullptr;
@@ -411,7 +421,7 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     a.out = nullptr; a.primal = nullptr; a.active = nullptr; a.plan_rows = plan_rows;
     if (mem == ISMPC_MEM_DEVICE) {
         a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt;
-        int rc = formc_launch_rollout(h, a, n, state, walk, push, n_ticks, traj_opt, status_opt, st);
+        int rc = formc_launch_rollout(h, a, n, state, walk, push, n_ticks, traj_opt, status_opt, status_trace_opt, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
         return ISMPC_OK;
@@ -430,6 +440,7 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     if (push && h->s_push.ensure(mb * sizeof(ismpc_push_t))) return ISMPC_ERR_ALLOC;
     if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (status_opt && h->s_status.ensure(mb * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
+    if (status_trace_opt && h->s_trace.ensure((size_t)n * n_ticks * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
     CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
@@ -440,9 +451,11 @@ extern "C" int ismpc_formc_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_st
     int rc = formc_launch_rollout(h, a, n, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr,
-                                  status_opt ? (int32_t*)h->s_status.p : nullptr, st);
+                                  status_opt ? (int32_t*)h->s_status.p : nullptr,
+                                  status_trace_opt ? (int32_t*)h->s_trace.p : nullptr, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
+    if (status_trace_opt) CK(cudaMemcpyAsync(status_trace_opt, h->s_trace.p, (size_t)n * n_ticks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(state, h->s_state.p, n * sizeof(ismpc_state_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(walk, h->s_walk.p, n * sizeof(ismpc_walk_t), cudaMemcpyDeviceToHost, st));
     if (traj_opt) CK(cudaMemcpyAsync(traj_opt, h->s_traj.p, (size_t)n * n_ticks * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -468,7 +481,7 @@ extern "C" int ismpc_forma_set_model(ismpc_handle* h, const ismpc_forma_model_t*
 static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc_forma_inst_t* inst,
                         const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
                         const ismpc_push_t* push, ismpc_forma_out_t* out, double* primal_opt, int8_t* active_opt,
-                        double* traj_opt, double* pred_opt, int32_t* status_opt, int mem, void* stream)
+                        double* traj_opt, double* pred_opt, int32_t* status_opt, int32_t* trace_opt, int mem, void* stream)
 {
     if (!h) return ISMPC_ERR_ARG;
     if (!h->forma_ready) return ISMPC_ERR_MODEL;
@@ -490,7 +503,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     if (mem == ISMPC_MEM_DEVICE) {
         a.inst = inst; a.fs_timing = fs_timing; a.fs_plan = fs_plan; a.out = out; a.primal = primal_opt;
         a.active = (signed char*)active_opt;
-        int rc = rollout ? forma_rollout_launch(a, lp, inst, fs_plan, push, n_ticks, traj_opt, pred_opt, status_opt, st)
+        int rc = rollout ? forma_rollout_launch(a, lp, inst, fs_plan, push, n_ticks, traj_opt, pred_opt, status_opt, trace_opt, st)
                          : forma_tick_launch(a, lp, st);
         h->launches += rollout ? 2 : 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "forma launch");
@@ -507,6 +520,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     if (traj_opt && h->s_traj.ensure((size_t)n * n_ticks * 6 * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (pred_opt && h->s_pred.ensure((size_t)n * n_ticks * 2 * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (status_opt && h->s_status.ensure(mb * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
+    if (trace_opt && h->s_trace.ensure((size_t)n * n_ticks * 2 * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
     CK(cudaMemcpyAsync(h->s_ainst.p, inst, n * sizeof(ismpc_forma_inst_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_timing.p, fs_timing, (size_t)timing_len * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_plan.p, fs_plan, (size_t)plan_rows * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -520,7 +534,8 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
         rc = forma_rollout_launch(a, lp, (ismpc_forma_inst_t*)h->s_ainst.p, (double*)h->s_plan.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr, pred_opt ? (double*)h->s_pred.p : nullptr,
-                                  status_opt ? (int32_t*)h->s_status.p : nullptr, st);
+                                  status_opt ? (int32_t*)h->s_status.p : nullptr,
+                                  trace_opt ? (int32_t*)h->s_trace.p : nullptr, st);
     else
         rc = forma_tick_launch(a, lp, st);
     h->launches += rollout ? 2 : 1;
@@ -531,6 +546,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
         if (traj_opt) CK(cudaMemcpyAsync(traj_opt, h->s_traj.p, (size_t)n * n_ticks * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (pred_opt) CK(cudaMemcpyAsync(pred_opt, h->s_pred.p, (size_t)n * n_ticks * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (status_opt) CK(cudaMemcpyAsync(status_opt, h->s_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (trace_opt) CK(cudaMemcpyAsync(trace_opt, h->s_trace.p, (size_t)n * n_ticks * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     } else {
         CK(cudaMemcpyAsync(out, h->s_aout.p, n * sizeof(ismpc_forma_out_t), cudaMemcpyDeviceToHost, st));
         if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -546,7 +562,7 @@ extern "C" int ismpc_forma_solve_batch(ismpc_handle* h, int n, const ismpc_forma
 {
     return forma_common(h, n, 1, false, const_cast<ismpc_forma_inst_t*>(inst), fs_timing, timing_len,
                         const_cast<double*>(fs_plan), plan_rows, nullptr, out, primal_opt, active_opt, nullptr,
-                        nullptr, nullptr, mem, stream);
+                        nullptr, nullptr, nullptr, mem, stream);
 }
 
 extern "C" int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
@@ -555,7 +571,7 @@ extern "C" int ismpc_forma_rollout(ismpc_handle* h, int n, int n_ticks, ismpc_fo
                                    void* stream)
 {
     return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
-                        nullptr, traj_opt, nullptr, status_opt, mem, stream);
+                        nullptr, traj_opt, nullptr, status_opt, nullptr, mem, stream);
 }
 
 extern "C" int ismpc_forma_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
@@ -564,7 +580,16 @@ extern "C" int ismpc_forma_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc
                                       int32_t* status_opt, int mem, void* stream)
 {
     return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
-                        nullptr, traj_opt, pred_traj_opt, status_opt, mem, stream);
+                        nullptr, traj_opt, pred_traj_opt, status_opt, nullptr, mem, stream);
+}
+
+extern "C" int ismpc_forma_rollout_ex2(ismpc_handle* h, int n, int n_ticks, ismpc_forma_inst_t* inst,
+                                       const int32_t* fs_timing, int timing_len, double* fs_plan, int plan_rows,
+                                       const ismpc_push_t* push, double* traj_opt, double* pred_traj_opt,
+                                       int32_t* status_opt, int32_t* status_trace_opt, int mem, void* stream)
+{
+    return forma_common(h, n, n_ticks, true, inst, fs_timing, timing_len, fs_plan, plan_rows, push, nullptr, nullptr,
+                        nullptr, traj_opt, pred_traj_opt, status_opt, status_trace_opt, mem, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -589,7 +614,7 @@ extern "C" int ismpc_feet_place_rollout(ismpc_handle* h, int n, int n_ticks, con
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (mem == ISMPC_MEM_DEVICE) {
-        int rc = feet_place_launch(n, n_ticks, *model, inst, fs_timing, pred_traj, foot_plan, st);
+        int rc = feet_place_launch(n, n_ticks, *model, inst, fs_timing, timing_len, pred_traj, foot_plan, foot_plan_rows, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_place_launch");
         return ISMPC_OK;
@@ -603,7 +628,7 @@ extern "C" int ismpc_feet_place_rollout(ismpc_handle* h, int n, int n_ticks, con
     CK(cudaMemcpyAsync(h->s_pred.p, pred_traj, bp, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->f_plan.p, foot_plan, bf, cudaMemcpyHostToDevice, st));
     int rc = feet_place_launch(n, n_ticks, *model, (const ismpc_feet_inst_t*)h->f_inst.p, (const int32_t*)h->s_timing.p,
-                               (const double*)h->s_pred.p, (double*)h->f_plan.p, st);
+                               timing_len, (const double*)h->s_pred.p, (double*)h->f_plan.p, foot_plan_rows, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_place_launch");
     CK(cudaMemcpyAsync(foot_plan, h->f_plan.p, bf, cudaMemcpyDeviceToHost, st));
@@ -624,7 +649,7 @@ extern "C" int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (mem == ISMPC_MEM_DEVICE) {
-        int rc = feet_export_launch(n, *model, inst, foot_plan, n_steps, fixed, swing, fl, fr, rl, rr, st);
+        int rc = feet_export_launch(n, *model, inst, foot_plan, foot_plan_rows, n_steps, fixed, swing, fl, fr, rl, rr, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_export_launch");
         return ISMPC_OK;
@@ -637,8 +662,8 @@ extern "C" int ismpc_feet_export(ismpc_handle* h, int n, const ismpc_feet_model_
     CK(cudaMemcpyAsync(h->f_plan.p, foot_plan, bf, cudaMemcpyHostToDevice, st));
     double* o = (double*)h->f_out.p;
     const size_t od = bo / sizeof(double);
-    int rc = feet_export_launch(n, *model, (const ismpc_feet_inst_t*)h->f_inst.p, (const double*)h->f_plan.p, n_steps,
-                                fixed, swing, o, o + od, o + 2 * od, o + 3 * od, st);
+    int rc = feet_export_launch(n, *model, (const ismpc_feet_inst_t*)h->f_inst.p, (const double*)h->f_plan.p,
+                                foot_plan_rows, n_steps, fixed, swing, o, o + od, o + 2 * od, o + 3 * od, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "feet_export_launch");
     CK(cudaMemcpyAsync(fl, o, bo, cudaMemcpyDeviceToHost, st));

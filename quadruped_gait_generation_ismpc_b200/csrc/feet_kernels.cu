@@ -90,12 +90,25 @@ __device__ inline void feet_walk_tick(const ismpc_feet_model_t& p, int counter, 
     }
 }
 
+// A record is used only if its rows lie inside the tables handed to the call (the caller's records are data, not
+// trusted indices): plan rows [plan_first_row, +plan_rows) within foot_plan_rows, timing entries [timing_first,
+// +n_timing) within timing_len, fs_counter >= 1 (1-based).  Anything else is skipped: the placement leaves the plan
+// untouched, the export writes zeros.
+__device__ __forceinline__ bool feet_inst_in_range(const ismpc_feet_inst_t& in, int foot_plan_rows, int timing_len)
+{
+    return in.plan_first_row >= 0 && in.plan_rows >= 0 && (long long)in.plan_first_row + in.plan_rows <= foot_plan_rows &&
+           in.timing_first >= 0 && in.n_timing >= 0 && (long long)in.timing_first + in.n_timing <= timing_len &&
+           in.fs_counter >= 1;
+}
+
 __global__ void feet_place_kernel(int n, int n_ticks, ismpc_feet_model_t mdl, const ismpc_feet_inst_t* inst,
-                                  const int32_t* fs_timing, const double* pred_traj, double* foot_plan)
+                                  const int32_t* fs_timing, int timing_len, const double* pred_traj, double* foot_plan,
+                                  int foot_plan_rows)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const ismpc_feet_inst_t in = inst[i];
+    if (!feet_inst_in_range(in, foot_plan_rows, timing_len)) return;
     const int32_t* ft = fs_timing + in.timing_first;
     double* fp = foot_plan + (size_t)in.plan_first_row * 8;
     int j = in.j, fsc = in.fs_counter;
@@ -114,7 +127,8 @@ __global__ void feet_place_kernel(int n, int n_ticks, ismpc_feet_model_t mdl, co
 }
 
 __global__ void feet_export_kernel(int n, ismpc_feet_model_t mdl, const ismpc_feet_inst_t* inst, const double* foot_plan,
-                                   int n_steps, int fixed, int swing, double* fl, double* fr, double* rl, double* rr)
+                                   int foot_plan_rows, int n_steps, int fixed, int swing, double* fl, double* fr, double* rl,
+                                   double* rr)
 {
     const int per = fixed + swing;
     const long long total = (long long)n * n_steps * per;
@@ -124,10 +138,13 @@ __global__ void feet_export_kernel(int n, ismpc_feet_model_t mdl, const ismpc_fe
     const int k = (int)(gid - (long long)i * n_steps * per);
     const int step = k / per + 1, s = k - (step - 1) * per + 1;        // 1-based step and sample within the step
     const ismpc_feet_inst_t in = inst[i];
-    const double* fp = foot_plan + (size_t)in.plan_first_row * 8;
+    // the export reads plan rows only (no timing table)
+    const bool ok = in.plan_first_row >= 0 && in.plan_rows >= 0 && (long long)in.plan_first_row + in.plan_rows <= foot_plan_rows;
+    const double* fp = foot_plan + (size_t)(ok ? in.plan_first_row : 0) * 8;
     double* dst[4] = {rl, rr, fr, fl};
     int mvA = 0, mvB = 0, kk = 0;                                       // x columns of the swinging feet, swing sample index
-    if (step + 1 <= in.plan_rows) {
+    const bool have = ok && step + 1 <= in.plan_rows;
+    if (have) {
         if (mdl.gait == ISMPC_GAIT_TROT) {
             if (s > fixed) { kk = s - fixed; if (step % 2 == 1) { mvA = 1; mvB = 5; } else { mvA = 7; mvB = 3; } }
         } else {
@@ -140,7 +157,7 @@ __global__ void feet_export_kernel(int n, ismpc_feet_model_t mdl, const ismpc_fe
     for (int f = 0; f < 4; ++f) {
         const int c = 2 * f + 1;
         double x = 0.0, y = 0.0, zz = 0.0;
-        if (step + 1 <= in.plan_rows) {
+        if (have) {
             x = FP(step, c); y = FP(step, c + 1);
             if (c == mvA || c == mvB) {
                 x = FP(step, c) + (FP(step + 1, c) - FP(step, c)) / swing * kk;
@@ -255,18 +272,20 @@ int plan_generate_launch(int n, const ismpc_plan_model_t& m, const ismpc_plan_re
 }
 
 int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const int32_t* fs_timing,
-                      const double* pred_traj, double* foot_plan, cudaStream_t st)
+                      int timing_len, const double* pred_traj, double* foot_plan, int foot_plan_rows, cudaStream_t st)
 {
-    feet_place_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, n_ticks, m, inst, fs_timing, pred_traj, foot_plan);
+    feet_place_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, n_ticks, m, inst, fs_timing, timing_len, pred_traj, foot_plan,
+                                                       foot_plan_rows);
     return (int)cudaGetLastError();
 }
 
-int feet_export_launch(int n, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const double* foot_plan, int n_steps,
-                       int fixed, int swing, double* fl, double* fr, double* rl, double* rr, cudaStream_t st)
+int feet_export_launch(int n, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst, const double* foot_plan,
+                       int foot_plan_rows, int n_steps, int fixed, int swing, double* fl, double* fr, double* rl, double* rr,
+                       cudaStream_t st)
 {
     const long long total = (long long)n * n_steps * (fixed + swing);
     if (total <= 0) return 0;
-    feet_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, m, inst, foot_plan, n_steps, fixed, swing, fl, fr, rl, rr);
+    feet_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, m, inst, foot_plan, foot_plan_rows, n_steps, fixed, swing, fl, fr, rl, rr);
     return (int)cudaGetLastError();
 }
 

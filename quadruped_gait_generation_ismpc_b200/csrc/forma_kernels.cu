@@ -25,10 +25,16 @@ __device__ __forceinline__ long long forma_next_item(int* queue)
 }
 
 // plan rows / timing entries of an instance record inside the tables handed to the call (a step needs two timing entries)
-__device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in, int plan_rows, int timing_len)
+__device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in, const int32_t* fs_timing, int plan_rows,
+                                                    int timing_len)
 {
-    return in.plan_first_row >= 0 && in.n_fs >= 2 && (long long)in.plan_first_row + in.n_fs <= (long long)plan_rows &&
-           in.timing_first >= 0 && in.n_timing >= 2 && (long long)in.timing_first + in.n_timing <= (long long)timing_len;
+    if (!(in.plan_first_row >= 0 && in.n_fs >= 2 && (long long)in.plan_first_row + in.n_fs <= (long long)plan_rows &&
+          in.timing_first >= 0 && in.n_timing >= 2 && (long long)in.timing_first + in.n_timing <= (long long)timing_len))
+        return false;
+    // 1-based counters index ft[idx-1] / plan[(row-1)*2]; the step length ft[1]-ft[0] and ds are divisors
+    if (in.fs_counter < 1 || in.j < 1 || in.ds < 1) return false;
+    const int32_t* ft = fs_timing + in.timing_first;
+    return ft[1] > ft[0];
 }
 
 template <int FT>
@@ -50,7 +56,7 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
         if (item >= 2LL * a.n) break;
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
         const ismpc_forma_inst_t in = a.inst[inst];
-        if (!forma_inst_in_range(in, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
+        if (!forma_inst_in_range(in, a.fs_timing, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
             if (lane == 0) atomicOr(&a.out[inst].status, (int)ISMPC_ST_QP_FAIL);
             continue;
         }
@@ -92,6 +98,7 @@ struct FormARolloutArgs {
     double* traj;
     double* pred;          // nullable, n x n_ticks x 2: predicted footstep handed to the second QP
     int32_t* status;
+    int32_t* trace;        // nullable, n x n_ticks x 2: status of every tick, per axis (x, y)
 };
 
 template <int FT>
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_roll
         if (item >= 2LL * a.n) break;
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
         const ismpc_forma_inst_t in = ra.inst_io[inst];
-        if (!forma_inst_in_range(in, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
+        if (!forma_inst_in_range(in, a.fs_timing, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
             if (lane == 0 && ra.status) atomicOr(&ra.status[inst], (int)ISMPC_ST_QP_FAIL);
             continue;
         }
@@ -129,8 +136,10 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_roll
         for (int tick = 0; tick < ra.n_ticks; ++tick) {
             if (fsc == pu.fs && ct >= pu.ct0 && ct < pu.ct1) s3[1] += a.model.dt * (axis == 0 ? pu.ax : pu.ay); // bang.m:104-114
             int iters; double kkt;
-            acc |= forma_tick_axis<FT>(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis,
-                                       a.warm_start && tick > 0, a.use_pdas, rg, &iters, &kkt);
+            const int tick_status = forma_tick_axis<FT>(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis,
+                                                        a.warm_start && tick > 0, a.use_pdas, rg, &iters, &kkt);
+            acc |= tick_status;
+            if (ra.trace && lane == 0) ra.trace[((size_t)inst * ra.n_ticks + tick) * 2 + axis] = tick_status;
             const double zd0 = sm.x[0], pred = sm.x[C];
             __syncwarp();
             forma_integrate(eta, a.model.dt, s3, zd0);
@@ -175,7 +184,7 @@ __global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ismpc_forma_inst_t* io = inst_io + i;
-    if (!forma_inst_in_range(*io, plan_rows, timing_len)) return;     // the rollout kernel flagged and skipped it
+    if (!forma_inst_in_range(*io, fs_timing, plan_rows, timing_len)) return;     // the rollout kernel flagged and skipped it
     const int32_t* ft = fs_timing + io->timing_first;
     int j = io->j, fsc = io->fs_counter, first_ramp = io->cl_first_ramp;
     for (int tick = 0; tick < n_ticks; ++tick) {
@@ -236,7 +245,7 @@ int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStrea
 
 int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_forma_inst_t* inst_io,
                          double* fs_plan_io, const ismpc_push_t* push, int n_ticks, double* traj, double* pred,
-                         int32_t* status, cudaStream_t st)
+                         int32_t* status, int32_t* trace, cudaStream_t st)
 {
     FormAArgs a = a_in;
     a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = p.warm_start;
@@ -245,7 +254,7 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
-    FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status};
+    FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status, trace};
     kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
     forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing, a.plan_rows, a.timing_len);
     return (int)cudaGetLastError();

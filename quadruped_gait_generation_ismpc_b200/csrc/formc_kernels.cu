@@ -245,6 +245,7 @@ struct FormCRolloutArgs {
     int n_ticks;
     double* traj;               // nullable, n x n_ticks x 6
     int32_t* status;            // nullable
+    int32_t* trace;             // nullable, n x n_ticks: status of every tick
 };
 
 // Closed loop: the CTA keeps its instance and advances it n_ticks times (Controller::update bookkeeping,
@@ -270,7 +271,7 @@ formc_rollout_kernel(FormCRolloutArgs ra)
         const double* plan_t = a.plan + (size_t)in.plan_first_row * 4;
         for (int tick = 0; tick < ra.n_ticks; ++tick) {
             // footstep switch (Controller.cpp:297-302, enabled)
-            if (wk.footstep_counter < in.n_steps &&
+            if (wk.footstep_counter >= 0 && wk.footstep_counter < in.n_steps &&
                 wk.sim_time >= plan_t[(size_t)wk.footstep_counter * 4 + 3] - 1.0) {
                 wk.control_iter = 0; wk.mpc_iter = 0; wk.footstep_counter += 1; wk.support_foot = !wk.support_foot;
             }
@@ -281,6 +282,7 @@ formc_rollout_kernel(FormCRolloutArgs ra)
             __syncthreads();
             st = s_out.next;
             acc_status |= s_out.status;
+            if (ra.trace && threadIdx.x == 0) ra.trace[(size_t)inst * ra.n_ticks + tick] = s_out.status;
             if (ra.traj && threadIdx.x < 6) {
                 double v = threadIdx.x < 3 ? st.com_pos[threadIdx.x] : st.com_vel[threadIdx.x - 3];
                 ra.traj[((size_t)inst * ra.n_ticks + tick) * 6 + threadIdx.x] = v;
@@ -331,11 +333,11 @@ int formc_tick_launch(const FormCArgs& a, int grid, int cluster_size, cudaStream
 }
 
 int formc_rollout_launch(const FormCArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,
-                         int n_ticks, double* traj, int32_t* status, int grid, cudaStream_t st)
+                         int n_ticks, double* traj, int32_t* status, int32_t* trace, int grid, cudaStream_t st)
 {
     size_t smem = formc_smem_bytes(a.model.N);
     cudaFuncSetAttribute(formc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    FormCRolloutArgs ra{a, state_io, walk_io, push, n_ticks, traj, status};
+    FormCRolloutArgs ra{a, state_io, walk_io, push, n_ticks, traj, status, trace};
     formc_rollout_kernel<<<grid, FORMC_THREADS, smem, st>>>(ra);
     return (int)cudaGetLastError();
 }

@@ -176,7 +176,7 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
 // shared memory (Controller::update bookkeeping as in formc_rollout_warp_kernel).
 __global__ void __launch_bounds__(64, 7)
 formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,
-                          int n_ticks, double* traj, int32_t* status_out)
+                          int n_ticks, double* traj, int32_t* status_out, int32_t* trace)
 {
     extern __shared__ __align__(16) double smem_d[];
     const FormCArgs& a = wa.base;
@@ -199,7 +199,7 @@ formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
         const double* plan_t = a.plan + (size_t)in.plan_first_row * 4;
 #pragma unroll 1
         for (int tick = 0; tick < n_ticks; ++tick) {
-            if (wk.footstep_counter < in.n_steps &&
+            if (wk.footstep_counter >= 0 && wk.footstep_counter < in.n_steps &&
                 wk.sim_time >= __ldg(plan_t + (size_t)wk.footstep_counter * 4 + 3) - 1.0) {      // Controller.cpp:297-302
                 wk.control_iter = 0; wk.mpc_iter = 0; wk.footstep_counter += 1; wk.support_foot = !wk.support_foot;
             }
@@ -217,6 +217,7 @@ formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
             st.com_pos[0] = hand[0]; st.com_pos[1] = hand[1]; st.com_pos[2] = hand[2];
             st.com_vel[0] = hand[3]; st.com_vel[1] = hand[4]; st.com_vel[2] = hand[5];
             acc_status |= (int)hand[6];
+            if (trace && threadIdx.x == 0) trace[(size_t)inst * n_ticks + tick] = (int)hand[6];
             if (traj && threadIdx.x < 6) traj[((size_t)inst * n_ticks + tick) * 6 + threadIdx.x] = hand[threadIdx.x];
             pair_barrier();                                      // everyone has read the hand-over before it is rewritten
             wk.control_iter += 1;                                                    // Controller.cpp:503
@@ -234,7 +235,7 @@ formc_rollout_pair_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
 // Controller.cpp:297-302 with the footstep switch enabled, :503-504).
 __global__ void __launch_bounds__(32, 1)
 formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_t* walk_io, const ismpc_push_t* push,
-                          int n_ticks, double* traj, int32_t* status_out)
+                          int n_ticks, double* traj, int32_t* status_out, int32_t* trace)
 {
     extern __shared__ __align__(16) double smem_d[];
     const FormCArgs& a = wa.base;
@@ -255,7 +256,7 @@ formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
         const double* plan_t = a.plan + (size_t)in.plan_first_row * 4;
 #pragma unroll 1
         for (int tick = 0; tick < n_ticks; ++tick) {
-            if (wk.footstep_counter < in.n_steps &&
+            if (wk.footstep_counter >= 0 && wk.footstep_counter < in.n_steps &&
                 wk.sim_time >= __ldg(plan_t + (size_t)wk.footstep_counter * 4 + 3) - 1.0) {      // Controller.cpp:297-302
                 wk.control_iter = 0; wk.mpc_iter = 0; wk.footstep_counter += 1; wk.support_foot = !wk.support_foot;
             }
@@ -266,6 +267,7 @@ formc_rollout_warp_kernel(FormCWarpArgs wa, ismpc_state_t* state_io, ismpc_walk_
             formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r, nullptr, nullptr, parity);
             st = r.next;
             acc_status |= r.status;
+            if (trace && lane == 0) trace[(size_t)inst * n_ticks + tick] = r.status;
             if (traj && lane < 6) {
                 double v = st.com_pos[0];
                 v = lane == 1 ? st.com_pos[1] : v; v = lane == 2 ? st.com_pos[2] : v;
@@ -294,33 +296,36 @@ int formc_warp_supported(int N) { return N >= 2 && N <= ISMPC_MAX_N; }
 // batches: 65,536 instances run 1.25x faster than with <1>).  variant 0 = pick by batch size, 2 = pair.
 // (the variant is per handle: ismpc_set_option("formc_variant"), passed down with every launch)
 
-// The dynamic shared-memory limit is a per-device function attribute: set it whenever a handle queries residency (once
-// per handle and model), on that handle's device -- no process-wide cache, handles on several devices or threads are fine.
-static void formc_warp_configure(size_t smem)
+// The dynamic shared-memory limit is an attribute of the FUNCTION on a device, not of a handle: two handles on one
+// device with different horizons would otherwise lower each other's limit.  It is therefore always set to what the
+// largest supported horizon (ISMPC_MAX_N) needs -- the limit only gates launches, residency follows the size actually
+// requested at launch.  Returns the first CUDA error.
+static int formc_warp_configure()
 {
-    {
-        cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(formc_tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(smem + FORMC_PAIR_RED * sizeof(double)));
-        cudaFuncSetAttribute(formc_rollout_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(smem + FORMC_PAIR_RED * sizeof(double)));
-    }
+    const size_t smem = formc_warp_smem_bytes(ISMPC_MAX_N), pair = formc_pair_smem_bytes(ISMPC_MAX_N);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_rollout_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
+    return 0;
 }
 
 // CTAs (= warps = instances in flight) the GPU keeps resident: res[0] for the tick kernel <1>, res[1] for <16>,
 // res[2] for the rollout kernel, res[3] for the pair tick kernel, res[4] for the pair rollout kernel.
-void formc_warp_resident(int N, int sm_count, int res[5])
+int formc_warp_resident(int N, int sm_count, int res[5])
 {
     const size_t smem = formc_warp_smem_bytes(N);
-    formc_warp_configure(smem);
+    const int rc = formc_warp_configure();
+    if (rc) return rc;
     int b = 0;
     res[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<1>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[2] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_warp_kernel, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[3] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[4] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    return 0;
 }
 
 // One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
@@ -344,18 +349,18 @@ int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int 
 }
 
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
-                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int n, const int res[5],
-                              int variant, cudaStream_t st)
+                              const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int32_t* trace, int n,
+                              const int res[5], int variant, cudaStream_t st)
 {
     if (variant == 2 || (variant == 0 && n <= res[4])) {
         const int grid = n < res[4] ? n : res[4];
         formc_rollout_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
-                                                                                           traj, status);
+                                                                                           traj, status, trace);
         return (int)cudaGetLastError();
     }
     const int grid = n < res[2] ? n : res[2];
     formc_rollout_warp_kernel<<<grid, 32, formc_warp_smem_bytes(a.base.model.N), st>>>(a, state_io, walk_io, push, n_ticks,
-                                                                                      traj, status);
+                                                                                      traj, status, trace);
     return (int)cudaGetLastError();
 }
 

@@ -9,14 +9,33 @@ from parity import PRIMAL_TOL, primal_rel_err, active_set_mismatch
 pytestmark = pytest.mark.gpu
 
 
-def _compare(handle, model, state, walk, inst, plan, nthreads=8):
+FAIL_BITS = (abi.ST_Z_FAIL, abi.ST_X_FAIL, abi.ST_Y_FAIL)
+
+
+def _status_parity(g_status, o_ret):
+    """SURVEY App. C.3 (iii) made exact: QP by QP (z, x, y) the GPU flags a failure exactly where the reference's qpOASES
+    call returns non-zero (the code utils.cpp:128 drops).  If the vertical QP fails the horizontal ones have no lambda
+    to be built from, so they are only compared where z solved."""
+    zfail = o_ret[:, 0] != 0
+    assert np.array_equal((g_status & abi.ST_Z_FAIL) != 0, zfail), "vertical QP: status differs from the oracle's return code"
+    for k in (1, 2):
+        gk = (g_status & FAIL_BITS[k]) != 0
+        ok_ = o_ret[:, k] != 0
+        bad = np.nonzero((gk != ok_) & ~zfail)[0]
+        assert len(bad) == 0, "QP %d: GPU status and oracle return code differ on instances %s" % (k, bad[:10])
+
+
+def _compare(handle, model, state, walk, inst, plan, nthreads=8, oracle_failures=0):
+    """oracle_failures: the number of instances of THIS input on which qpOASES returns non-zero (measured once on the CPU,
+    deterministic); more than that fails the test, and the GPU must flag exactly those instances, QP by QP."""
     handle.formc_set_model(model)
     g = handle.formc_solve_batch(state, walk, inst, plan)
     o = O.formc_batch(model, state, walk, inst, plan, nthreads=nthreads)
     N = int(model["N"][0])
     ok = (o["ret"] == 0).all(axis=1) & (o["out"]["status"] & abi.ST_WINDOW == 0)
-    assert ok.sum() >= 0.8 * len(state), "too many oracle failures: %d of %d" % ((~ok).sum(), len(state))
-    # GPU must flag the instances the oracle found infeasible as failed too (no silent garbage)
+    assert (~ok).sum() <= oracle_failures, "oracle failures: %d of %d (expected %d)" % ((~ok).sum(), len(state), oracle_failures)
+    assert np.array_equal(g["out"]["status"] & abi.ST_WINDOW, o["out"]["status"] & abi.ST_WINDOW)
+    _status_parity(g["out"]["status"], o["ret"])
     gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
     assert not gfail[ok].any(), "GPU failed on instances the oracle solved: %s" % np.nonzero(gfail & ok)[0][:10]
     err = primal_rel_err(g["primal"][ok].reshape(-1, 3, N), o["primal"][ok].reshape(-1, 3, N))
@@ -36,11 +55,12 @@ def _compare(handle, model, state, walk, inst, plan, nthreads=8):
 
 
 def test_reference_instance_closed_loop(handle):
-    """Config 1: the DART app's single instance, 60 closed-loop ticks, oracle in lock-step from the GPU state."""
+    """Config 1: the DART app's single instance, 1,000 closed-loop ticks k0 = 0..999, oracle in lock-step
+    from the GPU state; primal 1e-6 and identical active set on every tick."""
     model = abi.formc_model()
     state, walk, inst, plan = synth.reference_formc_instance()
     handle.formc_set_model(model)
-    for k in range(60):
+    for k in range(1000):
         walk["sim_time"] = k; walk["mpc_iter"] = k % 45; walk["control_iter"] = k % 45
         g = handle.formc_solve_batch(state, walk, inst, plan)
         o = O.formc_batch(model, state, walk, inst, plan)
@@ -54,13 +74,13 @@ def test_reference_instance_closed_loop(handle):
 def test_config2_batch_1024(handle):
     """Config 2: 1,024 randomised trot instances, N=100."""
     state, walk, inst, plan = synth.formc_batch(1024)
-    _compare(handle, abi.formc_model(), state, walk, inst, plan)
+    _compare(handle, abi.formc_model(), state, walk, inst, plan, oracle_failures=1)
 
 
 def test_vertical_inequalities_active(handle):
     """CoM well above / below the target height so that rows of 0 <= S_bar_z f <= 1e4 become active."""
     state, walk, inst, plan = synth.formc_batch(256, seed=77, z_spread=0.08)
-    g, o, ok = _compare(handle, abi.formc_model(), state, walk, inst, plan)
+    g, o, ok = _compare(handle, abi.formc_model(), state, walk, inst, plan, oracle_failures=2)
     assert (o["active"][ok][:, :100] != 0).any(), "test is vacuous: no vertical row active"
 
 
@@ -149,7 +169,7 @@ def test_prepared_gait_equals_generic_path(handle):
     handle.formc_prepare_gait(35, 10)
     p = handle.formc_solve_batch(state, walk, inst, plan)
     ok = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
-    assert ok.mean() > 0.7
+    assert (~ok).sum() <= 1          # qpOASES finds one x QP of this input infeasible (measured on the CPU oracle)
     assert np.array_equal(g["out"]["status"], p["out"]["status"])
     assert primal_rel_err(p["primal"][ok].reshape(-1, 3, 100), g["primal"][ok].reshape(-1, 3, 100)).max() <= 1e-9
     assert np.array_equal(p["active"][ok], g["active"][ok])
@@ -187,7 +207,7 @@ def test_warp_per_instance_equals_cta_per_instance(handle, N):
     for b in res:
         assert np.array_equal(a["out"]["status"], b["out"]["status"])
         ok = (a["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) == 0
-        assert ok.mean() > 0.7
+        assert (~ok).sum() <= {50: 3, 100: 1}.get(N, 0)      # instances qpOASES finds infeasible on these inputs
         # H_z loses digits with the horizon (cond ~ N^4): at N = 400 the explicit H_z^-1 table is good to ~1e-8 only
         tol = 1e-9 if N <= 200 else 1e-7
         assert primal_rel_err(b["primal"][ok].reshape(-1, 3, N), a["primal"][ok].reshape(-1, 3, N)).max() <= tol
@@ -240,16 +260,17 @@ def test_uneven_ground(handle):
     model = abi.formc_model()
     handle.formc_set_model(model)
     handle.formc_prepare_gait(35, 10)
-    _compare_prepared(handle, model, state, walk, inst, plan)
+    _compare_prepared(handle, model, state, walk, inst, plan, oracle_failures=1)
 
 
-def _compare_prepared(handle, model, state, walk, inst, plan):
+def _compare_prepared(handle, model, state, walk, inst, plan, oracle_failures=0):
     """_compare without resetting the model (keeps the prepared gait)."""
     g = handle.formc_solve_batch(state, walk, inst, plan)
     o = O.formc_batch(model, state, walk, inst, plan, nthreads=8)
     N = int(model["N"][0])
     ok = (o["ret"] == 0).all(axis=1) & (o["out"]["status"] & abi.ST_WINDOW == 0)
-    assert ok.sum() >= 0.7 * len(state)
+    assert (~ok).sum() <= oracle_failures
+    _status_parity(g["out"]["status"], o["ret"])
     gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
     assert not gfail[ok].any()
     err = primal_rel_err(g["primal"][ok].reshape(-1, 3, N), o["primal"][ok].reshape(-1, 3, N))
@@ -290,7 +311,7 @@ def test_ragged_and_maximum_horizons(handle, N):
     n = 24 if N < 512 else 6
     steps = (2 * N + 900) // 45 + 3
     state, walk, inst, plan = synth.formc_batch(n, seed=7 * N, N=N, n_steps=steps)
-    _compare(handle, abi.formc_model(N=N), state, walk, inst, plan)
+    _compare(handle, abi.formc_model(N=N), state, walk, inst, plan, oracle_failures=3 if N == 37 else 0)
 
 
 def test_other_step_timing_and_raised_ground(handle):
@@ -326,6 +347,7 @@ def test_window_reaching_the_last_step(handle):
     ok = (o["ret"] == 0).all(axis=1)
     gfail = (g["out"]["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL)) != 0
     assert not gfail[ok].any()
+    _status_parity(g["out"]["status"], o["ret"])         # "fail together": QP by QP
     assert ok.sum() >= 8, "test is vacuous: the oracle solved %d instances" % ok.sum()
     err = primal_rel_err(g["primal"][ok].reshape(-1, 3, 100), o["primal"][ok].reshape(-1, 3, 100))
     assert err.max() <= PRIMAL_TOL
