@@ -142,7 +142,8 @@ int oracle_qp_dual_active_set(int nV, int nC, const double* H, const double* g,
                     double t = u[a] / r[a];
                     if (t < t1) { t1 = t; l = a; }
                 }
-            int dependent = !(zn > 1e-13 * fmax(npd, 1e-300));
+            /* nV independent rows span the space: whatever rounding leaves in zn, the next row depends on them */
+            int dependent = q >= maxq || !(zn > 1e-13 * fmax(npd, 1e-300));
             double sviol = dotn(nV, np, x) - beta; /* <0 when violated */
             double t2 = dependent ? INF : (-sviol / zn);
             if (!dependent && t2 < 0.0) t2 = 0.0;
@@ -153,7 +154,11 @@ int oracle_qp_dual_active_set(int nV, int nC, const double* H, const double* g,
             }
             double t = t1 < t2 ? t1 : t2;
             if (t >= INF) { ret = -2; goto done; } /* infeasible */
-            if (!dependent) for (int k = 0; k < nV; ++k) x[k] += t * z[k];
+            if (!dependent && t > 0.0) {
+                for (int k = 0; k < nV; ++k) x[k] += t * z[k];
+                /* rows set aside as dependent-and-satisfied were judged at the old x: look at them again */
+                for (int i = 0; i < nC; ++i) if (state[i] == 2) state[i] = 0;
+            }
             for (int a = 0; a < q; ++a) u[a] -= t * r[a];
             up += t;
             if (!dependent && t2 <= t1) {
@@ -185,6 +190,16 @@ int oracle_qp_dual_active_set(int nV, int nC, const double* H, const double* g,
         (void)viol;
     }
 done:
+    /* A return code of 0 must mean "this point is feasible": on infeasible problems the working set fills up to nV rows,
+     * the Schur complement turns singular and rounding can carry the iteration to a point that violates rows it holds
+     * active (qpOASES reports RET_INIT_FAILED_* on the same problems).  Checked on every row, equalities included. */
+    if (ret == 0) {
+        for (int i = 0; i < nC; ++i) {
+            double ax = dotn(nV, A + (size_t)i * nV, x);
+            double sc = fmax(1.0, fmax(fabs(lbA[i]) < 1e19 ? fabs(lbA[i]) : 0.0, fabs(ubA[i]) < 1e19 ? fabs(ubA[i]) : 0.0));
+            if ((lbA[i] > -1e19 && lbA[i] - ax > 1e-7 * sc) || (ubA[i] < 1e19 && ax - ubA[i] > 1e-7 * sc)) { ret = -2; break; }
+        }
+    }
     if (ws) for (int i = 0; i < nC; ++i) ws[i] = 0;
     if (y) for (int i = 0; i < nC; ++i) y[i] = 0.0;
     for (int a = 0; a < q; ++a) {

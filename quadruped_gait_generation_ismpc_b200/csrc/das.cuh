@@ -225,7 +225,20 @@ __device__ int das_solve(P& prob, DasWork& w, double* x, double* rv, double* z, 
         }
         warp_argmin(best, bidx);
         tm.lap(1);
-        if (bidx == 0x7fffffff) break;   // primal feasible -> optimal
+        if (bidx == 0x7fffffff) {        // no free row violated -> optimal, PROVIDED the rows held active are where they belong
+            // On an infeasible QP the working set fills up to nvar rows, S turns singular, and rounding can carry the
+            // iteration to a point that leaves rows it holds active (seen on formulation A with tight kinematic rows:
+            // qpOASES returns RET_INIT_FAILED_*, this loop used to end here with rc = 0).  rv is current: check them.
+            int off = 0;
+            for (int i = lane; i < m; i += 32) {
+                const int s0 = w.state[i];
+                if (s0 == 0) continue;
+                const double b = s0 < 0 ? prob.lo(i) : prob.hi(i);
+                off |= fabs(rv[i] - b) > 1e-7 * (1.0 + fabs(b));
+            }
+            if (__any_sync(ISMPC_FULL_MASK, off)) rc = 1;
+            break;
+        }
         const int p = bidx >> 1;
         const int sgp = (bidx & 1) ? -1 : +1;
         double sviol = best;             // n_p' x - beta_p  (< 0)
@@ -248,7 +261,8 @@ __device__ int das_solve(P& prob, DasWork& w, double* x, double* rv, double* z, 
                 if (rk > 1e-14) { double t = w.mu[k] / rk; if (t < t1) { t1 = t; l = k; } }
             }
             warp_argmin(t1, l);
-            const bool dependent = !(zn > 1e-13 * spp);
+            // (nvar independent rows span the space: whatever rounding leaves in zn, a further row depends on them)
+            const bool dependent = w.q >= n || !(zn > 1e-13 * spp);
             double t2 = dependent ? 1e300 : fmax(0.0, -sviol / zn);
             double t = fmin(t1, t2);
             if (t >= 1e300) { rc = 1; goto done; }   // infeasible

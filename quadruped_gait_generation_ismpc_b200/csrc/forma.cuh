@@ -723,6 +723,8 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
         eqv = warp_sum(eqv);
         for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
         viol = warp_max(viol);
+        // a point that misses the stability row or a bound is not a solution, whatever the loop returned
+        if (!(fabs(eqv - beq) <= 1e-7 * fmax(1.0, fabs(beq))) || !(viol <= 1e-7)) status |= ISMPC_ST_QP_FAIL;
     }
     *iters_out = iters;
     *kkt_out = fmax(fabs(eqv - beq), fmax(viol, 0.0));

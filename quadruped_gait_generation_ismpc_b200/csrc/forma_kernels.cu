@@ -254,6 +254,7 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
+    if (trace) cudaMemsetAsync(trace, 0, (size_t)a.n * n_ticks * 2 * sizeof(int32_t), st);   // skipped records write nothing
     FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status, trace};
     kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(ra);
     forma_rollout_fold<<<(a.n + 127) / 128, 128, 0, st>>>(a.n, n_ticks, inst_io, a.fs_timing, a.plan_rows, a.timing_len);

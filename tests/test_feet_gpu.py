@@ -116,3 +116,42 @@ def test_plan_generators_on_device(handle, gait):
             assert np.abs(fp[i] - rfp).max() <= 1e-13, (gait, N_gait, i)
             m = min(len(ce[i]), len(rce))
             assert np.abs(ce[i][:m] - rce[:m]).max() <= 1e-12, (gait, N_gait, i)
+
+
+@pytest.mark.parametrize("gait", ["trot", "walk"])
+def test_out_of_range_feet_records_are_skipped_not_read(handle, gait):
+    """Records whose plan rows or timing entries lie outside the tables handed to the call (or whose 1-based footstep
+    counter is < 1) are skipped: the placement leaves their plan rows -- and everybody else's -- as they would be without
+    them, the export writes zeros for them; nothing is read or written out of bounds."""
+    phis = [0.0, np.pi / 4, np.pi / 2, 0.3, 0.0, 0.7]
+    if gait == "walk":
+        inst, finst, ft, center, foot = _instances("walk", phis, 0.1, 50, 30, 2321)
+        model, T, n_steps, fixed, swing = abi.forma_model(q_foot=1e9), 230, 8, 0, 50
+    else:
+        inst, finst, ft, center, foot = _instances("trot", phis, 0.12, 50, 20, 2321)
+        model, T, n_steps, fixed, swing = abi.forma_model(), 230, 5, 20, 30
+    handle.forma_set_model(model)
+    r = handle.forma_rollout_pred(inst, ft, center, T)
+    fm = abi.feet_model(gait)
+    good = handle.feet_place_rollout(fm, finst, ft, r["pred"], foot)
+    ex_good = handle.feet_export(fm, finst, good, n_steps, fixed, swing)
+    bad = finst.copy()
+    bad["plan_first_row"][1] = foot.shape[0] - 3            # rows run off the end of the table
+    bad["plan_first_row"][2] = -7                           # negative
+    bad["timing_first"][3] = len(ft) - 2                    # timing entries run off the end
+    bad["fs_counter"][4] = 0                                # 1-based counter below 1
+    skipped = [1, 2, 3, 4]
+    out = handle.feet_place_rollout(fm, bad, ft, r["pred"], foot)
+    for i in range(len(phis)):
+        a = finst["plan_first_row"][i]; b = a + finst["plan_rows"][i]
+        if i in skipped:
+            assert np.array_equal(out[a:b], foot[a:b]), "instance %d was skipped but its rows changed" % i
+        else:
+            assert np.array_equal(out[a:b], good[a:b]), "instance %d is valid but differs" % i
+    ex = handle.feet_export(fm, bad, good, n_steps, fixed, swing)
+    for k in ("fl", "fr", "rl", "rr"):
+        for i in range(len(phis)):
+            if i in (1, 2):                                  # the export reads plan rows only
+                assert not ex[k][i].any()
+            else:
+                assert np.array_equal(ex[k][i], ex_good[k][i])

@@ -327,3 +327,27 @@ def test_horizontal_qp_is_a_knapsack_problem():
             worst_passes = max(worst_passes, passes)
     assert n_sat >= 25, "vacuous: too few saturated instances"
     assert worst_passes <= 6
+
+
+def test_portable_solver_on_infeasible_qps():
+    """The portable dual active set reports infeasible QPs as such (never a buffer overrun, never ret = 0 with a point that
+    violates its rows) and agrees with qpOASES' return code where oracle/_ref is present."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_qp_dense_gpu import _infeasible_batch
+    H, g, A, lb, ub = _infeasible_batch()
+    p = O.qp_batch(H, g, A, lb, ub, solver=O.SOLVER_PORT)
+    assert (p["ret"][0::2] != 0).all() and (p["ret"][1::2] == 0).all(), p["ret"]
+    if O.have_ref():
+        q = O.qp_batch(H, g, A, lb, ub, solver=O.SOLVER_QPOASES, kind="ref")
+        assert np.array_equal(q["ret"] != 0, p["ret"] != 0)
+        ok = p["ret"] == 0
+        assert np.abs(q["x"][ok] - p["x"][ok]).max() < 1e-7
+    # formulation A with footsteps that may hardly move and a CoM velocity no ZMP in the box can catch: infeasible
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    model = abi.forma_model(disp_forw=0.06, disp_forw_dummy=0.03, disp_L=0.05)
+    inst, ft, plan = synth.forma_batch(4, gait="trot", seed=61)
+    inst["st"][:, 1] += 0.5; inst["st"][:, 4] += 0.5
+    for solver in ([O.SOLVER_PORT, O.SOLVER_QPOASES] if O.have_ref() else [O.SOLVER_PORT]):
+        o = O.forma_batch(model, inst, ft, plan, solver=solver, nthreads=4)
+        assert (o["ret"] != 0).all(), (solver, o["ret"])

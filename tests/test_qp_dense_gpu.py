@@ -135,3 +135,34 @@ def test_unconstrained_and_infeasible(handle):
     r2 = handle.qp_solve_batch(H, g, A, lb2, ub2)
     assert (r2["status"] == 0).all()
     np.testing.assert_allclose(r2["x"], -np.linalg.solve(H, g[..., None])[..., 0], rtol=1e-9, atol=1e-10)
+
+
+def _infeasible_batch(seed=17, n=32, nV=14, nC=24):
+    """Strictly convex QPs of which every second one is infeasible: two parallel rows with disjoint intervals, and for
+    a few a whole cone of rows that pushes the working set to nV rows before the contradiction shows."""
+    rng = np.random.default_rng(seed)
+    M = rng.normal(size=(n, nV, nV))
+    H = M @ M.transpose(0, 2, 1) / nV + np.eye(nV)
+    g = rng.normal(size=(n, nV)); A = rng.normal(size=(n, nC, nV))
+    x0 = rng.normal(size=(n, nV))
+    ax = np.einsum("nij,nj->ni", A, x0)
+    lb = ax - rng.uniform(0.1, 1.0, size=(n, nC)); ub = ax + rng.uniform(0.1, 1.0, size=(n, nC))
+    for i in range(0, n, 2):
+        A[i, -1] = A[i, 3]
+        lb[i, -1] = ub[i, 3] + 0.5; ub[i, -1] = ub[i, 3] + 1.0          # row 3 and the last row cannot both hold
+        if i % 4 == 0:                                                   # tight box on every variable first
+            A[i, :nV] = np.eye(nV); lb[i, :nV] = x0[i] - 1e-3; ub[i, :nV] = x0[i] + 1e-3
+            A[i, -1] = 1.0; lb[i, -1] = x0[i].sum() + 1.0; ub[i, -1] = x0[i].sum() + 2.0
+    return H, g, A, lb, ub
+
+
+def test_infeasible_dense_qps_are_flagged_like_qpoases(handle):
+    """The return code utils.cpp:128 drops: on infeasible QPs qpOASES' init fails; the GPU seam must flag exactly those
+    problems (ISMPC_ST_QP_FAIL) and solve the rest to 1e-6."""
+    H, g, A, lb, ub = _infeasible_batch()
+    r = handle.qp_solve_batch(H, g, A, lb, ub)
+    o = O.qp_batch(H, g, A, lb, ub, nthreads=8)
+    assert (o["ret"][0::2] != 0).all() and (o["ret"][1::2] == 0).all(), o["ret"]
+    assert np.array_equal(r["status"] != 0, o["ret"] != 0), (r["status"], o["ret"])
+    ok = o["ret"] == 0
+    assert primal_rel_err(r["x"][ok], o["x"][ok]).max() <= PRIMAL_TOL
