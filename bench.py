@@ -114,6 +114,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(n):
+    """`config` of both arms (this repo's and --impl reference): the same dict, so that the driver's same_config holds."""
+    return {"workload": "formC_tick_trot_1024xN100", "instances_per_gpu": n, "horizon_N": HORIZON,
+            "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)",
+            "launch": "GPU arm: CUDA graph of the K steps (one kernel node per step), replayed once per timed repeat; "
+                      "the median of the repeats is reported, every repeat beside it (`repeats`)",
+            "l2": "GPU arm: a 256 MB buffer is written before every timed repeat (L2 = 126 MB flushed), and the K steps "
+                  "of a repeat read K distinct device batches (1.6 MB each) that no earlier launch of the repeat touched"}
+
+
 def cpu_reference_run(steps, warmup, sample_n=None, threads=None):
     """The reference's CPU implementation of the path: restated builders + the reference's qpOASES with the
     solveQP call form (oracle/_ref), every host thread, one cold QProblem per solve per thread."""
@@ -138,19 +148,26 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each step is a bounded sample (256 of the 1,024 instances) so that K steps finish within minutes
-    qps, per_step, threads, kind, n, nfail = cpu_reference_run(args.steps, args.warmup, sample_n=256)
+    # every step is one pass over ALL 1,024 instances of the workload (~0.25 s on 16 threads): the same config as the
+    # GPU arm; K steps + W warm-up passes over 64 instances finish within seconds
+    qps, per_step, threads, kind, n, nfail = cpu_reference_run(args.steps, args.warmup, sample_n=args.batch)
     line = {"impl": "reference", "metric": "batched ISMPC QP solves/sec", "value": qps, "unit": "QP solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "formC_tick_trot_1024xN100", "instances": n, "horizon_N": HORIZON,
-                       "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)"},
+            "config": workload_config(n),
             "cpu_baseline": {"value": qps, "unit": "QP solves/s", "cores": threads, "kind": kind,
-                             "sample": "%d instances x %d steps, all %d host threads, cold qpOASES QProblem per solve"
-                                       % (n, args.steps, threads), "failed_instances": nfail},
+                             "sample": "all %d instances x %d steps, all %d host threads, cold qpOASES QProblem per solve "
+                                       "(utils.cpp:121-130); constructor matrices built once per model (MPCSolver.cpp:144-156), "
+                                       "H_z rebuilt every tick as the reference does (:258)" % (n, args.steps, threads),
+                             "failed_instances": nfail},
             "e2e": {"value": qps, "unit": "QP solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def spread(xs):
+    xs = sorted(float(x) for x in xs)
+    return {"n": len(xs), "median": statistics.median(xs), "min": xs[0], "max": xs[-1]}
 
 
 def main():
@@ -160,8 +177,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="instances per GPU")
+    ap.add_argument("--repeats", type=int, default=int(os.environ.get("ISMPC_BENCH_REPEATS", "7")),
+                    help="timed repeats of the K-step region (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-form-a", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the horizon sweep and the dense-seam leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,14 +200,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    K, W, n = args.steps, max(args.warmup, 3), args.batch
+    K, W, n, R = args.steps, max(args.warmup, 3), args.batch, max(args.repeats, 1)
     h = binding.Handle(device=local, max_batch=max(n, 8192))
     model = abi.formc_model(N=HORIZON)
     h.formc_set_model(model)
     h.formc_prepare_gait(35, 10)          # parameters.cpp:43-44 (device-resident calls cannot read the gait themselves)
 
     # ---- inputs: distinct batches rotating over a footprint larger than L2 -------------------------------
-    seeds = [synth.SEED0 ^ 2 ^ (rank * 7919 + s) for s in range(4)]
+    seeds = [synth.SEED0 ^ 2 ^ (rank * 7919 + s) for s in range(8)]
     host_batches = [synth.formc_batch(n, seed=s, N=HORIZON) for s in seeds]
     per_batch = sum(a.nbytes for a in host_batches[0]) + n * abi.FORMC_OUT.itemsize
     n_slots = max(8, int(1.5 * L2_BYTES / per_batch) + 1)
@@ -201,6 +221,10 @@ def main():
         slots.append(dict(state=to_dev(st), walk=to_dev(wk), inst=to_dev(ins), plan=to_dev(pl), rows=pl.shape[0],
                           out=torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)))
     stream = torch.cuda.current_stream().cuda_stream
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # 256 MB > L2 (126 MB)
+
+    def flush_l2(k=0):
+        flush_buf.fill_(k & 0x7f)
 
     def step(k, on=None):
         s = slots[k % n_slots]
@@ -219,38 +243,54 @@ def main():
     for k in range(W):
         step(k)
     barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream ---------------------------------------
+    # ---- eager arm: K separate C-ABI calls from Python, events around every step (per-tick latency) --------
     l0 = h.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    flush_l2()
     barrier()
     ev[0].record()
     for k in range(K):
         step(W + k)
         ev[k + 1].record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[K])
+    eager_ms = ev[0].elapsed_time(ev[K])
     launches = h.kernel_launches - l0
     per_step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
-    eager_ms_max = sharding.max_over_ranks(total_ms, device=dev)
-    # ---- the same K steps as ONE CUDA graph (K kernel nodes): what a caller with a launch-bound loop does -----
-    # The tick lasts ~14 us; K Python -> ctypes -> cudaLaunchKernel round trips cost about as much as the kernels.
-    # The library only enqueues on the caller's stream, so the K calls are captured as they are and replayed.
-    graph_ms = None
-    try:
-        cs = torch.cuda.Stream()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=cs):
-            sp = torch.cuda.current_stream().cuda_stream
-            for k in range(K):
-                step(W + k, on=sp)
-        g.replay()                                   # untimed: uploads the graph
+    eager_ms_max = sharding.max_over_ranks(eager_ms, device=dev)
+    # ---- headline: the K steps as ONE CUDA graph (K kernel nodes), R timed replays --------------------------
+    # A tick lasts ~10 us; K Python -> ctypes -> cudaLaunchKernel round trips cost more than the kernels.  The library
+    # only enqueues on the caller's stream, so the K calls are captured as they are.  Every timed replay is exactly K
+    # steps, bracketed by barrier + synchronize; before each one the L2 is flushed (256 MB written) and the K steps read
+    # K distinct slots, so nothing a replay reads was left in L2 by the warm-up, the upload replay or an earlier repeat.
+    # `value` is the MEDIAN over the R replays of the max-over-ranks time.
+    cs = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=cs):
+        sp = torch.cuda.current_stream().cuda_stream
+        for k in range(K):
+            step(W + k, on=sp)
+    g.replay()                                   # untimed: uploads the graph
+    barrier()
+    graph_ms = []
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for r in range(R):
+        flush_l2(r)
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(); g.replay(); g1.record()
         barrier()
-        graph_ms = g0.elapsed_time(g1)
-    except Exception as e:                           # capture refused: keep the eager number
-        print("bench.py: CUDA-graph arm skipped (%s)" % e, file=sys.stderr)
+        graph_ms.append(sharding.max_over_ranks(g0.elapsed_time(g1), device=dev))
+    total_ms_max = statistics.median(graph_ms)
+    value = 3.0 * n * world * K / (total_ms_max * 1e-3)
+    # one tick as a one-node graph, replayed on its own: what a caller that launches a tick and waits for it sees
+    g1t = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g1t, stream=cs):
+        step(W + K, on=torch.cuda.current_stream().cuda_stream)
+    g1t.replay(); torch.cuda.synchronize()
+    single_us = []
+    for r in range(50):
+        torch.cuda.synchronize()
+        g0.record(); g1t.replay(); g1.record(); g1.synchronize()
+        single_us.append(g0.elapsed_time(g1) * 1e3)
     # ---- the same K steps alternating over TWO handles on two streams (independent batches overlap: the slowest CTAs
     # of one tick no longer hold the next tick back).  Reported next to `value`, which stays the serialised number.
     overlap_ms = None
@@ -273,42 +313,32 @@ def main():
             s_a.wait_stream(s_b)
         g2.replay()
         barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record(); g2.replay(); o1.record()
-        barrier()
-        overlap_ms = sharding.max_over_ranks(o0.elapsed_time(o1), device=dev)
+        ov = []
+        for r in range(min(R, 3)):
+            flush_l2(r)
+            barrier()
+            g0.record(); g2.replay(); g1.record()
+            barrier()
+            ov.append(sharding.max_over_ranks(g0.elapsed_time(g1), device=dev))
+        overlap_ms = statistics.median(ov)
         h2.close()
     except Exception as e:
         print("bench.py: two-stream arm skipped (%s)" % e, file=sys.stderr)
-    launch_mode = "eager: one C-ABI call per step"
-    if graph_ms is not None and graph_ms < total_ms:
-        total_ms = graph_ms
-        launch_mode = "CUDA graph of the K steps (one kernel node per step), replayed once inside the timed region"
-    total_ms_max = sharding.max_over_ranks(total_ms, device=dev)
-    value = 3.0 * n * world * K / (total_ms_max * 1e-3)
 
-    # ---- kernel duration in isolation (roofline): events around single launches, inputs rotating ----------
-    kdur = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for k in range(min(K, 100)):
-        torch.cuda.synchronize()
-        e0.record(); step(W + K + k); e1.record(); e1.synchronize()
-        kdur.append(e0.elapsed_time(e1))
-    isolated_ms = statistics.median(kdur)          # one launch on an idle stream: kernel + launch latency
-    # the timed region is K launches of the dominant kernel back to back on this stream and nothing else:
-    # its CUDA-event time / K is that kernel's average launch duration
-    kernel_ms = total_ms / K
+    # the timed region is K launches of the dominant kernel back to back on one stream and nothing else:
+    # its CUDA-event time / K is that kernel's average launch duration (launch gaps included)
+    kernel_ms = total_ms_max / K
     FLOP_FORMC = float(load_ncu().get("fp64_flop_per_instance_tick", FLOP_FORMC_FALLBACK))
 
     # ---- e2e: the C ABI with HOST buffers (pinned), copies inside the timed region -------------------------
-    # Headline e2e = the serving loop a caller runs: DEPTH handles on DEPTH streams, ISMPC_MEM_HOST_ASYNC, so that
-    # step k+1's host->device copies overlap step k's kernel and device->host copy.  Every step copies its own
-    # inputs from pinned host memory and lands its result records in pinned host memory, where they are read.
-    # The synchronous single call (ISMPC_MEM_HOST) is reported next to it as e2e_sync.
-    # The footstep plans are constructor data in the reference (MPCSolver::MPCSolver(ftsp_and_timings); Controller
-    # builds the matrix once): they are handed to the handle once, outside the timed region (ismpc_formc_set_plan),
-    # and a step moves what MPCSolver::solve receives per tick -- state, walk state, instance record -- in and the
-    # result record out.  `e2e_with_plan` is the same loop with the whole plan table copied in every step as well.
+    # The serving loop a caller runs, in the reference's host language: host/FormCPipeline.hpp over the C ABI
+    # (lib/libismpc_host.so, plain g++), T host threads x D handles / streams, ISMPC_MEM_HOST_ASYNC, so that step k+1's
+    # host->device copy overlaps step k's kernel and device->host copy.  Every step copies its own state / walk-state /
+    # instance records from pinned host memory (one block, one copy) and lands its result records in pinned host
+    # memory, where the loop reads them.  The footstep plans are constructor data in the reference
+    # (MPCSolver::MPCSolver(ftsp_and_timings)): they are handed to the handles once, outside the timed region
+    # (ismpc_formc_set_plan).  The clock is the pool's own (steady_clock from before the first submit until the last
+    # result is read), per rank; a repeat counts as the MAX over ranks, the value is the median over R repeats.
     all_plans = np.concatenate([b[3] for b in host_batches])
     pinned = []
     row0 = 0
@@ -316,149 +346,82 @@ def main():
         d = {}
         ins_res = ins.copy(); ins_res["plan_first_row"] += row0          # rows of this batch in the resident table
         row0 += pl.shape[0]
-        # state | walk | instance records back to back in ONE pinned allocation: the library then moves a tick's
-        # inputs in a single copy (ismpc_formc_solve_batch, host-memory modes)
-        for name, recs in (("pack", (st, wk, ins)), ("pack_res", (st, wk, ins_res))):
-            raw = np.concatenate([np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in recs])
-            t = torch.from_numpy(raw.copy()).pin_memory()
-            d[name] = t
-            o1 = st.nbytes; o2 = o1 + wk.nbytes
-            d[name + "_ptr"] = (t.data_ptr(), t.data_ptr() + o1, t.data_ptr() + o2)
-        d["plan"] = torch.from_numpy(np.ascontiguousarray(pl).view(np.uint8).reshape(-1).copy()).pin_memory()
-        d["plan_ptr"] = d["plan"].data_ptr()
-        d["rows"] = pl.shape[0]
+        raw = np.concatenate([np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in (st, wk, ins_res)])
+        t = torch.from_numpy(raw.copy()).pin_memory()
+        d["pack_res"] = t
+        o1 = st.nbytes; o2 = o1 + wk.nbytes
+        d["pack_res_ptr"] = (t.data_ptr(), t.data_ptr() + o1, t.data_ptr() + o2)
         pinned.append(d)
     h2d = pinned[0]["pack_res"].numel(); d2h = n * abi.FORMC_OUT.itemsize
-    h2d_with_plan = h2d + pinned[0]["plan"].numel()
     h.formc_set_plan(all_plans)
 
     def e2e_sync_step(k, out):
-        d = pinned[k % len(pinned)]
-        ps, pw, pi = d["pack_res_ptr"]
+        ps, pw, pi = pinned[k % len(pinned)]["pack_res_ptr"]
         h.formc_solve_batch_raw(n, ps, pw, pi, None, 0, out.data_ptr(), mem=abi.MEM_HOST, stream=stream)
 
     out_sync = torch.zeros(d2h, dtype=torch.uint8).pin_memory()
     for k in range(W):
         e2e_sync_step(k, out_sync)
     barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        e2e_sync_step(k, out_sync)
-    barrier()
-    e2e_sync_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
-
-    DEPTH = int(os.environ.get("ISMPC_E2E_DEPTH", "4"))      # calls in flight: 2 -> 110, 3 -> 149, 4 -> 161, 6 -> 154 M QP/s
-    pipe = []
-    for s_ in range(DEPTH):
-        hh = binding.Handle(device=local, max_batch=max(n, 1024)); hh.formc_set_model(model); hh.formc_prepare_gait(35, 10)
-        hh.formc_set_plan(all_plans)
-        pipe.append({"h": hh, "stream": torch.cuda.Stream(device=dev), "out": torch.zeros(d2h, dtype=torch.uint8).pin_memory()})
-    checksum = [0]
-
-    for p_ in pipe:
-        p_["out_np"] = p_["out"].numpy(); p_["out_ptr"] = p_["out"].data_ptr(); p_["cu_stream"] = p_["stream"].cuda_stream
-
-    def e2e_pipe_step(k, mode=0):
-        p_ = pipe[k % DEPTH]
-        p_["stream"].synchronize()                          # step k-DEPTH is complete: its records are in host memory
-        if k >= DEPTH:
-            checksum[0] += int(p_["out_np"][112])           # read the result (status word of record 0)
-        d = pinned[k % len(pinned)]
-        if mode == 1:                                       # the whole plan table travels with every step
-            ps, pw, pi = d["pack_ptr"]
-            p_["h"].formc_solve_batch_raw(n, ps, pw, pi, d["plan_ptr"], d["rows"], p_["out_ptr"], mem=abi.MEM_HOST_ASYNC,
-                                          stream=p_["cu_stream"])
-        elif mode == 2:                                     # mapped: the kernel reads / writes the pinned host buffers itself
-            ps, pw, pi = d["pack_res_ptr"]
-            p_["h"].formc_solve_batch_raw(n, ps, pw, pi, None, 0, p_["out_ptr"], mem=abi.MEM_DEVICE, stream=p_["cu_stream"])
-        else:
-            ps, pw, pi = d["pack_res_ptr"]
-            p_["h"].formc_solve_batch_raw(n, ps, pw, pi, None, 0, p_["out_ptr"], mem=abi.MEM_HOST_ASYNC,
-                                          stream=p_["cu_stream"])
-
-    def e2e_loop(with_plan):
-        for k in range(max(W, DEPTH)):                      # at least one call on every handle before the clock starts
-            e2e_pipe_step(k, with_plan)
-        for p_ in pipe:
-            p_["stream"].synchronize()
-        barrier()
+    sync_s = []
+    for r in range(min(R, 3)):
         t0 = time.perf_counter()
         for k in range(K):
-            e2e_pipe_step(k, with_plan)
-        for p_ in pipe:
-            p_["stream"].synchronize()
-        barrier()
-        return sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
+            e2e_sync_step(k, out_sync)
+        sync_s.append(sharding.max_over_ranks(time.perf_counter() - t0, device=dev))
+    e2e_sync_s = statistics.median(sync_s)
 
-    e2e_plan_s = e2e_loop(1)
-    l0 = sum(p_["h"].kernel_launches for p_ in pipe)
-    e2e_s = e2e_loop(0)
-    e2e_value = 3.0 * n * world * K / e2e_s
-    e2e_launches = sum(p_["h"].kernel_launches for p_ in pipe) - l0       # warm-up + timed steps of this arm
-    last_copy = pipe[(K - 1) % DEPTH]["out_np"].copy()
-    e2e_mapped_s = e2e_loop(2)
-    mapped_equal = bool(np.array_equal(last_copy, pipe[(K - 1) % DEPTH]["out_np"]))
-
-    # ---- the same serving loop from C++ (host/FormCPipeline.hpp over the C ABI): the reference's host language ----
-    # W warm-up steps, barrier, K timed steps ending with every stream waited for, barrier.  Same pinned input blocks,
-    # same rotation, its own DEPTH handles / streams / pinned result buffers; the loop reads every step's result.
     import ctypes as C
     hostlib = C.CDLL(os.path.join(os.path.dirname(binding.LIB_PATH), "libismpc_host.so"))
-    hostlib.ismpc_host_pipeline_create.restype = C.c_void_p
-    hostlib.ismpc_host_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
-    hostlib.ismpc_host_pipeline_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-    hostlib.ismpc_host_pipeline_destroy.argtypes = [C.c_void_p]
-    hostlib.ismpc_host_pipeline_launches.restype = C.c_longlong
-    hostlib.ismpc_host_pipeline_launches.argtypes = [C.c_void_p]
+    hostlib.ismpc_host_pool_create.restype = C.c_void_p
+    hostlib.ismpc_host_pool_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    hostlib.ismpc_host_pool_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hostlib.ismpc_host_pool_destroy.argtypes = [C.c_void_p]
+    hostlib.ismpc_host_pool_set_spin_us.argtypes = [C.c_void_p, C.c_int]
+    hostlib.ismpc_host_pool_launches.restype = C.c_longlong
+    hostlib.ismpc_host_pool_launches.argtypes = [C.c_void_p]
     hostlib.ismpc_host_last_error.restype = C.c_char_p
-    hostlib.ismpc_host_pipelines_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
-    # a second host thread pays off only where the rank has cores to itself (8 ranks on a 32-thread box: 1 thread each)
-    T_DEFAULT = 2 if (os.cpu_count() or 1) // world >= 8 and K >= 64 else 1      # (a handful of steps: not worth a thread)
-    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", str(T_DEFAULT)))        # host threads, one pipeline each (1x4: 249, 1x6: 267, 2x3: 296, 2x4: 303, 3x3: 310 M QP/s)
-    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4" if T_HOST > 1 else "6"))      # calls in flight per thread
-    pps = []
-    for _ in range(T_HOST):
-        pp = hostlib.ismpc_host_pipeline_create(local, n, D_HOST, model.ctypes.data, 35, 10, plans_c.ctypes.data, plans_c.shape[0])
-        if not pp:
-            raise RuntimeError("ismpc_host_pipeline_create: " + hostlib.ismpc_host_last_error().decode())
-        pps.append(pp)
-    pp_arr = (C.c_void_p * T_HOST)(*pps)
+    cores_per_rank = max(1, (os.cpu_count() or 1) // world)
+    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "2" if cores_per_rank >= 4 else "1"))   # host threads, one pipeline each
+    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4" if T_HOST > 1 else "6"))           # calls in flight per thread
+    pool = hostlib.ismpc_host_pool_create(local, n, T_HOST, D_HOST, model.ctypes.data, 35, 10, plans_c.ctypes.data, plans_c.shape[0])
+    if not pool:
+        raise RuntimeError("ismpc_host_pool_create: " + hostlib.ismpc_host_last_error().decode())
+    hostlib.ismpc_host_pool_set_spin_us(pool, 200000)     # parked workers poll: a repeat never starts with a futex wake-up
     blocks = (C.c_void_p * len(pinned))(*[d["pack_res"].data_ptr() for d in pinned])
-    csum = C.c_longlong(0)
+    csum = C.c_longlong(0); el = C.c_double(0.0)
     out_cpp = np.zeros((T_HOST, D_HOST, n), dtype=abi.FORMC_OUT)
-    l_before = sum(hostlib.ismpc_host_pipeline_launches(pp) for pp in pps)
+    l_before = hostlib.ismpc_host_pool_launches(pool)
     # warm-up rounded up to whole rounds of the threads, and at least one call on every handle (a handle's first call
     # allocates its staging and workspace and queries occupancy: milliseconds that do not belong in the timed region)
     WC = max(-(-W // T_HOST) * T_HOST, T_HOST * D_HOST)
-    if hostlib.ismpc_host_pipelines_run(pp_arr, T_HOST, 0, WC, blocks, len(pinned), C.byref(csum), None) != 0:
-        raise RuntimeError("ismpc_host_pipelines_run: " + hostlib.ismpc_host_last_error().decode())
-    barrier()
-    t0 = time.perf_counter()
-    rc_cpp = hostlib.ismpc_host_pipelines_run(pp_arr, T_HOST, WC, K, blocks, len(pinned), C.byref(csum), out_cpp.ctypes.data)
-    barrier()
-    e2e_cpp_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
-    if rc_cpp != 0:
-        raise RuntimeError("ismpc_host_pipelines_run: " + hostlib.ismpc_host_last_error().decode())
-    e2e_cpp_launches = sum(hostlib.ismpc_host_pipeline_launches(pp) for pp in pps) - l_before
-    for pp in pps:
-        hostlib.ismpc_host_pipeline_destroy(pp)
-    # where the last step's records are: thread t takes steps WC+t, WC+t+T, ...; its slots go round-robin from the
-    # number of steps it has submitted since creation
-    k_last = WC + K - 1
-    t_last = (k_last - WC) % T_HOST
-    done_before = WC // T_HOST + (k_last - WC - t_last) // T_HOST   # steps thread t_last submitted before this one
-    slot_last = done_before % D_HOST
-    # its last step against a synchronous call on the same pinned block
+    if hostlib.ismpc_host_pool_run(pool, 0, WC, blocks, len(pinned), C.byref(csum), None, None) != 0:
+        raise RuntimeError("ismpc_host_pool_run: " + hostlib.ismpc_host_last_error().decode())
+    e2e_runs = []
+    k_next = WC
+    for r in range(R):
+        barrier()
+        rc_cpp = hostlib.ismpc_host_pool_run(pool, k_next, K, blocks, len(pinned), C.byref(csum), out_cpp.ctypes.data, C.byref(el))
+        if rc_cpp != 0:
+            raise RuntimeError("ismpc_host_pool_run: " + hostlib.ismpc_host_last_error().decode())
+        e2e_runs.append(sharding.max_over_ranks(el.value, device=dev))
+        k_next += K
+    e2e_cpp_s = statistics.median(e2e_runs)
+    e2e_cpp_launches = hostlib.ismpc_host_pool_launches(pool) - l_before
+    # the records of the last step against a synchronous call on the same pinned block
+    k_last = k_next - 1
+    t_last = (k_last - (k_next - K)) % T_HOST
+    cpp_equal = None; bad_cpp = None
     e2e_sync_step(k_last, out_sync)
     ref_last = np.frombuffer(out_sync.numpy().tobytes(), dtype=abi.FORMC_OUT)
-    cpp_equal = bool(out_cpp[t_last, slot_last].tobytes() == ref_last.tobytes())
-    bad_cpp = int(((out_cpp[t_last, slot_last]["status"] & 7) != 0).sum())
-    # sanity: the e2e result equals the device-resident result for the same batch
-    chk = np.frombuffer(pipe[(K - 1) % DEPTH]["out"].numpy().tobytes(), dtype=abi.FORMC_OUT)
-    bad = int(((chk["status"] & 7) != 0).sum())
-    for p_ in pipe:
-        p_["h"].close()
+    for s_ in range(D_HOST):                                   # the slot that holds it is one of the thread's D slots
+        if out_cpp[t_last, s_].tobytes() == ref_last.tobytes():
+            cpp_equal = True
+            bad_cpp = int(((out_cpp[t_last, s_]["status"] & 7) != 0).sum())
+    if cpp_equal is None:
+        cpp_equal = False
+    hostlib.ismpc_host_pool_destroy(pool)
     clk = clocks.stop()
 
     # ---- final gather of the result records (the only collective on this path) -----------------------------
@@ -473,42 +436,33 @@ def main():
         line = {"metric": "batched ISMPC QP solves/sec", "value": value, "unit": "QP solves/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "formC_tick_trot_1024xN100", "instances_per_gpu": n, "horizon_N": HORIZON,
-                           "qp_per_instance_tick": 3, "formulation": "C (MPCSolver::solve)", "launch": launch_mode,
-                           "l2": "inputs rotate over %d distinct device batches (%.0f MB > L2 126 MB)"
-                                 % (n_slots, n_slots * per_batch / 1e6)},
+                "config": workload_config(n),
+                "repeats": {"timed_replays_of_the_K_step_graph_ms": spread(graph_ms), "all_ms": graph_ms,
+                            "value_is": "3 x instances x n_gpus x K / median"},
                 "e2e": {"value": 3.0 * n * world * K / e2e_cpp_s, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad_cpp,
                         "last_step_equals_synchronous_call": cpp_equal,
+                        "repeats_s": spread(e2e_runs),
                         "how": "C++ host loop (host/FormCPipeline.hpp, the reference's host language) over the C ABI: "
-                               "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d host threads x %d handles / streams "
-                               "(that many calls in flight); every step copies its state / walk-state / instance records in "
-                               "(one pinned block, one copy) and its result records out, and the loop reads each result; the "
-                               "footstep plans are resident in the handles (ismpc_formc_set_plan), as they are constructor "
-                               "data of the reference's MPCSolver" % (T_HOST, D_HOST),
+                               "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d persistent host threads x %d "
+                               "handles / streams (that many calls in flight); every step copies its state / walk-state / instance "
+                               "records in (one pinned block, one copy) and its result records out, and the loop reads every "
+                               "result; the footstep plans are resident in the handles (ismpc_formc_set_plan), as they are "
+                               "constructor data of the reference's MPCSolver; K steps per repeat timed by the pool's own clock "
+                               "(first submit -> last result read), max over ranks, median of %d repeats" % (T_HOST, D_HOST, R),
                         "kernel_launches": int(e2e_cpp_launches)},
-                "e2e_python": {"value": e2e_value, "unit": "QP solves/s", "h2d_bytes_per_step": int(h2d),
-                               "d2h_bytes_per_step": int(d2h), "failed_instances_last_step": bad,
-                               "how": "the same loop written in Python over ctypes (~13 us of interpreter and call overhead per step)",
-                               "kernel_launches": int(e2e_launches)},
-                "e2e_with_plan": {"value": 3.0 * n * world * K / e2e_plan_s, "unit": "QP solves/s",
-                                  "h2d_bytes_per_step": int(h2d_with_plan), "d2h_bytes_per_step": int(d2h),
-                                  "how": "the same loop with the whole footstep-plan table passed and copied in every step"},
-                "e2e_mapped": {"value": 3.0 * n * world * K / e2e_mapped_s, "unit": "QP solves/s",
-                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                               "records_equal_copy_arm": mapped_equal,
-                               "how": "the same serving loop without copy calls: ismpc_formc_solve_batch(ISMPC_MEM_DEVICE) is "
-                                      "handed the pinned (mapped) host buffers, the kernel reads its records from host "
-                                      "memory and stores the result records into host memory itself"},
                 "e2e_sync": {"value": 3.0 * n * world * K / e2e_sync_s, "unit": "QP solves/s",
-                             "how": "one synchronous ismpc_formc_solve_batch(ISMPC_MEM_HOST) call per step",
+                             "how": "one synchronous ismpc_formc_solve_batch(ISMPC_MEM_HOST) call per step from Python (what a "
+                                    "single Controller-style caller sees)",
                              "ms_per_step": e2e_sync_s / K * 1e3},
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": load_traffic(), "peak_source": peak_src,
                              "kernel": "formc_tick_pair_kernel", "kernel_ms": kernel_ms,
-                             "algorithmic_bytes_per_instance_tick": B_ALG_FORMC},
+                             "algorithmic_bytes_per_instance_tick": B_ALG_FORMC,
+                             "note": "the kernel is bound by the dependent-issue latency of one warp pair per instance, not "
+                                     "by HBM or FP64 throughput (DESIGN.md section 4); both fractions are small by construction"},
                 "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
                                   "peak": fp64_peak, "unit": "TFLOP/s",
                                   "frac": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
@@ -526,9 +480,12 @@ def main():
                                 {"value": 3.0 * n * world * K / (overlap_ms * 1e-3), "unit": "QP solves/s", "ms_per_step": overlap_ms / K,
                                  "how": "the K steps as one CUDA graph alternating over two handles on two streams "
                                         "(consecutive steps are independent batches and overlap)"}),
-                "latency": {"p50_tick_us": statistics.median(per_step_ms) * 1e3,
-                            "p90_tick_us": sorted(per_step_ms)[int(0.9 * (K - 1))] * 1e3,
-                            "isolated_launch_us": isolated_ms * 1e3},
+                "latency": {"p50_tick_us": statistics.median(single_us),
+                            "p90_tick_us": sorted(single_us)[int(0.9 * (len(single_us) - 1))],
+                            "how": "one tick of 1,024 instances as a one-node CUDA graph, launched on an idle stream and waited "
+                                   "for, CUDA events around it, 50 samples",
+                            "eager_p50_tick_us": statistics.median(per_step_ms) * 1e3,
+                            "eager_p90_tick_us": sorted(per_step_ms)[int(0.9 * (K - 1))] * 1e3},
                 "instance_ticks_per_s": value / 3.0,
                 "gathered_records": int(len(full))}
 
@@ -568,13 +525,25 @@ def main():
                 cl["qp_solves_per_s"] = 3.0 * cl["instance_ticks_per_s"]
                 cl["instances_with_a_failed_tick"] = "rank 0: %d" % cl["instances_with_a_failed_tick"]
             line["closed_loop_form_c"] = cl
+    # ---- configs[3] (horizon sweep) and the dense solveQP seam: rank 0, single-GPU lines only --------------------------
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            line["horizon_sweep"] = bench_horizon_sweep(h, torch, dev, stream)
+        except Exception as e:  # noqa: BLE001
+            line["horizon_sweep"] = {"error": repr(e)}
+        try:
+            line["dense_seam"] = bench_dense_seam(h, torch, dev, stream, hbm_peak, fp64_peak)
+        except Exception as e:  # noqa: BLE001
+            line["dense_seam"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             reps = 3
             qps, per_step, threads, kind, ns, nfail = cpu_reference_run(reps, 1)
             line["cpu_baseline"] = {"value": qps, "unit": "QP solves/s", "cores": threads, "kind": kind,
                                     "sample": "%d instances x %d passes of the same workload, all %d host threads, "
-                                              "cold qpOASES QProblem per solve (utils.cpp:121-130)" % (ns, reps, threads),
+                                              "cold qpOASES QProblem per solve (utils.cpp:121-130); constructor matrices "
+                                              "once per model, H_z rebuilt per tick (MPCSolver.cpp:144-156, :258)"
+                                              % (ns, reps, threads),
                                     "failed_instances": nfail}
             q1, _, _, _, n1, _ = cpu_reference_run(1, 0, sample_n=128, threads=1)
             line["cpu_baseline"]["single_thread"] = {"value": q1, "unit": "QP solves/s", "cores": 1,
@@ -586,6 +555,105 @@ def main():
     h.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_horizon_sweep(h, torch, dev, stream, n=1024):
+    """configs[3]: horizon sweep N = 50/100/200/400 at 1,024 instances, both formulations (form C: 3 QPs per
+    instance-tick, warp / warp-pair per QP; form A: 1 QP of nV = 2(C+3) per instance-tick, C = N, P = 2N, two warps per
+    QP).  Time per launch: BURST launches back to back between two CUDA events, median of 7, inputs device-resident."""
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    BURST = 8
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    def timed(fn, reps=7, warm=2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for k in range(reps + warm):
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(BURST):
+                fn()
+            e1.record(); e1.synchronize()
+            if k >= warm:
+                ts.append(e0.elapsed_time(e1) * 1e3 / BURST)
+        return statistics.median(ts)
+
+    rows = []
+    for N in (50, 100, 200, 400):
+        steps = (2 * N + 900) // 45 + 3
+        st, wk, ins, pl = synth.formc_batch(n, seed=N, N=N, n_steps=steps)
+        h.formc_set_model(abi.formc_model(N=N)); h.formc_prepare_gait(35, 10)
+        d = [to_dev(x) for x in (st, wk, ins, pl)]
+        out = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev)
+        us = timed(lambda: h.formc_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                                   pl.shape[0], out.data_ptr(), stream=stream))
+        o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMC_OUT)
+        rows.append({"formulation": "C", "N": N, "instances": n, "us_per_tick": us, "qp_solves_per_s": 3.0 * n / (us * 1e-6),
+                     "failed": int((o["status"] & (abi.ST_Z_FAIL | abi.ST_X_FAIL | abi.ST_Y_FAIL) != 0).sum())})
+    for C_ in (50, 100, 200, 400):
+        step = C_ // 2
+        h.forma_set_model(abi.forma_model(C=C_, P=2 * C_))
+        inst, ft, plan = synth.forma_batch(n, gait="trot", C=C_, step=step, ds=max(2, step * 2 // 5), sim_ticks=20 * step)
+        rng = np.random.default_rng(5)
+        ticks = rng.choice([3, step // 3, step - 1, step + step // 4, 2 * step + 5, 3 * step - 2], size=n)
+        for t in np.unique(ticks):
+            sel = np.nonzero(ticks == t)[0]
+            r = h.forma_rollout(inst[sel], ft, plan, int(t), want_traj=False)
+            inst[sel] = r["inst"]
+            rowsel = (inst["plan_first_row"][sel][:, None] + np.arange(inst["n_fs"][sel][0])[None, :]).reshape(-1)
+            plan[rowsel] = r["fs_plan"][rowsel]
+        d = [to_dev(x) for x in (inst, ft, plan)]
+        out = torch.zeros(n * abi.FORMA_OUT.itemsize, dtype=torch.uint8, device=dev)
+        us = timed(lambda: h.forma_solve_batch_raw(n, d[0].data_ptr(), d[1].data_ptr(), len(ft), d[2].data_ptr(), plan.shape[0],
+                                                   out.data_ptr(), stream=stream))
+        o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=abi.FORMA_OUT)
+        rows.append({"formulation": "A", "N": C_, "instances": n, "us_per_tick": us, "qp_solves_per_s": n / (us * 1e-6),
+                     "mean_iters_per_qp": float(o["iters"].mean()), "failed": int((o["status"] & abi.ST_FAIL_MASK != 0).sum()),
+                     "dual_active_set_fallbacks": int((o["status"] & abi.ST_GI_FALLBACK != 0).sum())})
+    h.formc_set_model(abi.formc_model(N=HORIZON)); h.formc_prepare_gait(35, 10)
+    return {"workload": "configs[3]: N = 50/100/200/400, 1,024 mid-gait trot instances, cold ticks", "rows": rows}
+
+
+def bench_dense_seam(h, torch, dev, stream, hbm_peak, fp64_peak, n=1024):
+    """The literal replacement of Eigen::VectorXd solveQP(H, f, A, lbA, ubA) (utils.cpp:89-139): ismpc_qp_solve_batch on
+    DENSE inputs of the two shapes the path produces -- nV = 100 / nC = 101 (a stage-3 horizontal QP stacked as the
+    reference would pass it: H = I, A = [a'; I]) and nV = 206 / nC = 208 (the canonical ISMPC QP: diagonal H, two
+    stability rows, 2C ZMP rows delta*tril - mapping, 2F kinematic rows) -- 1,024 problems per call, device-resident.
+    The seam cannot exploit structure (it receives dense matrices), so its set-up is GEMM-shaped: rooflines are given
+    both for the flops it executes and for the reference-algorithm model F_ref = (k+1)(14 nV^2 + 2 nC nV) of SURVEY 8(d)."""
+    from quadruped_gait_generation_ismpc_b200 import abi, synth
+    res = {"problems_per_call": n, "rows": []}
+    for shape in ("formc_horizontal", "forma_stacked"):
+        H, g, A, lb, ub = synth.dense_qp_batch(shape, n)
+        nV, nC = H.shape[1], A.shape[1]
+        dH, dg, dA, dlb, dub = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (H, g, A, lb, ub)]
+        dx = torch.zeros((n, nV), dtype=torch.float64, device=dev)
+        dst = torch.zeros(n, dtype=torch.int32, device=dev); dit = torch.zeros(n, dtype=torch.int32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for k in range(6):
+            torch.cuda.synchronize()
+            e0.record()
+            h.qp_solve_batch_raw(n, nV, nC, dH.data_ptr(), dg.data_ptr(), dA.data_ptr(), dlb.data_ptr(), dub.data_ptr(),
+                                 dx.data_ptr(), status=dst.data_ptr(), iters=dit.data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+            e1.record(); e1.synchronize()
+            if k >= 1:
+                ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts)
+        it = dit.cpu().numpy(); stt = dst.cpu().numpy()
+        setup_flop = nV ** 3 * (1 / 3 + 1 / 3 + 2 / 3) + 2.0 * nC * nV * nV + 2.0 * nC * nC * nV + 2.0 * nV * nV + 2.0 * nC * nV
+        f_ref = float(((it + 1.0) * (14.0 * nV * nV + 2.0 * nC * nV)).mean())
+        in_bytes = 8.0 * (nV * nV + nV + nC * nV + 2 * nC) + 8.0 * nV
+        res["rows"].append({"shape": shape, "nV": nV, "nC": nC, "ms_per_call": ms, "qp_solves_per_s": n / (ms * 1e-3),
+                            "failed": int((stt != 0).sum()), "mean_working_set_changes": float(it.mean()),
+                            "setup_flop_per_qp_executed": setup_flop,
+                            "fp64_frac_executed_setup": setup_flop * n / (ms * 1e-3) / 1e12 / fp64_peak,
+                            "reference_algorithm_flop_per_qp": f_ref,
+                            "fp64_frac_reference_algorithm": f_ref * n / (ms * 1e-3) / 1e12 / fp64_peak,
+                            "hbm_frac_compulsory_bytes": in_bytes * n / (ms * 1e-3) / 1e9 / hbm_peak})
+    return res
 
 
 def _midgait(h, inst, ft, plan, seed=5):

@@ -286,6 +286,39 @@ void oracle_formc_vertical_matrices(const oracle_formc_params* p, double* Sz, do
     free(Sgz); free(Sgzv);
 }
 
+/* The reference builds these matrices ONCE, in the constructor (MPCSolver.cpp:144-156), and every solve() reuses the
+ * members.  The per-tick functions below therefore take them from a per-model cache (keyed by what they depend on: N,
+ * dt, mass, g) instead of rebuilding them each tick -- what stays per tick is what solve() itself recomputes, notably
+ * H_z (MPCSolver.cpp:258).  Entries are immutable once published; the lock covers look-up and construction. */
+#include <pthread.h>
+typedef struct { int N; double dt, mass, g; double *Sz, *Szv, *Tz, *Tzv, *Tg, *Tgv; } formc_vm_entry;
+#define FORMC_VM_SLOTS 16
+static formc_vm_entry g_vm[FORMC_VM_SLOTS];
+static int g_vm_n = 0;
+static pthread_mutex_t g_vm_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static const formc_vm_entry* formc_vertical_cached(const oracle_formc_params* p)
+{
+    const formc_vm_entry* hit = NULL;
+    pthread_mutex_lock(&g_vm_lock);
+    for (int i = 0; i < g_vm_n; ++i)
+        if (g_vm[i].N == p->N && g_vm[i].dt == p->dt && g_vm[i].mass == p->mass && g_vm[i].g == p->g) { hit = &g_vm[i]; break; }
+    if (!hit) {
+        formc_vm_entry* e = &g_vm[g_vm_n < FORMC_VM_SLOTS ? g_vm_n : FORMC_VM_SLOTS - 1];
+        if (g_vm_n >= FORMC_VM_SLOTS) { free(e->Sz); free(e->Szv); free(e->Tz); free(e->Tzv); free(e->Tg); free(e->Tgv); }
+        else ++g_vm_n;
+        int N = p->N;
+        e->N = N; e->dt = p->dt; e->mass = p->mass; e->g = p->g;
+        e->Sz = (double*)malloc(sizeof(double) * N * N); e->Szv = (double*)malloc(sizeof(double) * N * N);
+        e->Tz = (double*)malloc(sizeof(double) * N * 2); e->Tzv = (double*)malloc(sizeof(double) * N * 2);
+        e->Tg = (double*)malloc(sizeof(double) * N); e->Tgv = (double*)malloc(sizeof(double) * N);
+        oracle_formc_vertical_matrices(p, e->Sz, e->Szv, e->Tz, e->Tzv, e->Tg, e->Tgv);
+        hit = e;
+    }
+    pthread_mutex_unlock(&g_vm_lock);
+    return hit;
+}
+
 /* number of flight-phase equality rows, MPCSolver.cpp:223-229 */
 static int formc_ne(const oracle_formc_params* p, int mpc_iter)
 {
@@ -299,16 +332,11 @@ int oracle_formc_vertical_qp(const oracle_formc_params* p, const double z0[2], c
                              double* H, double* gq, double* A, double* lbA, double* ubA, int* ne_out)
 {
     int N = p->N;
-    double* Sz = (double*)malloc(sizeof(double) * N * N);
-    double* Szv = (double*)malloc(sizeof(double) * N * N);
-    double* Tz = (double*)malloc(sizeof(double) * N * 2);
-    double* Tzv = (double*)malloc(sizeof(double) * N * 2);
-    double* Tg = (double*)malloc(sizeof(double) * N);
-    double* Tgv = (double*)malloc(sizeof(double) * N);
+    const formc_vm_entry* vm = formc_vertical_cached(p);          /* members built by the constructor, :144-156 */
+    const double *Sz = vm->Sz, *Szv = vm->Szv, *Tz = vm->Tz, *Tzv = vm->Tzv, *Tg = vm->Tg, *Tgv = vm->Tgv;
     double* v = (double*)malloc(sizeof(double) * N);
     double* w = (double*)malloc(sizeof(double) * N);
-    oracle_formc_vertical_matrices(p, Sz, Szv, Tz, Tzv, Tg, Tgv);
-    /* H_z, :258 */
+    /* H_z, :258 (rebuilt every tick by the reference, although constant) */
     for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) {
             double s1 = 0, s2 = 0;
@@ -347,7 +375,7 @@ int oracle_formc_vertical_qp(const oracle_formc_params* p, const double z0[2], c
         lbA[ne + k] = 0.0; ubA[ne + k] = p->fz_max;
     }
     if (ne_out) *ne_out = ne;
-    free(Sz); free(Szv); free(Tz); free(Tzv); free(Tg); free(Tgv); free(v); free(w);
+    free(v); free(w);
     return ne + N;
 }
 
@@ -356,13 +384,8 @@ void oracle_formc_lambda(const oracle_formc_params* p, const double z0[2], const
                          double* lambda, double* zpos)
 {
     int N = p->N;
-    double* Sz = (double*)malloc(sizeof(double) * N * N);
-    double* Szv = (double*)malloc(sizeof(double) * N * N);
-    double* Tz = (double*)malloc(sizeof(double) * N * 2);
-    double* Tzv = (double*)malloc(sizeof(double) * N * 2);
-    double* Tg = (double*)malloc(sizeof(double) * N);
-    double* Tgv = (double*)malloc(sizeof(double) * N);
-    oracle_formc_vertical_matrices(p, Sz, Szv, Tz, Tzv, Tg, Tgv);
+    const formc_vm_entry* vm = formc_vertical_cached(p);          /* members built by the constructor, :144-156 */
+    const double *Sz = vm->Sz, *Tz = vm->Tz, *Tg = vm->Tg;
     for (int j = 0; j < N; ++j) {
         double zacc = (1.0 / p->mass) * f[j] - 1.0 * p->g;      /* :296 */
         double zp = 0;
@@ -371,7 +394,6 @@ void oracle_formc_lambda(const oracle_formc_params* p, const double z0[2], const
         lambda[j] = (p->g + zacc) / zp;                          /* :306 */
         if (zpos) zpos[j] = zp;
     }
-    free(Sz); free(Szv); free(Tz); free(Tzv); free(Tg); free(Tgv);
 }
 
 static void mat2_mul(const double A[4], const double B[4], double C[4])

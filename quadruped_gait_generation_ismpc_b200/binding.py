@@ -329,6 +329,13 @@ class Handle:
                                          C.c_void_p(stream) if stream else None)
         self._check(rc, "ismpc_forma_rollout")
 
+    def qp_solve_batch_raw(self, n, nV, nC, H, g, A, lbA, ubA, x, y=None, ws=None, status=None, iters=None,
+                           mem=abi.MEM_DEVICE, stream=None):
+        rc = self._L.ismpc_qp_solve_batch(self._h, n, nV, nC, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x),
+                                          _ptr(y), _ptr(ws), _ptr(status), _ptr(iters), mem,
+                                          C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_qp_solve_batch")
+
     # ---- generic dense QP (solveQP seam) ----------------------------------------------------------
     def qp_solve_batch(self, H, g, A, lbA, ubA):
         H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)

@@ -104,3 +104,154 @@ extern "C" int ismpc_host_pipelines_run(void* const* pipes, int T, int k0, int s
     if (checksum) *checksum = sum;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same serving loop with PERSISTENT host threads (what a real caller has: its worker threads exist before the first
+// tick).  A pool owns T pipelines; thread 0 is the caller's own thread, threads 1..T-1 are parked between runs -- they
+// spin on a generation counter for a short while (a run that follows the previous one closely starts within a
+// microsecond) and then sleep on a condition variable.  ismpc_host_pool_run times the K steps itself: the clock starts
+// before the first submit and stops when every stream of every pipeline has been waited for and every result read.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+
+namespace {
+
+struct HostPool {
+    std::vector<std::unique_ptr<FormCPipeline>> pipes;
+    std::vector<std::thread> workers;
+    std::vector<long long> sums;
+    std::vector<std::string> errs;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<long long> generation{0};
+    std::atomic<int> done{0};
+    bool quit = false;
+    int spin_us = 300;               // how long a parked worker polls before it sleeps (ismpc_host_pool_set_spin_us)
+    // the job
+    int k0 = 0, steps = 0, n_blocks = 0;
+    const void* const* in_blocks = nullptr;
+    ismpc_formc_out_t* out_copy = nullptr;
+
+    void work(int t)
+    {
+        FormCPipeline& p = *pipes[(size_t)t];
+        const int T = (int)pipes.size();
+        const size_t n = (size_t)p.n();
+        sums[(size_t)t] = 0; errs[(size_t)t].clear();
+        try {
+            int submitted = 0;
+            for (int k = k0 + t; k < k0 + steps; k += T, ++submitted) {
+                const int s = p.acquire();
+                if (submitted >= p.depth()) sums[(size_t)t] += p.out(s)[0].status;      // the result of the step that used the slot
+                const char* b = static_cast<const char*>(in_blocks[k % n_blocks]);
+                p.submit_from(s, reinterpret_cast<const ismpc_state_t*>(b),
+                              reinterpret_cast<const ismpc_walk_t*>(b + n * sizeof(ismpc_state_t)),
+                              reinterpret_cast<const ismpc_formc_inst_t*>(b + n * (sizeof(ismpc_state_t) + sizeof(ismpc_walk_t))));
+            }
+            p.wait_all();
+            for (int s = 0; s < p.depth(); ++s) sums[(size_t)t] += p.out(s)[0].status;   // ... and of the last `depth` steps
+            if (out_copy)
+                for (int s = 0; s < p.depth(); ++s)
+                    std::memcpy(out_copy + ((size_t)t * p.depth() + s) * n, p.out(s), n * sizeof(ismpc_formc_out_t));
+        } catch (const std::exception& e) {
+            errs[(size_t)t] = e.what();
+        }
+    }
+
+    void worker_main(int t)
+    {
+        long long seen = 0;
+        for (;;) {
+            // spin briefly, then sleep
+            bool go = false;
+            const auto t_spin = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+            while (std::chrono::steady_clock::now() < t_spin) {
+                if (generation.load(std::memory_order_acquire) != seen) { go = true; break; }
+            }
+            if (!go) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || generation.load(std::memory_order_acquire) != seen; });
+                if (quit) return;
+            }
+            if (quit) return;
+            seen = generation.load(std::memory_order_acquire);
+            work(t);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            generation.fetch_add(1, std::memory_order_release);
+        }
+        cv.notify_all();
+        for (std::thread& w : workers) w.join();
+    }
+};
+
+}  // namespace
+
+extern "C" void* ismpc_host_pool_create(int device, int n, int threads, int depth, const ismpc_formc_model_t* model, int S,
+                                        int F_ds, const double* plan_xyzt, int plan_rows)
+{
+    try {
+        if (threads < 1 || threads > 64) throw std::runtime_error("ismpc_host_pool_create: threads must be 1..64");
+        std::unique_ptr<HostPool> hp(new HostPool());
+        for (int t = 0; t < threads; ++t)
+            hp->pipes.emplace_back(new FormCPipeline(device, n, depth, *model, S, F_ds, plan_xyzt, plan_rows, /*own_staging=*/false));
+        hp->sums.assign((size_t)threads, 0); hp->errs.assign((size_t)threads, std::string());
+        for (int t = 1; t < threads; ++t) hp->workers.emplace_back(&HostPool::worker_main, hp.get(), t);
+        return hp.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+extern "C" void ismpc_host_pool_destroy(void* p) { delete static_cast<HostPool*>(p); }
+
+// Low-latency serving: parked workers poll for `us` microseconds before they go to sleep (default 300; a control loop
+// that ticks every few milliseconds sets this above its period so that a tick never pays a futex wake-up).
+extern "C" void ismpc_host_pool_set_spin_us(void* p, int us) { if (p && us >= 0) static_cast<HostPool*>(p)->spin_us = us; }
+
+extern "C" long long ismpc_host_pool_launches(void* pv)
+{
+    long long t = 0;
+    for (auto& p : static_cast<HostPool*>(pv)->pipes) t += p->kernel_launches();
+    return t;
+}
+
+// Steps k0 .. k0+steps-1: thread t takes steps k0+t, k0+t+T, ...  out_copy_opt: T x depth x n records (the result records
+// of every pipeline's slots after the run).  elapsed_s_opt: wall-clock seconds from before the first submit until the
+// last result has been read.  Returns 0, or -1 with the first error in ismpc_host_last_error().
+extern "C" int ismpc_host_pool_run(void* pv, int k0, int steps, const void* const* in_blocks, int n_blocks,
+                                   long long* checksum, ismpc_formc_out_t* out_copy_opt, double* elapsed_s_opt)
+{
+    HostPool& hp = *static_cast<HostPool*>(pv);
+    const int T = (int)hp.pipes.size();
+    hp.k0 = k0; hp.steps = steps; hp.in_blocks = in_blocks; hp.n_blocks = n_blocks; hp.out_copy = out_copy_opt;
+    hp.done.store(0, std::memory_order_release);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (T > 1) {
+        { std::lock_guard<std::mutex> lk(hp.mu); hp.generation.fetch_add(1, std::memory_order_release); }
+        hp.cv.notify_all();
+    }
+    hp.work(0);
+    while (hp.done.load(std::memory_order_acquire) < T - 1) { /* the workers finish within microseconds of thread 0 */ }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s_opt) *elapsed_s_opt = std::chrono::duration<double>(t1 - t0).count();
+    long long sum = 0;
+    for (int t = 0; t < T; ++t) {
+        if (!hp.errs[(size_t)t].empty()) { g_err = hp.errs[(size_t)t]; return -1; }
+        sum += hp.sums[(size_t)t];
+    }
+    if (checksum) *checksum = sum;
+    return 0;
+}

@@ -133,3 +133,68 @@ def push_batch(n, seed=SEED0 ^ 5, formc=False):
     else:
         push["fs"] = rng.integers(2, 9, n); push["ct0"] = 1; push["ct1"] = 15
     return push
+
+
+def dense_qp_batch(shape, n, seed=SEED0 ^ 21):
+    """DENSE inputs for the solveQP seam (ismpc_qp_solve_batch), in the two shapes the path produces, feasible by
+    construction (bounds are laid around A v0 for a reference point v0; equality rows hold at v0).
+    "formc_horizontal": nV = 100, nC = 101 -- stage 3 of MPCSolver::solve stacked as the reference would pass it to
+        solveQP: H = I, g = -mid, A = [a'; I], a_i = -e^{eta dt (N-1-i)}(e^{eta dt} - 1) (nominal eta),
+        box mid +- 0.045.
+    "forma_stacked": nV = 206, nC = 208 -- the canonical ISMPC QP (quad_as_bip_bang.m:121-257): variables
+        [zd_x(C); x_f(F); zd_y(C); y_f(F)], H = diag(1, Qf), rows = [stab_x; stab_y; ZMP_x(C); ZMP_y(C); kin_x(F); kin_y(F)],
+        ZMP rows dt*tril(1) - mapping, mapping with a linear blend over ds samples before each footstep switch."""
+    rng = np.random.default_rng(seed)
+    if shape == "formc_horizontal":
+        N, dt, eta = 100, 0.01, np.sqrt(9.81 / 0.69)
+        a = -np.exp(eta * dt * (N - 1 - np.arange(N))) * (np.exp(eta * dt) - 1.0)
+        H = np.broadcast_to(np.eye(N), (n, N, N)).copy()
+        A = np.zeros((n, N + 1, N)); A[:, 0, :] = a; A[:, 1:, :] = np.eye(N)
+        L = rng.uniform(0.05, 0.25, (n, 1)); k0 = rng.integers(0, 45, (n, 1))
+        t = k0 + np.arange(N)[None, :]
+        si, ri = t // 45, t % 45
+        mid = L * (si + np.where(ri < 35, 0.0, (ri - 35) / 10.0))
+        # the reference point sits on one side of its box over the first samples (where |a| is largest), so that the
+        # minimum-norm correction nu*a saturates several box rows: working sets of 1 + a handful of rows, as on the path
+        sgn = rng.choice([-1.0, 1.0], (n, 1)); width = rng.integers(18, 40, (n, 1))
+        u0 = mid + 0.045 * sgn * (np.arange(N)[None, :] < width) * rng.uniform(0.8, 1.0, (n, N))
+        lb = np.concatenate([(u0 @ a)[:, None], mid - 0.045], axis=1)
+        ub = np.concatenate([(u0 @ a)[:, None], mid + 0.045], axis=1)
+        return H, -mid, A, lb, ub
+    C, F, dt, step, ds, Qf = 100, 3, 0.01, 50, 20, 1e7
+    eta = np.sqrt(9.8 / 0.56)
+    nv1 = C + F; nV = 2 * nv1; nC = nV + 2
+    lam = np.exp(-eta * dt)
+    stab = (1.0 / eta) * (1.0 - lam) / (1.0 - lam ** C) * np.exp(-eta * dt * np.arange(C)) - dt * np.exp(-eta * dt * C)
+    P = dt * np.tril(np.ones((C, C)))
+    H = np.zeros((n, nV, nV)); g = np.zeros((n, nV)); A = np.zeros((n, nC, nV)); lb = np.zeros((n, nC)); ub = np.zeros((n, nC))
+    hd = np.concatenate([np.ones(C), Qf * np.ones(F), np.ones(C), Qf * np.ones(F)])
+    D = np.eye(F) - np.eye(F, k=-1)
+    for p in range(n):
+        j0 = int(rng.integers(0, step))
+        T = np.arange(1, F + 2) * step - j0                       # ticks until the next F+1 footstep switches
+        mp = np.zeros((C, F + 1))
+        for i in range(1, C + 1):
+            pf = int((T <= i).sum())
+            pf = min(pf, F)
+            rem = (T[pf] - i) if pf <= F else ds + 1
+            if rem > ds or pf == F:
+                mp[i - 1, pf] = 1.0
+            else:
+                mp[i - 1, pf] = rem / ds; mp[i - 1, pf + 1] = 1.0 - rem / ds
+        H[p][np.arange(nV), np.arange(nV)] = hd
+        for ax in range(2):
+            o = ax * nv1
+            A[p, ax, o:o + C] = stab
+            A[p, 2 + ax * C: 2 + (ax + 1) * C, o:o + C] = P
+            A[p, 2 + ax * C: 2 + (ax + 1) * C, o + C:o + nv1] = -mp[:, 1:]
+            A[p, 2 + 2 * C + ax * F: 2 + 2 * C + (ax + 1) * F, o + C:o + nv1] = D
+        stepl = rng.uniform(0.05, 0.15) * np.array([np.cos(0.3), np.sin(0.3)])
+        plan = np.arange(1, F + 1)[:, None] * stepl[None, :]
+        v0 = np.concatenate([rng.normal(0, 0.2, C), plan[:, 0] + rng.normal(0, 0.01, F),
+                             rng.normal(0, 0.2, C), plan[:, 1] + rng.normal(0, 0.01, F)])
+        r0 = A[p] @ v0
+        lb[p] = r0 - rng.uniform(0.0, 0.02, nC); ub[p] = r0 + rng.uniform(0.0, 0.02, nC)
+        lb[p, :2] = ub[p, :2] = r0[:2]
+        g[p] = np.concatenate([np.zeros(C), -Qf * plan[:, 0], np.zeros(C), -Qf * plan[:, 1]])
+    return H, g, A, lb, ub

@@ -166,3 +166,12 @@ def test_infeasible_dense_qps_are_flagged_like_qpoases(handle):
     assert np.array_equal(r["status"] != 0, o["ret"] != 0), (r["status"], o["ret"])
     ok = o["ret"] == 0
     assert primal_rel_err(r["x"][ok], o["x"][ok]).max() <= PRIMAL_TOL
+
+
+@pytest.mark.parametrize("shape", ["formc_horizontal", "forma_stacked"])
+def test_bench_workloads_of_the_dense_seam(handle, shape):
+    """The two dense workloads bench.py times through ismpc_qp_solve_batch (nV = 100 / nC = 101 and nV = 206 / nC = 208):
+    same answers as the reference's qpOASES call."""
+    H, g, A, lb, ub = synth.dense_qp_batch(shape, 24)
+    r, o = _check(handle, H, g, A, lb, ub, min_ok=1.0)
+    assert (o["nwsr"] > 0).any()
