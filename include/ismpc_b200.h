@@ -25,8 +25,10 @@
  * stream before returning; ISMPC_MEM_HOST_ASYNC (ismpc_formc_solve_batch, ismpc_forma_solve_batch and the ismpc_forma_rollout calls) is the same without the final
  * synchronisation: the call returns as soon as the copies and the kernel are enqueued, the host buffers must be
  * pinned and stay untouched, and the handle must not be used again, until the caller has synchronised `stream` --
- * two handles on two streams give a double-buffered pipeline.  The caller owns all buffers; the handle owns only its workspace.  One
- * handle per GPU, not shared between threads.  Functions return 0 or a negative ISMPC_ERR_* code;
+ * two handles on two streams give a double-buffered pipeline.  The caller owns all buffers; the handle owns only its workspace.
+ * A HANDLE SERIALISES ON ONE STREAM AT A TIME, IN EVERY MODE: all calls on a handle share its workspaces (the form-A work
+ * queue head, the dual active-set slices, the host-mode staging), so work enqueued through one handle on two streams, or
+ * from two threads, races.  Use one handle per stream / per thread; distinct handles are independent (also on one GPU).  Functions return 0 or a negative ISMPC_ERR_* code;
  * per-instance problems are reported in out[i].status -- the library never calls exit().
  * There is no CPU fallback: every entry point fails with ISMPC_ERR_CUDA if no sm_100 device works.
  */

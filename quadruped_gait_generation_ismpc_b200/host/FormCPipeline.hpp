@@ -46,13 +46,7 @@ public:
             if (!s.out) throw std::runtime_error("FormCPipeline: ismpc_host_alloc failed");
         }
     }
-    ~FormCPipeline()
-    {
-        for (Slot& s : slots_) {
-            if (s.h) { ismpc_wait(s.h, s.stream); ismpc_destroy(s.h); }
-            ismpc_host_free(s.in); ismpc_host_free(s.out);
-        }
-    }
+    ~FormCPipeline() = default;      // every Slot releases what it owns (also when the constructor throws half-way)
     FormCPipeline(const FormCPipeline&) = delete;
     FormCPipeline& operator=(const FormCPipeline&) = delete;
 
@@ -92,7 +86,17 @@ public:
     }
 
 private:
-    struct Slot { ismpc_handle* h = nullptr; void* stream = nullptr; char* in = nullptr; ismpc_formc_out_t* out = nullptr; };
+    struct Slot {
+        ismpc_handle* h = nullptr; void* stream = nullptr; char* in = nullptr; ismpc_formc_out_t* out = nullptr;
+        Slot() = default;
+        Slot(const Slot&) = delete;
+        Slot& operator=(const Slot&) = delete;
+        ~Slot()
+        {
+            if (h) { if (stream) ismpc_wait(h, stream); ismpc_destroy(h); }
+            ismpc_host_free(in); ismpc_host_free(out);
+        }
+    };
     static void check(int rc, ismpc_handle* h, const char* what)
     {
         if (rc != ISMPC_OK)

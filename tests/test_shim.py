@@ -164,3 +164,106 @@ def test_pipeline_example_runs():
     rows = np.array([[float(x) for x in ln.split()] for ln in out.strip().splitlines()])
     assert rows.shape == (5, 4) and np.array_equal(rows[:, 0], np.arange(5))
     assert np.abs(rows[:, 3] - 0.69).max() < 1e-3 and np.isfinite(rows).all()
+
+
+# ---- the drop-in header against the reference's OWN State / WalkState ("Fix the drop-in") -----------------
+REF_DIR = "/root/reference/AMR_code_DART"
+# AMR_code_DART/types.hpp:7-29 -- member names of `State`, in order (the stand-in is generated from this list where the
+# reference tree is absent, e.g. on the GPU box; where it is present the reference's own header is used)
+STATE_MEMBERS = ["comPos", "comVel", "comAcc", "zmpPos"] + \
+    ["%s%sFoot%s" % (lr, bf, q) for lr, bf in (("left", "Back"), ("right", "Back"), ("left", "Front"), ("right", "Front"))
+     for q in ("Pos", "Vel", "Acc")] + \
+    ["torsoOrient", "leftBackFootOrient", "rightBackFootOrient", "leftFrontFootOrient", "rightFrontFootOrient"]
+
+
+def _reference_headers(d):
+    """types.hpp and parameters.cpp as the drop-in header will find them: the reference's own files where
+    /root/reference exists (copied into the temporary build directory, never into the repository), generated stand-ins
+    elsewhere; utils.cpp is always a stub (the real one needs HPIPM / BLASFEO / Eigen::Geometry)."""
+    import shutil
+    inc = os.path.join(d, "ref")
+    os.makedirs(inc)
+    have_ref = os.path.exists(os.path.join(REF_DIR, "types.hpp"))
+    if have_ref:
+        shutil.copy(os.path.join(REF_DIR, "types.hpp"), inc)
+        shutil.copy(os.path.join(REF_DIR, "parameters.cpp"), inc)
+    else:
+        assert len(STATE_MEMBERS) == 21
+        body = "".join("    Eigen::Vector3d %s;\n" % m for m in STATE_MEMBERS)
+        meth = """
+    inline Eigen::VectorXd getComPose() { Eigen::VectorXd p(6); p << torsoOrient, comPos; return p; }
+    inline Eigen::VectorXd getSupportFootPose(bool s) { Eigen::VectorXd p(6); if (s == 0) p << leftBackFootOrient, leftBackFootPos; else p << rightBackFootOrient, rightBackFootPos; return p; }
+    inline Eigen::VectorXd getFrontSwingFootPose(bool s) { Eigen::VectorXd p(6); if (s == 1) p << rightFrontFootOrient, rightFrontFootPos; else p << leftFrontFootOrient, leftFrontFootPos; return p; }
+    inline Eigen::VectorXd getBackSwingFootPose(bool s) { Eigen::VectorXd p(6); if (s == 1) p << leftBackFootOrient, leftBackFootPos; else p << rightBackFootOrient, rightBackFootPos; return p; }
+    inline Eigen::VectorXd getRelComPose(bool s) { return vvRel(getComPose(), getSupportFootPose(s)); }
+    inline Eigen::VectorXd getRelFrontSwingFootPose(bool s) { return vvRel(getFrontSwingFootPose(s), getSupportFootPose(s)); }
+    inline Eigen::VectorXd getRelBackSwingFootPose(bool s) { return vvRel(getBackSwingFootPose(s), getSupportFootPose(s)); }
+"""
+        open(os.path.join(inc, "types.hpp"), "w").write(
+            '#pragma once\n#include <Eigen/Core>\n#include "utils.cpp"\nstruct State {\n' + body + meth + "};\n"
+            "struct WalkState { bool supportFoot; double simulationTime; int mpcIter, controlIter, footstepCounter, indInitial; };\n")
+        open(os.path.join(inc, "parameters.cpp"), "w").write(
+            "#pragma once\n#include <math.h>\n"
+            "const double mpcTimeStep = 0.01; const double controlTimeStep = 0.01; const double singleSupportDuration = 0.35;\n"
+            "const double doubleSupportDuration = 0.1; const double predictionTime = 1.0; const double comTargetHeight = 0.69;\n"
+            "const double footConstraintSquareWidth = 0.09; const double mass_hrp4 = 50.0; const double g = 9.81;\n"
+            "const double eta = sqrt(g/comTargetHeight); const int N = round(predictionTime/mpcTimeStep);\n"
+            "const int S = round(singleSupportDuration/mpcTimeStep); const int F = round(doubleSupportDuration/mpcTimeStep);\n")
+    open(os.path.join(inc, "utils.cpp"), "w").write(
+        "#pragma once\n#include <Eigen/Core>\n"
+        "inline Eigen::VectorXd vvRel(Eigen::VectorXd v2, Eigen::VectorXd v1) { Eigen::VectorXd r(6);"
+        " for (int i = 0; i < 6; ++i) r(i) = v2(i) - v1(i); return r; }\n")
+    return inc, have_ref
+
+
+def _build_dropin_driver(d):
+    inc, have_ref = _reference_headers(d)
+    exe = os.path.join(d, "dropin_driver")
+    libdir = os.path.dirname(binding.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "dropin_driver.cpp"),
+                           "-I" + inc, "-I" + os.path.join(ROOT, "quadruped_gait_generation_ismpc_b200", "host", "dropin"),
+                           "-I" + os.path.join(ROOT, "tests", "cpp", "eigen_stub"),
+                           "-L" + libdir, "-lismpc_b200", "-Wl,-rpath," + libdir])
+    return exe, have_ref
+
+
+def test_dropin_header_compiles_against_the_references_state():
+    """Controller.cpp's two call sites (`new MPCSolver(ftsp_and_time_ref)`, `desired = solver->solve(desired, walkState,
+    ftsp_and_time_ref)`) compile against host/dropin/MPCSolver.hpp with `State` / `WalkState` from the reference's own
+    types.hpp (in this container) or a stand-in with the same 21 members and getRel* methods (elsewhere).  No GPU: the
+    constructor fails loudly."""
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        exe, have_ref = _build_dropin_driver(d)
+        if os.path.exists(REF_DIR):
+            assert have_ref, "the reference tree is here but its types.hpp was not used"
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+        r = subprocess.run([exe, "1"], capture_output=True, text=True)
+        assert r.returncode != 0 and "ismpc_create" in r.stderr
+
+
+@pytest.mark.gpu
+def test_dropin_closed_loop_carries_every_member_and_matches_oracle():
+    """The drop-in class in the Controller's loop: CoM as the oracle's lock-step closed loop, every member of `State`
+    that solve() does not own comes back untouched (MPCSolver.cpp:210,500), and the plan is uploaded again exactly when
+    its contents change (once here), not every tick."""
+    from oracle import oracle as O
+    T = 24
+    with tempfile.TemporaryDirectory() as d:
+        exe, _ = _build_dropin_driver(d)
+        out = subprocess.check_output([exe, str(T)], text=True).strip().splitlines()
+    traj = np.array([[float(x) for x in ln.split()] for ln in out[:T]])
+    assert traj.shape == (T, 7) and (traj[:, 6] == 0).all()
+    assert out[T] == "carried 1" and out[T + 1] == "uploads 2" and out[T + 2] == "pose 6", out[T:]
+    model = abi.formc_model()
+    state, walk, inst, plan = synth.reference_formc_instance()
+    for k in range(T):
+        walk["sim_time"] = k
+        o = O.formc_batch(model, state, walk, inst, plan)
+        assert (o["ret"] == 0).all()
+        nxt = np.concatenate([o["out"]["next"]["com_pos"][0], o["out"]["next"]["com_vel"][0]])
+        assert np.abs(traj[k, :6] - nxt).max() < 1e-6, "tick %d" % k
+        state["com_pos"][0] = traj[k, :3]; state["com_vel"][0] = traj[k, 3:6]
+        walk["control_iter"] += 1
+        walk["mpc_iter"] = int(np.floor(walk["control_iter"][0] * 0.01 / 0.01))
