@@ -47,6 +47,7 @@ struct ismpc_handle {
     // form A
     bool forma_ready = false;
     ismpc_forma_model_t am{};
+    FormAOccCache a_occ;           // occupancy of the form-A kernels for the current shape (queried once)
     FormATuning a_tune;            // ismpc_set_option("forma_*"); the ISMPC_FORMA_* environment variables set the defaults at creation
     // staging (host-memory calls)
     DevBuf s_state, s_walk, s_cinst, s_cout, s_plan, s_primal, s_active, s_push, s_traj, s_status;
@@ -98,6 +99,7 @@ extern "C" int ismpc_create(ismpc_handle** out, int device, int max_batch)
     auto env_int = [](const char* nm, int dflt) { const char* v = getenv(nm); return (v && *v) ? atoi(v) : dflt; };
     h->a_tune.R = env_int("ISMPC_FORMA_R", 0); h->a_tune.warps_per_cta = env_int("ISMPC_FORMA_WPC", 0);
     h->a_tune.pdas = env_int("ISMPC_FORMA_PDAS", 1) != 0; h->a_tune.warm = env_int("ISMPC_FORMA_WARM", 1) != 0;
+    h->a_tune.reg = env_int("ISMPC_FORMA_REG", 1) != 0;
     *out = h;
     return ISMPC_OK;
 }
@@ -159,8 +161,9 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     }
     if (strcmp(name, "forma_pdas") == 0) { h->a_tune.pdas = value != 0; return ISMPC_OK; }
     if (strcmp(name, "forma_warm") == 0) { h->a_tune.warm = value != 0; return ISMPC_OK; }
+    if (strcmp(name, "forma_reg") == 0) { h->a_tune.reg = value != 0; return ISMPC_OK; }
     if (strcmp(name, "forma_R") == 0) { if (value < 0) return ISMPC_ERR_ARG; h->a_tune.R = value; return ISMPC_OK; }
-    if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 4) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
+    if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 2) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
     if (strcmp(name, "formc_kernel") == 0) {
         if (value < 0 || value > 2) return ISMPC_ERR_ARG;
         h->opt_formc_kernel = value;
@@ -495,7 +498,7 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     FormAArgs a;
     a.n = n; a.model = h->am; a.timing_len = timing_len; a.plan_rows = plan_rows; a.sm_count = h->sm_count;
     FormALaunchPlan lp;
-    forma_plan(h->am, h->sm_count, 2LL * n, h->a_tune, &lp);
+    forma_plan(h->am, h->sm_count, 2LL * n, h->a_tune, &lp, &h->a_occ);
     if (h->a_Lwork.ensure((lp.spill_doubles + 2) * sizeof(double)) || h->a_queue.ensure(sizeof(int))) return ISMPC_ERR_ALLOC;
     a.Jspill = lp.spill_doubles ? (double*)h->a_Lwork.p : nullptr;
     a.queue = (int*)h->a_queue.p;

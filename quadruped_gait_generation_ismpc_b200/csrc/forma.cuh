@@ -35,7 +35,7 @@ struct FormAArgs {
     int R;                 // rows of the inverse factor kept in shared memory (das.cuh)
     double* Jspill;        // global slices for rows >= R: one per resident warp (grid * warps_per_cta)
     int* queue;            // work queue head (items = (instance, axis) pairs), zeroed before the launch
-    int use_pdas;          // structured primal-dual active-set fast path enabled
+    int use_pdas;          // bit 0: structured primal-dual active-set fast path enabled; bit 1: its register-resident build
     int warm_start;        // rollout: start each tick from the previous tick's working set shifted by one
 };
 
@@ -267,6 +267,101 @@ __device__ inline bool warp_gauss_jordan(double* K, int dim)
     return true;
 }
 
+// ---- peeling step of the structured working-set iteration, on the shared-memory copies of the state (out of line: it
+// runs in a fraction of the iterations and is large) ----
+// When nothing is violated and the only rows with a wrong-sign multiplier are ends of runs, the plain rule peels the runs
+// one row per iteration (the next end row turns wrong once its neighbour is gone: a third of the cold mid-gait QPs spent
+// 20-45 iterations that way).  With nu and the footsteps frozen, the multiplier a run would have at its end if it stopped
+// at row e is closed form (segment constant of the new free stretch against the one-row segment before e), so the run is
+// cut back in one step to the first row whose multiplier keeps its sign.  The next solve corrects nu; overshoot shows up
+// as violated rows and is re-added wholesale.   st: working set, nxt: staged new state (0 = wrong end row; cut rows are
+// marked 3), cseg: segment constant per row.
+template <int NX, class XF>
+__device__ __forceinline__ void forma_peel_body(const FormAProb& pb, signed char* st, int* nxt, const double* cseg,
+                                                const double* rg, double nu, const XF& xf, unsigned end_mask, double qz_dt)
+{
+    const int lane = lane_id();
+    const int C = pb.C;
+    int r0, r1; lane_chunk(C, lane, r0, r1);
+    auto beta = [&](int k) -> double { return st[k] < 0 ? pb.lo_[k] : pb.hi_[k]; };
+    auto mx = [&](int i) -> double {                     // m_i . xf'
+        const int p = pb.mp[i]; const double w = pb.mw[i];
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < NX; ++f) s += ((p == f + 1 ? w : 0.0) + (p == f ? 1.0 - w : 0.0)) * xf[f];
+        return s;
+    };
+    auto tgt = [&](int k) -> double { return beta(k) + mx(k); };
+            unsigned todo = end_mask;
+            while (todo) {
+                const int L = __ffs(todo) - 1; todo &= todo - 1;
+                int a0, a1; lane_chunk(C, L, a0, a1);
+                for (int i = a0; i < a1; ++i) {
+                    const int sg = st[i];
+                    if (sg == 0 || nxt[i] != 0) continue;             // not a wrong end row (3 = cut by an earlier end)
+                    const bool right = i + 1 >= C || st[i + 1] != sg, left = i == 0 || st[i - 1] != sg;
+                    if (right) {
+                        int lb = -1, kn = C;                           // last row before i outside the run, next active row after i
+                        for (int k = r0; k < r1; ++k) {
+                            if (k < i && st[k] != sg) lb = k;
+                            if (k > i && st[k] != 0 && kn == C) kn = k;
+                        }
+                        lb = __reduce_max_sync(ISMPC_FULL_MASK, lb); kn = __reduce_min_sync(ISMPC_FULL_MASK, kn);
+                        const int s = lb + 1;
+                        const double tkn = kn < C ? tgt(kn) : 0.0, PAkn = kn < C ? pb.PA[kn] : 0.0;
+                        int best = -1;
+                        for (int e = r0 > s ? r0 : s; e < r1 && e <= i; ++e) {
+                            const double te = tgt(e);
+                            const double c_new = kn < C ? (qz_dt * (tkn - te) - nu * (PAkn - pb.PA[e])) * rg[kn - e] : 0.0;
+                            const double c_prev = e > s ? qz_dt * (te - tgt(e - 1)) - nu * pb.a[e] : cseg[s];
+                            const double y = c_prev - c_new;
+                            if (sg < 0 ? y > 0.0 : y < 0.0) best = e;
+                        }
+                        best = __reduce_max_sync(ISMPC_FULL_MASK, best);
+                        const int from = best >= s ? best + 1 : s;
+                        for (int k = r0 > from ? r0 : from; k < r1 && k <= i; ++k) nxt[k] = 3;
+                    }
+                    if (left) {
+                        int ub = C, kp = -1;                           // first row after i outside the run, last active row before i
+                        for (int k = r0; k < r1; ++k) {
+                            if (k > i && st[k] != sg && ub == C) ub = k;
+                            if (k < i && st[k] != 0) kp = k;
+                        }
+                        ub = __reduce_min_sync(ISMPC_FULL_MASK, ub); kp = __reduce_max_sync(ISMPC_FULL_MASK, kp);
+                        const int e = ub - 1;
+                        const double tkp = kp >= 0 ? tgt(kp) : 0.0, PAkp = kp >= 0 ? pb.PA[kp] : 0.0;
+                        const double c_after = e + 1 < C ? cseg[e + 1] : 0.0;
+                        int best = C;
+                        for (int s2 = r1 - 1 < e ? r1 - 1 : e; s2 >= r0 && s2 >= i; --s2) {
+                            const double ts = tgt(s2);
+                            const double c_new = (qz_dt * (ts - tkp) - nu * (pb.PA[s2] - PAkp)) * rg[s2 - kp];
+                            const double c_next = s2 < e ? qz_dt * (tgt(s2 + 1) - ts) - nu * pb.a[s2 + 1] : c_after;
+                            const double y = c_new - c_next;
+                            if (sg < 0 ? y > 0.0 : y < 0.0) best = s2;
+                        }
+                        best = __reduce_min_sync(ISMPC_FULL_MASK, best);
+                        const int to = best <= e ? best - 1 : e;
+                        for (int k = r0 > i ? r0 : i; k < r1 && k <= to; ++k) nxt[k] = 3;
+                    }
+                    __syncwarp();
+                }
+            }
+}
+static __device__ __noinline__ void forma_peel_smem(const FormAProb* pbp, signed char* st, int* nxt, const double* cseg,
+                                             const double* rg, double nu, double xf0, double xf1, double xf2,
+                                             unsigned end_mask, double qz_dt)
+{
+    const double xf[3] = {xf0, xf1, xf2};
+    forma_peel_body<3>(*pbp, st, nxt, cseg, rg, nu, xf, end_mask, qz_dt);
+}
+template <int FT>
+__device__ __noinline__ void forma_peel_smem_wide(const FormAProb* pbp, signed char* st, int* nxt, const double* cseg,
+                                                  const double* rg, double nu, const double (&xf)[FT], unsigned end_mask,
+                                                  double qz_dt)
+{
+    forma_peel_body<FT>(*pbp, st, nxt, cseg, rg, nu, xf, end_mask, qz_dt);
+}
+
 // On entry sm.lo / sm.hi hold the bounds in SHIFTED coordinates (ZMP rows: + shift*sum_f m_if; first kinematic
 // row: - shift), planf the footstep targets minus shift; sm.das.state the starting working set.
 // rg[g] = 1/g for g = 1..C.  On return 0: sm.x = [zd; xf] (xf absolute), sm.rv row values (shifted),
@@ -275,7 +370,7 @@ constexpr int PDAS_DAMP_AFTER = 12;
 constexpr int PDAS_MAX_ITERS = 80;
 
 template <int FT>
-__device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
+__device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
                                  const double* planf, const double* rg, int maxit, int* iters_out)
 {
     constexpr int NS = 2 + 2 * FT + FT * (FT + 1) / 2;
@@ -512,61 +607,11 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
         // the one-row segment before e), so the run is cut back in one step to the first row whose multiplier keeps
         // its sign.  The next solve corrects nu; overshoot shows up as violated rows and is re-added wholesale.
         if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, viol | wrong_in)) {
-            auto tgt = [&](int k) -> double { return beta(k) + mx(k); };
-            unsigned todo = end_mask;
-            while (todo) {
-                const int L = __ffs(todo) - 1; todo &= todo - 1;
-                int a0, a1; lane_chunk(C, L, a0, a1);
-                for (int i = a0; i < a1; ++i) {
-                    const int sg = st[i];
-                    if (sg == 0 || nxt[i] != 0) continue;             // not a wrong end row (3 = cut by an earlier end)
-                    const bool right = i + 1 >= C || st[i + 1] != sg, left = i == 0 || st[i - 1] != sg;
-                    if (right) {
-                        int lb = -1, kn = C;                           // last row before i outside the run, next active row after i
-                        for (int k = r0; k < r1; ++k) {
-                            if (k < i && st[k] != sg) lb = k;
-                            if (k > i && st[k] != 0 && kn == C) kn = k;
-                        }
-                        lb = __reduce_max_sync(ISMPC_FULL_MASK, lb); kn = __reduce_min_sync(ISMPC_FULL_MASK, kn);
-                        const int s = lb + 1;
-                        const double tkn = kn < C ? tgt(kn) : 0.0, PAkn = kn < C ? pb.PA[kn] : 0.0;
-                        int best = -1;
-                        for (int e = r0 > s ? r0 : s; e < r1 && e <= i; ++e) {
-                            const double te = tgt(e);
-                            const double c_new = kn < C ? (qz_dt * (tkn - te) - nu * (PAkn - pb.PA[e])) * rg[kn - e] : 0.0;
-                            const double c_prev = e > s ? qz_dt * (te - tgt(e - 1)) - nu * pb.a[e] : cseg[s];
-                            const double y = c_prev - c_new;
-                            if (sg < 0 ? y > 0.0 : y < 0.0) best = e;
-                        }
-                        best = __reduce_max_sync(ISMPC_FULL_MASK, best);
-                        const int from = best >= s ? best + 1 : s;
-                        for (int k = r0 > from ? r0 : from; k < r1 && k <= i; ++k) nxt[k] = 3;
-                    }
-                    if (left) {
-                        int ub = C, kp = -1;                           // first row after i outside the run, last active row before i
-                        for (int k = r0; k < r1; ++k) {
-                            if (k > i && st[k] != sg && ub == C) ub = k;
-                            if (k < i && st[k] != 0) kp = k;
-                        }
-                        ub = __reduce_min_sync(ISMPC_FULL_MASK, ub); kp = __reduce_max_sync(ISMPC_FULL_MASK, kp);
-                        const int e = ub - 1;
-                        const double tkp = kp >= 0 ? tgt(kp) : 0.0, PAkp = kp >= 0 ? pb.PA[kp] : 0.0;
-                        const double c_after = e + 1 < C ? cseg[e + 1] : 0.0;
-                        int best = C;
-                        for (int s2 = r1 - 1 < e ? r1 - 1 : e; s2 >= r0 && s2 >= i; --s2) {
-                            const double ts = tgt(s2);
-                            const double c_new = (qz_dt * (ts - tkp) - nu * (pb.PA[s2] - PAkp)) * rg[s2 - kp];
-                            const double c_next = s2 < e ? qz_dt * (tgt(s2 + 1) - ts) - nu * pb.a[s2 + 1] : c_after;
-                            const double y = c_new - c_next;
-                            if (sg < 0 ? y > 0.0 : y < 0.0) best = s2;
-                        }
-                        best = __reduce_min_sync(ISMPC_FULL_MASK, best);
-                        const int to = best <= e ? best - 1 : e;
-                        for (int k = r0 > i ? r0 : i; k < r1 && k <= to; ++k) nxt[k] = 3;
-                    }
-                    __syncwarp();
-                }
-            }
+            double xf3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int f = 0; f < (FT < 3 ? FT : 3); ++f) xf3[f] = xf[f];
+            if constexpr (FT <= 3) forma_peel_smem(&pb, st, nxt, cseg, rg, nu, xf3[0], xf3[1], xf3[2], end_mask, qz_dt);
+            else forma_peel_smem_wide<FT>(&pb, st, nxt, cseg, rg, nu, xf, end_mask, qz_dt);
         }
         {
             const bool damp = it >= PDAS_DAMP_AFTER && end_mask != 0u;
@@ -589,6 +634,87 @@ __device__ inline int forma_pdas(const FormAShared& sm, const FormAProb& pb, dou
     return rc;
 }
 
+}  // namespace ismpc
+#include "forma_reg.cuh"
+namespace ismpc {
+
+// self-check of a solve: equality residual and worst bound violation (sm.x, sm.rv against sm.lo / sm.hi)
+__device__ __forceinline__ void forma_selfcheck(const FormAShared& sm, int C, int n, double& eqv, double& viol)
+{
+    const int lane = lane_id();
+    eqv = 0.0; viol = 0.0;
+    for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
+    eqv = warp_sum(eqv);
+    for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
+    viol = warp_max(viol);
+}
+
+// COLD PATH of a tick, kept out of line so that the hot path (build + register-resident working-set iteration) stays
+// small enough for the instruction cache and the register budget: the shared-memory build of the structured solve
+// (shapes the register build does not cover: C > 128 or F > 3, or `forma_reg` = 0) and the dual active set that
+// backs both up.  On entry the bounds are in shifted coordinates iff use_pdas != 0.  Returns status bits.
+template <int FT>
+__device__ __noinline__ int forma_solve_slow(const FormAShared* smp, const FormAProb* pbp, double beq, double cur, int warm,
+                                             int use_pdas, int tried_reg, const double* rg, int* iters_io, double* eqv_out,
+                                             double* viol_out)
+{
+    const FormAShared& sm = *smp;
+    FormAProb pb = *pbp;
+    const int lane = lane_id();
+    const int C = pb.C, F = pb.F, n = C + F;
+    int status = 0, iters = *iters_io;
+    double eqv = 0.0, viol = 0.0;
+    bool solved = false;
+    if (use_pdas && !tried_reg) {
+        int rc = 1;
+        for (int attempt = 0; attempt < (warm ? 2 : 1) && rc != 0; ++attempt) {
+            if (attempt) {                                          // a stale guess can stall: retry from the empty set
+                for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+                __syncwarp();
+            }
+            int it2 = 0;
+            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
+            iters += it2;
+        }
+        if (rc == 0) {
+            forma_selfcheck(sm, C, n, eqv, viol);
+            solved = fabs(eqv - beq) <= 1e-8 * fmax(1.0, fabs(beq)) && viol <= 1e-8;
+        }
+    }
+    if (!solved) {
+        if (use_pdas) {                                             // back to absolute coordinates for the dual active set
+            __syncwarp();
+            for (int i = lane; i < C; i += 32) {
+                const int p = sm.mp[i]; const double w = sm.mw[i];
+                const double ms = cur * ((p >= 1 ? w : 0.0) + (p + 1 <= F ? 1.0 - w : 0.0));
+                sm.lo[i] -= ms; sm.hi[i] -= ms;
+            }
+            if (lane == 0) { sm.lo[C] += cur; sm.hi[C] += cur; }
+            __syncwarp();
+        }
+        // ---- dual active set from the unconstrained minimiser zd = 0, xf = plan ----
+        for (int i = lane; i < C; i += 32) sm.x[i] = 0.0;
+        for (int f = lane; f < F; f += 32) sm.x[C + f] = sm.z[C + f];
+        for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+        __syncwarp();
+        if (use_pdas) status |= ISMPC_ST_GI_FALLBACK;
+        DasWork w = sm.das;
+        w.q = 0; w.neq = 0;
+        int rc = das_add_equality(pb, w, sm.x, sm.z, n, 0.0, beq);
+        if (rc < 0) status |= ISMPC_ST_QP_FAIL;
+        w.neq = w.q;
+        int it2 = 0;
+        rc = das_solve(pb, w, sm.x, sm.rv, sm.z, 6 * n + 50, &it2);
+        iters += it2;
+        if (rc != 0) status |= ISMPC_ST_QP_FAIL;
+        forma_selfcheck(sm, C, n, eqv, viol);
+        // a point that misses the stability row or a bound is not a solution, whatever the loop returned
+        if (!(fabs(eqv - beq) <= 1e-7 * fmax(1.0, fabs(beq))) || !(viol <= 1e-7)) status |= ISMPC_ST_QP_FAIL;
+    }
+    *iters_io = iters; *eqv_out = eqv; *viol_out = viol;
+    return status;
+}
+
 // One tick for one (instance, axis) by one warp.  Returns status bits; writes x (primal) in sm.x.
 // in: the instance (by reference; read only), plan: this instance's fs_plan rows, ft: its fs_timing.
 // warm != 0: sm.das.state holds a working-set guess (previous tick's set shifted by one tick).
@@ -607,35 +733,61 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     const int ds = in.ds, n_timing = in.n_timing, n_fs = in.n_fs;
     const int step = ft[1] - ft[0];
     DasTimer tmt; tmt.start();
+    // Everything this tick reads from global memory is fetched up front, one independent load per lane, and handed round
+    // with shuffles afterwards (the mapping and the centerline loops used to chain dependent loads, ~10 round trips):
+    //   ftw (lane l):  fs_timing entry fsCounter + l (1-based, clamped to the table) -- the mapping needs l = 1 .. F+2
+    //   pw  (lane l):  plan row seg_lo + l (clamped), seg_lo = first centerline segment of the tail window j+C+1 .. j+P
+    //   clP:           the two plan rows of cl(P) (ABSOLUTE index P, copied as written -- bang.m:195-198)
+    int idxw = fs_counter + lane; if (idxw > n_timing) idxw = n_timing;
+    const int ftw = ft[idxw - 1];
+    const int seg_lo = (j + C) / step;
+    int rw = seg_lo + lane; if (rw > n_fs - 1) rw = n_fs - 1;
+    const double pw = plan[rw * 2 + axis];
+    int segP = (P - 1) / step, rP = (P - 1) - segP * step;
+    if (segP > n_fs - 2) { segP = n_fs - 2; rP = step - 1; }
+    const double clPa = plan[segP * 2 + axis], clPb = plan[(segP + 1) * 2 + axis];
     // ---- stability row coefficients (bang.m:200-207) ----
-    const double lam = exp(-eta * dt);
-    const double k1 = (1.0 / eta) * (1.0 - lam) / (1.0 - pow(lam, (double)C));
-    const double k2 = dt * exp(-eta * dt * (double)C);
+    // e^{-eta dt i} for i = lane + 32 k as exp(-eta dt lane) * exp(-32 eta dt)^k: five exp calls per lane for the whole
+    // build instead of thirteen and a pow (products of <= 8 factors: a few 1e-16 relative)
+    const double ed = eta * dt;
+    const double lam = exp(-ed), lamC = exp(-ed * (double)C), e32 = exp(-32.0 * ed), el = exp(-ed * (double)lane);
+    const double k1 = (1.0 / eta) * (1.0 - lam) / (1.0 - lamC);
+    const double k2 = dt * lamC;
     double saa = 0.0;
-    for (int i = lane; i < C; i += 32) {
-        double ai = k1 * exp(-eta * dt * (double)i) - k2;
-        sm.a[i] = ai; sm.PA[i] = ai; saa += ai * ai;
+    {
+        double ei = el;
+        for (int i = lane; i < C; i += 32) {
+            const double ai = k1 * ei - k2;
+            sm.a[i] = ai; sm.PA[i] = ai; saa += ai * ai;
+            ei *= e32;
+        }
     }
     saa = warp_sum(saa);
     __syncwarp();
     warp_prefix_sum_smem(sm.PA, C);
     // ---- mapping (bang.m:126-140) + ZMP bounds (bang.m:147-150) ----
+    // pf = number of footstep switches up to tick t (the timing table increases, so the reference's early-exit loop counts
+    // the leading run of `t >= ft`); the loops run a uniform number of rounds so that the shuffles are warp-wide
     const double zq = st3[2];
-    for (int i = lane; i < C; i += 32) {
+    const int rounds = (C + 31) >> 5;
+    for (int k = 0; k < rounds; ++k) {
+        const int i = lane + 32 * k;
         const int t = j + i + 1;                                    // MATLAB j+i with i 1-based
-        int pf = 0;
+        int pf = 0; bool run = true;
         for (int mstep = 1; mstep <= F + 1; ++mstep) {
-            int idx = fs_counter + mstep;                           // 1-based fs_timing index
-            if (idx <= n_timing && t >= ft[idx - 1]) pf = mstep; else break;
+            const int fm = __shfl_sync(ISMPC_FULL_MASK, ftw, mstep);
+            run = run && (fs_counter + mstep <= n_timing) && (t >= fm);
+            pf += run ? 1 : 0;
         }
-        int idx = fs_counter + pf + 1;
-        if (idx > n_timing) idx = n_timing;
-        const int rem = ft[idx - 1] - t;
-        double wgt = (rem > ds) ? 1.0 : (double)rem / (double)ds;
-        sm.mw[i] = wgt; sm.mp[i] = (signed char)pf;
-        const double m0 = (pf == 0) ? wgt : 0.0;                    // mapping(:,1): weight on the current footstep
-        sm.lo[i] = 1.0 * (-zq - w_box / 2) + m0 * cur;
-        sm.hi[i] = 1.0 * (-zq + w_box / 2) + m0 * cur;
+        const int fr = __shfl_sync(ISMPC_FULL_MASK, ftw, pf + 1);   // ft[min(fsCounter + pf + 1, n_timing) - 1]
+        if (i < C) {
+            const int rem = fr - t;
+            const double wgt = (rem > ds) ? 1.0 : (double)rem / (double)ds;
+            sm.mw[i] = wgt; sm.mp[i] = (signed char)pf;
+            const double m0 = (pf == 0) ? wgt : 0.0;                // mapping(:,1): weight on the current footstep
+            sm.lo[i] = 1.0 * (-zq - w_box / 2) + m0 * cur;
+            sm.hi[i] = 1.0 * (-zq + w_box / 2) + m0 * cur;
+        }
     }
     // ---- kinematic bounds (bang.m:163-190) ----
     for (int f = lane; f < F; f += 32) {
@@ -644,13 +796,38 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
         double c0 = (f == 0) ? cur : 0.0;
         sm.lo[C + f] = -bnd + c0; sm.hi[C + f] = bnd + c0;
     }
-    // ---- anticipative tail (bang.m:195-198); cl(P) uses the ABSOLUTE index P, copied as written ----
+    // ---- anticipative tail (bang.m:195-198) ----
+    auto cl_ab = [&](double a_, double b_, int seg, int r) -> double {      // forma_centerline on fetched rows
+        if (seg == 0 && !first_ramp) return a_;
+        if (r < step - ds) return a_;
+        const int kk = r - (step - ds);
+        if (ds == 1 || kk == ds - 1) return b_;
+        return a_ + (double)kk * ((b_ - a_) / (double)(ds - 1));
+    };
     double ant = 0.0;
-    for (int i = C + 1 + lane; i <= P; i += 32)
-        ant += exp(-eta * dt * (double)i) * (1.0 - exp(-eta * dt)) *
-               (forma_centerline(plan, n_fs, axis, step, ds, first_ramp, j + i) - fs_store);
+    {
+        const int span = (j + P - 1) / step - seg_lo + 1;            // plan rows the window touches, beyond seg_lo
+        const double one_m_lam = 1.0 - lam;
+        double ei = lamC * lam * el;                                  // e^{-eta dt (C + 1 + lane)}
+        const int trounds = (P - C + 31) >> 5;
+        for (int k = 0; k < trounds; ++k) {
+            const int i = C + 1 + lane + 32 * k;
+            const int t = j + i;
+            int seg = (t - 1) / step, r = (t - 1) - seg * step;
+            if (seg > n_fs - 2) { seg = n_fs - 2; r = step - 1; }
+            double a_, b_;
+            if (span <= 31) {                                         // the window's rows sit in the lanes: two shuffles
+                int o = seg - seg_lo; if (o < 0) o = 0; if (o > 30) o = 30;
+                a_ = __shfl_sync(ISMPC_FULL_MASK, pw, o); b_ = __shfl_sync(ISMPC_FULL_MASK, pw, o + 1);
+            } else {                                                  // (steps of a tick or two: read the table directly)
+                a_ = plan[seg * 2 + axis]; b_ = plan[(seg + 1) * 2 + axis];
+            }
+            if (i <= P) ant += ei * one_m_lam * (cl_ab(a_, b_, seg, r) - fs_store);
+            ei *= e32;
+        }
+    }
     ant = warp_sum(ant);
-    ant += exp(-eta * dt * (double)P) * (forma_centerline(plan, n_fs, axis, step, ds, first_ramp, P) - fs_store);
+    ant += exp(-ed * (double)P) * (cl_ab(clPa, clPb, segP, rP) - fs_store);
     const double beq = st3[0] + st3[1] / eta - st3[2] - ant;       // bang.m:209-210
     // ---- footstep targets plan(fsCounter+1 .. fsCounter+F) (bang.m:244-245), kept in the tail of sm.z ----
     for (int f = lane; f < F; f += 32) {
@@ -664,6 +841,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     int status = 0, iters = 0;
     bool solved = false;
     double eqv = 0.0, viol = 0.0;
+    int tried_reg = 0;
     if (use_pdas) {
         // shifted coordinates: positions relative to the current footstep (see forma_pdas)
         for (int i = lane; i < C; i += 32) {
@@ -674,57 +852,35 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
         if (lane == 0) { sm.lo[C] -= cur; sm.hi[C] -= cur; }
         for (int f = lane; f < F; f += 32) sm.z[f] = sm.z[C + f] - cur;
         __syncwarp();
-        int rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &iters);
-        if (rc != 0 && warm) {                                      // a stale guess can stall: retry from the empty set
-            for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
-            __syncwarp();
-            int it2 = 0;
-            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
-            iters += it2;
-        }
-        tmt.lap(11);
-        if (rc == 0) {
-            for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
-            eqv = warp_sum(eqv);
-            for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
-            viol = warp_max(viol);
-            solved = fabs(eqv - beq) <= 1e-8 * fmax(1.0, fabs(beq)) && viol <= 1e-8;
-        }
-        if (!solved) {                                              // back to absolute coordinates for the fallback
-            __syncwarp();
-            for (int i = lane; i < C; i += 32) {
-                const int p = sm.mp[i]; const double w = sm.mw[i];
-                const double ms = cur * ((p >= 1 ? w : 0.0) + (p + 1 <= F ? 1.0 - w : 0.0));
-                sm.lo[i] -= ms; sm.hi[i] -= ms;
+        if constexpr (FT <= 3) {
+            if ((use_pdas & 2) && C <= 128) {
+                // ---- hot path: the working-set iteration with this lane's rows in registers (forma_reg.cuh) ----
+                tried_reg = 1;
+                int rc = 1;
+                for (int attempt = 0; attempt < (warm ? 2 : 1) && rc != 0; ++attempt) {
+                    if (attempt) {                                  // a stale guess can stall: retry from the empty set
+                        for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
+                        __syncwarp();
+                    }
+                    int it2 = 0;
+                    rc = forma_pdas_reg<FT, 4>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
+                    iters += it2;
+                }
+                tmt.lap(11);
+                if (rc == 0) {
+                    forma_selfcheck(sm, C, n, eqv, viol);
+                    solved = fabs(eqv - beq) <= 1e-8 * fmax(1.0, fabs(beq)) && viol <= 1e-8;
+                }
             }
-            if (lane == 0) { sm.lo[C] += cur; sm.hi[C] += cur; }
-            __syncwarp();
         }
     }
     if (!solved) {
-        // ---- fallback: dual active set from the unconstrained minimiser zd = 0, xf = plan ----
-        for (int i = lane; i < C; i += 32) sm.x[i] = 0.0;
-        for (int f = lane; f < F; f += 32) sm.x[C + f] = sm.z[C + f];
-        for (int i = lane; i < n; i += 32) sm.das.state[i] = 0;
-        __syncwarp();
-        if (use_pdas) status |= ISMPC_ST_GI_FALLBACK;
-        DasWork w = sm.das;
-        w.q = 0; w.neq = 0;
-        int rc = das_add_equality(pb, w, sm.x, sm.z, n, 0.0, beq);
-        if (rc < 0) status |= ISMPC_ST_QP_FAIL;
-        w.neq = w.q;
-        int it2 = 0;
-        rc = das_solve(pb, w, sm.x, sm.rv, sm.z, 6 * n + 50, &it2);
-        iters += it2;
-        if (rc != 0) status |= ISMPC_ST_QP_FAIL;
-        // self-check: equality residual and worst bound violation
-        eqv = 0.0; viol = 0.0;
-        for (int i = lane; i < C; i += 32) eqv += sm.a[i] * sm.x[i];
-        eqv = warp_sum(eqv);
-        for (int i = lane; i < n; i += 32) viol = fmax(viol, fmax(sm.lo[i] - sm.rv[i], sm.rv[i] - sm.hi[i]));
-        viol = warp_max(viol);
-        // a point that misses the stability row or a bound is not a solution, whatever the loop returned
-        if (!(fabs(eqv - beq) <= 1e-7 * fmax(1.0, fabs(beq))) || !(viol <= 1e-7)) status |= ISMPC_ST_QP_FAIL;
+        // (copies: the out-of-line call takes addresses, and the hot path's own structs must not escape to local memory --
+        // when they did, every shared-memory access of the iteration became a generic load behind a pointer re-read)
+        FormAShared smc = sm; FormAProb pbc = pb;
+        int it_c = iters; double eqv_c = 0.0, viol_c = 0.0;
+        status |= forma_solve_slow<FT>(&smc, &pbc, beq, cur, warm, use_pdas, tried_reg, rg, &it_c, &eqv_c, &viol_c);
+        iters = it_c; eqv = eqv_c; viol = viol_c;
     }
     *iters_out = iters;
     *kkt_out = fmax(fabs(eqv - beq), fmax(viol, 0.0));
@@ -747,7 +903,8 @@ __device__ inline void forma_shift_working_set(signed char* st, int C, int F, bo
 // bang.m:55-58,265-290: [c; cd; z]+ = A_upd [c; cd; z] + B_upd * zd(1)
 __device__ __forceinline__ void forma_integrate(double eta, double dt, double s[3], double zd0)
 {
-    const double ch = cosh(eta * dt), sh = sinh(eta * dt);
+    const double ex = exp(eta * dt), exi = 1.0 / ex;
+    const double ch = 0.5 * (ex + exi), sh = 0.5 * (ex - exi);      // (eta dt ~ 0.04: (e^x - e^-x)/2 is good to a few 1e-15 relative)
     const double n0 = ch * s[0] + (sh / eta) * s[1] + (1 - ch) * s[2] + (dt - sh / eta) * zd0;
     const double n1 = (eta * sh) * s[0] + ch * s[1] + (-eta * sh) * s[2] + (1 - ch) * zd0;
     const double n2 = 0 * s[0] + 0 * s[1] + 1 * s[2] + dt * zd0;

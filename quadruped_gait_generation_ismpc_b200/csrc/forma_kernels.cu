@@ -9,7 +9,14 @@
 
 namespace ismpc {
 
-constexpr int FORMA_MAX_THREADS = 128;   // 4 warps = 4 (instance, axis) items in flight per CTA
+// CTAs of two warps (= two (instance, axis) items in flight per CTA).  The F <= 3 kernels are held to 128 registers: 8 CTAs
+// = 16 warps per SM, 2,368 items in flight on 148 SMs -- every item of a 1,024-instance tick has its warp from the start.
+// (Registers are granted in steps of 32 per thread here: 144 or 160 registers both mean 12 warps per SM, and then the
+// last 272 items of the tick start 25-30 us late and set its time -- per-item trace of the debug build.)
+constexpr int FORMA_MAX_THREADS = 64;
+#ifndef FORMA_MAX_REGS
+#define FORMA_MAX_REGS 128               // 8 CTAs x 64 threads x 128 registers: 16 resident warps per SM
+#endif
 
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
 {
@@ -38,7 +45,7 @@ __device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in
 }
 
 template <int FT>
-__global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick_kernel(FormAArgs a)
+__global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_tick_kernel(FormAArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = warp_id(), lane = lane_id();
@@ -55,6 +62,9 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
         const long long item = forma_next_item(a.queue);
         if (item >= 2LL * a.n) break;
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
+#ifdef ISMPC_PHASE_TIMING
+        const long long t_item0 = dbg_globaltimer();
+#endif
         const ismpc_forma_inst_t in = a.inst[inst];
         if (!forma_inst_in_range(in, a.fs_timing, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
             if (lane == 0) atomicOr(&a.out[inst].status, (int)ISMPC_ST_QP_FAIL);
@@ -86,6 +96,9 @@ __global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_tick
         }
         __syncwarp();
         tme.lap(17);
+#ifdef ISMPC_PHASE_TIMING
+        if (lane == 0 && item < 8192) { g_trace[3 * item] = t_item0; g_trace[3 * item + 1] = dbg_globaltimer(); g_trace[3 * item + 2] = ((long long)dbg_smid() << 32) | (unsigned)iters; }
+#endif
     }
 }
 
@@ -102,7 +115,7 @@ struct FormARolloutArgs {
 };
 
 template <int FT>
-__global__ void __launch_bounds__(FORMA_MAX_THREADS, FT <= 3 ? 4 : 2) forma_rollout_kernel(FormARolloutArgs ra)
+__global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_rollout_kernel(FormARolloutArgs ra)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FormAArgs& a = ra.base;
@@ -198,7 +211,10 @@ __global__ void forma_rollout_fold(int n, int n_ticks, ismpc_forma_inst_t* inst_
 }
 
 // Shared-memory / residency plan for a model: R rows of the inverse factor in shared memory, the rest spilled.
-void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, const FormATuning& tune, FormALaunchPlan* p)
+// occ (in/out, may be null): cache of the occupancy query for this (kernel, CTA size, shared memory) -- the caller keeps it
+// with its handle, the query costs microseconds.
+void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, const FormATuning& tune, FormALaunchPlan* p,
+                FormAOccCache* occ)
 {
     const int C = m.C, F = m.F, q = C + F + 1;
     const size_t lim = 227 * 1024;
@@ -210,7 +226,7 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, con
     int R = tune.R > 0 ? tune.R : R_dflt;
     if (R > q) R = q;
     if (R < 1) R = 1;
-    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
+    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : FORMA_MAX_THREADS / 32;
     if (wpc < 1) wpc = 1;
     if (wpc > FORMA_MAX_THREADS / 32) wpc = FORMA_MAX_THREADS / 32;
     const size_t hdr = forma_cta_smem_header(C);
@@ -218,15 +234,28 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, con
     while (R > 1 && forma_warp_smem_bytes(C, F, R) * wpc + hdr > lim) --R;
     p->R = R; p->warps_per_cta = wpc;
     p->smem = forma_warp_smem_bytes(C, F, R) * wpc + hdr;
-    int per_sm = (int)((lim + 1024) / (p->smem + 1024));      // 1 KB per-CTA reservation
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm * wpc > 48) per_sm = 48 / wpc > 0 ? 48 / wpc : 1;
+    int per_sm = 0;
+    if (occ && occ->per_sm > 0 && occ->F3 == (F <= 3) && occ->wpc == wpc && occ->smem == p->smem) per_sm = occ->per_sm;
+    if (per_sm <= 0) {
+        // what the GPU really keeps resident (registers and shared memory), asked of the runtime
+        int b = 0;
+        cudaError_t e;
+        if (F <= 3) {
+            cudaFuncSetAttribute(forma_tick_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<3>, 32 * wpc, p->smem);
+        } else {
+            cudaFuncSetAttribute(forma_tick_kernel<ISMPC_MAX_FSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<ISMPC_MAX_FSTEPS>, 32 * wpc, p->smem);
+        }
+        per_sm = (e == cudaSuccess && b > 0) ? b : 1;
+        if (occ) { occ->per_sm = per_sm; occ->F3 = (F <= 3); occ->wpc = wpc; occ->smem = p->smem; }
+    }
     long long ctas = (items + wpc - 1) / wpc;
     long long resident = (long long)per_sm * sm_count;
     p->grid = (int)(ctas < resident ? ctas : resident);
     if (p->grid < 1) p->grid = 1;
     p->spill_doubles = forma_spill_doubles(C, F, R) * (size_t)p->grid * wpc;
-    p->use_pdas = tune.pdas && (size_t)tri(R, 0) >= (size_t)(1 + 2 * F) * (2 + 2 * F);
+    p->use_pdas = (tune.pdas && (size_t)tri(R, 0) >= (size_t)(1 + 2 * F) * (2 + 2 * F)) ? (tune.reg ? 3 : 1) : 0;
     p->warm_start = tune.warm;
 }
 

@@ -109,6 +109,25 @@ if os.environ.get("ISMPC_DBG"):
         print("  mean duration: unsaturated %.0f ns (%d), saturated %.0f ns (%d), horizontal skipped %.0f ns (%d)"
               % (du[~sat & ~skipped].mean(), (~sat & ~skipped).sum(), du[sat].mean(), sat.sum(), du[skipped].mean() if skipped.any() else 0, skipped.sum()))
         sys.exit(0)
+    if which == "forma":
+        m = min(2 * n, 8192)
+        tr = (C.c_longlong * (3 * m))()
+        binding.lib().ismpc_debug_read_trace(tr, 3 * m)
+        tr = np.array(list(tr)).reshape(m, 3)
+        t0 = tr[:, 0].min()
+        st_, en_ = tr[:, 0] - t0, tr[:, 1] - t0
+        du = en_ - st_
+        its = tr[:, 2] & 0xffffffff
+        print("per item (ns): start p50 %d p90 %d max %d | duration p50 %d p90 %d p99 %d max %d | end max %d"
+              % (np.percentile(st_, 50), np.percentile(st_, 90), st_.max(), np.percentile(du, 50), np.percentile(du, 90),
+                 np.percentile(du, 99), du.max(), en_.max()))
+        A = np.stack([np.ones(m), its], axis=1)
+        coef, *_ = np.linalg.lstsq(A, du.astype(float), rcond=None)
+        print("duration ~ %.0f ns + %.0f ns per iteration; iterations per item: mean %.2f p99 %d max %d" % (coef[0], coef[1], its.mean(), np.percentile(its, 99), its.max()))
+        order = np.argsort(en_)
+        print("last 8 items to finish: (start, dur, iters)", [(int(st_[i]), int(du[i]), int(its[i])) for i in order[-8:]])
+        order = np.argsort(du)
+        print("longest 8 items: (start, dur, iters)", [(int(st_[i]), int(du[i]), int(its[i])) for i in order[-8:]])
     nz = [(i, x) for i, x in enumerate(v) if x]
     print("phase clocks (CTA 0): stamp -> cycles since the previous non-zero stamp:",
           [(nz[k][0], nz[k][1] - nz[k - 1][1]) for k in range(1, len(nz))], "total", nz[-1][1] - nz[0][1] if nz else 0)
