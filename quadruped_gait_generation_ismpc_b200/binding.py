@@ -349,3 +349,114 @@ class Handle:
                                           _ptr(x), _ptr(y), _ptr(ws), _ptr(status), _ptr(iters), abi.MEM_HOST, None)
         self._check(rc, "ismpc_qp_solve_batch")
         return dict(x=x, y=y, ws=ws, status=status, iters=iters)
+
+
+# ---- all GPUs of one box behind one C ABI (include/ismpc_b200_multigpu.h, lib/libismpc_b200_mg.so) --------------------
+MG_LIB_PATH = os.path.join(_HERE, "lib", "libismpc_b200_mg.so")
+MG_EXPORTS = ["ismpc_group_create", "ismpc_group_destroy", "ismpc_group_size", "ismpc_group_last_error",
+              "ismpc_group_kernel_launches", "ismpc_group_handle", "ismpc_group_shard", "ismpc_group_formc_configure",
+              "ismpc_group_formc_solve_batch", "ismpc_group_formc_scatter", "ismpc_group_formc_rollout", "ismpc_group_wait",
+              "ismpc_group_formc_gather"]
+GATHER_NCCL, GATHER_HOST = 0, 1
+_mglib = None
+
+
+def mglib():
+    global _mglib
+    if _mglib is not None:
+        return _mglib
+    if not os.path.exists(MG_LIB_PATH):
+        raise IsmpcError("multi-GPU library %s is missing: run __graft_entry__.build()" % MG_LIB_PATH)
+    lib()                                     # libismpc_b200.so first (the multi-GPU library is built on its C ABI)
+    L = C.CDLL(MG_LIB_PATH)
+    L.ismpc_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ismpc_group_destroy.argtypes = [C.c_void_p]
+    L.ismpc_group_size.argtypes = [C.c_void_p]
+    L.ismpc_group_last_error.restype = C.c_char_p
+    L.ismpc_group_last_error.argtypes = [C.c_void_p]
+    L.ismpc_group_kernel_launches.restype = C.c_int64
+    L.ismpc_group_kernel_launches.argtypes = [C.c_void_p]
+    L.ismpc_group_handle.restype = C.c_void_p
+    L.ismpc_group_handle.argtypes = [C.c_void_p, C.c_int]
+    L.ismpc_group_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ismpc_group_formc_configure.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ismpc_group_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.ismpc_group_formc_scatter.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.ismpc_group_formc_rollout.argtypes = [C.c_void_p, C.c_int]
+    L.ismpc_group_wait.argtypes = [C.c_void_p]
+    L.ismpc_group_formc_gather.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+    _mglib = L
+    return L
+
+
+class Group:
+    """One handle + stream + host thread per device, contiguous shards (include/ismpc_b200_multigpu.h)."""
+
+    def __init__(self, devices, max_batch_per_device, gather_mode=GATHER_NCCL):
+        self._L = mglib()
+        self._g = C.c_void_p()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._L.ismpc_group_create(C.byref(self._g), _ptr(dev), len(dev), int(max_batch_per_device), gather_mode)
+        if rc != 0:
+            raise IsmpcError("ismpc_group_create failed: %s (no sm_100 CUDA device? there is no CPU fallback)"
+                             % lib().ismpc_error_string(rc).decode())
+        self.n_devices = len(dev)
+
+    def close(self):
+        if self._g:
+            self._L.ismpc_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise IsmpcError("%s: %s [%s]" % (what, lib().ismpc_error_string(rc).decode(),
+                                             self._L.ismpc_group_last_error(self._g).decode()))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.ismpc_group_kernel_launches(self._g))
+
+    def shard(self, n_total, rank):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self._L.ismpc_group_shard(self._g, n_total, rank, C.byref(a), C.byref(b)), "ismpc_group_shard")
+        return a.value, b.value
+
+    def formc_configure(self, model, S, F_ds, plan):
+        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        self._check(self._L.ismpc_group_formc_configure(self._g, _ptr(model), int(S), int(F_ds), _ptr(plan), plan.shape[0]),
+                    "ismpc_group_formc_configure")
+
+    def formc_solve_batch(self, state, walk, inst, out=None):
+        n = len(state)
+        if out is None:
+            out = np.zeros(n, dtype=abi.FORMC_OUT)
+        self._check(self._L.ismpc_group_formc_solve_batch(self._g, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(out)),
+                    "ismpc_group_formc_solve_batch")
+        return out
+
+    def formc_solve_batch_raw(self, n, state, walk, inst, out):
+        self._check(self._L.ismpc_group_formc_solve_batch(self._g, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(out)),
+                    "ismpc_group_formc_solve_batch")
+
+    def formc_scatter(self, state, walk, inst, push=None):
+        self._check(self._L.ismpc_group_formc_scatter(self._g, len(state), _ptr(state), _ptr(walk), _ptr(inst), _ptr(push)),
+                    "ismpc_group_formc_scatter")
+        self._n = len(state)
+
+    def formc_rollout(self, n_ticks):
+        self._check(self._L.ismpc_group_formc_rollout(self._g, int(n_ticks)), "ismpc_group_formc_rollout")
+
+    def wait(self):
+        self._check(self._L.ismpc_group_wait(self._g), "ismpc_group_wait")
+
+    def formc_gather(self):
+        n = self._n
+        state = np.zeros(n, dtype=abi.STATE); walk = np.zeros(n, dtype=abi.WALK); status = np.zeros(n, dtype=np.int32)
+        self._check(self._L.ismpc_group_formc_gather(self._g, _ptr(state), _ptr(walk), _ptr(status)), "ismpc_group_formc_gather")
+        return dict(state=state, walk=walk, status=status)
