@@ -535,6 +535,18 @@ def main():
             line["dense_seam"] = bench_dense_seam(h, torch, dev, stream, hbm_peak, fp64_peak)
         except Exception as e:  # noqa: BLE001
             line["dense_seam"] = {"error": repr(e)}
+    # ---- the same work from ONE process driving all GPUs (lib/libismpc_b200_mg.so, host/MPCSolverMultiGpu.hpp): rank 0
+    # runs it on every GPU of the job while the other ranks wait on a CPU (gloo) barrier, so their GPUs are idle ----------
+    if world > 1:
+        try:
+            side = dist.new_group(backend="gloo")
+            dist.barrier(group=side)
+            if rank == 0:
+                line["multi_gpu_single_process"] = bench_group(torch, world, n, K, W, R, model, host_batches)
+            dist.barrier(group=side)
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                line["multi_gpu_single_process"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             reps = 3
@@ -555,6 +567,82 @@ def main():
     h.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_group(torch, G, n, K, W, R, model, host_batches):
+    """SURVEY 8(e) behind the boundary: one process, one handle + stream + persistent host thread per GPU
+    (ismpc_group_*, what host/MPCSolverMultiGpu.hpp wraps).  (a) K ticks of G x n instances through pinned HOST buffers
+    (every device copies its shard in, solves, copies its records out); (b) the closed loop resident on the GPUs:
+    scatter once, 1,000 ticks with pushes and no communication, then the one collective -- ncclAllGather of the result
+    records -- and the copy to the host, all inside the timed region."""
+    from quadruped_gait_generation_ismpc_b200 import abi, binding, synth
+    import ctypes as C
+    N = n * G
+    L = binding.lib()
+    g = binding.Group(list(range(G)), max(n, 1000), binding.GATHER_NCCL)
+    res = {"devices": G, "how": "rank 0 alone drives all %d GPUs through lib/libismpc_b200_mg.so (one handle, stream and host "
+                               "thread per device, contiguous shards); the other ranks wait on a CPU barrier" % G}
+    try:
+        plans = np.concatenate([b[3] for b in host_batches[:2]])
+        g.formc_configure(model, 35, 10, plans)
+        # (a) host-buffer ticks: two pinned input blocks of G x n instances, alternating
+        blocks = []
+        for b in range(2):
+            st, wk, ins, pl = host_batches[b]
+            ins = ins.copy(); ins["plan_first_row"] += b * host_batches[0][3].shape[0]
+            reps = [np.tile(a, G) for a in (st, wk, ins)]
+            ptrs = []
+            for a in reps:
+                p = L.ismpc_host_alloc(a.nbytes)
+                C.memmove(p, a.ctypes.data, a.nbytes)
+                ptrs.append(p)
+            blocks.append(ptrs)
+        out_p = L.ismpc_host_alloc(N * abi.FORMC_OUT.itemsize)
+        for k in range(max(W, 2)):
+            g.formc_solve_batch_raw(N, blocks[k % 2][0], blocks[k % 2][1], blocks[k % 2][2], out_p)
+        ts = []
+        for r in range(R):
+            t0 = time.perf_counter()
+            for k in range(K):
+                g.formc_solve_batch_raw(N, blocks[k % 2][0], blocks[k % 2][1], blocks[k % 2][2], out_p)
+            ts.append(time.perf_counter() - t0)
+        t = statistics.median(ts)
+        out = np.frombuffer(C.string_at(out_p, N * abi.FORMC_OUT.itemsize), dtype=abi.FORMC_OUT)
+        res["host_buffer_ticks"] = {"value": 3.0 * N * K / t, "unit": "QP solves/s", "ms_per_step": t / K * 1e3,
+                                    "instances_per_step": N, "repeats_s": spread(ts),
+                                    "failed_instances_last_step": int(((out["status"] & 7) != 0).sum()),
+                                    "h2d_bytes_per_step": int(N * (abi.STATE.itemsize + abi.WALK.itemsize + abi.FORMC_INST.itemsize)),
+                                    "d2h_bytes_per_step": int(N * abi.FORMC_OUT.itemsize),
+                                    "how": "ismpc_group_formc_solve_batch: one synchronous call per step, every device moves and "
+                                           "solves its shard concurrently"}
+        for ptrs in blocks:
+            for p in ptrs:
+                L.ismpc_host_free(p)
+        L.ismpc_host_free(out_p)
+        # (b) resident closed loop + the final NCCL gather
+        nr, T = 1000, 1000
+        steps_plan = (T + 2 * HORIZON + 900) // 45 + 3
+        state, walk, inst, plan = synth.formc_batch(nr, seed=(synth.SEED0 ^ 11), n_steps=steps_plan, k0_cap=100)
+        push = synth.push_batch(nr, seed=(synth.SEED0 ^ 5), formc=True)
+        state, walk, inst, push = [np.tile(a, G) for a in (state, walk, inst, push)]
+        g.formc_configure(model, 35, 10, plan)
+        ts = []
+        for r in range(3):
+            g.formc_scatter(state, walk, inst, push)
+            t0 = time.perf_counter()
+            g.formc_rollout(T)
+            fin = g.formc_gather()
+            ts.append(time.perf_counter() - t0)
+        t = min(ts)
+        res["closed_loop_resident"] = {"workload": "formC_rollout_trot_%dx%dticks_push on each of %d GPUs, then ncclAllGather of the "
+                                                   "state / walk-state / status records and one copy to the host" % (nr, T, G),
+                                       "instance_ticks_per_s": nr * G * T / t, "qp_solves_per_s": 3.0 * nr * G * T / t,
+                                       "ms_total": t * 1e3, "gathered_records": int(len(fin["state"])),
+                                       "instances_with_a_failed_tick": int(((fin["status"] & 7) != 0).sum())}
+        res["kernel_launches"] = g.kernel_launches
+    finally:
+        g.close()
+    return res
 
 
 def bench_horizon_sweep(h, torch, dev, stream, n=1024):

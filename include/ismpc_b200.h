@@ -197,7 +197,10 @@ void ismpc_host_free(void* p);
  *                         active set only.   "forma_warm": 1 = rollouts start each tick from the previous working set
  *                         (default), 0 = every tick cold.   "forma_R", "forma_warps_per_cta": shared-memory rows of
  *                         the fallback's factor and warps per CTA of the form-A kernels (0 = default).
- *                         The ISMPC_FORMA_{PDAS,WARM,R,WPC} environment variables set these defaults when a handle is created.
+ *                         "forma_reg": 1 = the working-set iteration keeps its rows in registers where the shape allows
+ *                         (C <= 128, F <= 3; default), 0 = shared-memory walk.
+ *                         The ISMPC_FORMA_{PDAS,WARM,R,WPC,REG} environment variables set these defaults when a handle is created.
+ *   "dense_dmma":         ismpc_qp_solve_batch: 1 = condensing GEMMs on the FP64 tensor cores (DMMA, default), 0 = CUDA cores.
  * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);
 

@@ -33,6 +33,7 @@ struct ismpc_handle {
     char err[256] = {0};
     int opt_formc_cluster = 0;     // 0 = automatic
     int opt_formc_variant = 0;     // 0 = by batch size, 2 = two warps per instance, 1 / 16 = one warp (register budgets)
+    int opt_dense_dmma = 1;        // dense seam: condensing GEMMs on the FP64 tensor cores (DMMA); 0 = CUDA cores
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
     int w_res[5] = {0, 0, 0, 0, 0};   // CTAs the GPU keeps resident: tick kernel (two register budgets), rollout kernel, pair tick / rollout kernels; 0 = not queried
@@ -164,6 +165,7 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     if (strcmp(name, "forma_reg") == 0) { h->a_tune.reg = value != 0; return ISMPC_OK; }
     if (strcmp(name, "forma_R") == 0) { if (value < 0) return ISMPC_ERR_ARG; h->a_tune.R = value; return ISMPC_OK; }
     if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 2) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
+    if (strcmp(name, "dense_dmma") == 0) { h->opt_dense_dmma = value != 0; return ISMPC_OK; }
     if (strcmp(name, "formc_kernel") == 0) {
         if (value < 0 || value > 2) return ISMPC_ERR_ARG;
         h->opt_formc_kernel = value;
@@ -794,7 +796,7 @@ extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, cons
     if (h->q_work.ensure(qp_dense_work_doubles(n, nV, nC) * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (mem == ISMPC_MEM_DEVICE) {
         int rc = qp_dense_launch(n, nV, nC, H, g, A, lbA, ubA, x, y_opt, (signed char*)ws_opt, status, iters_opt,
-                                 (double*)h->q_work.p, st);
+                                 (double*)h->q_work.p, h->opt_dense_dmma, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "qp_dense_launch");
         return ISMPC_OK;
@@ -815,7 +817,7 @@ extern "C" int ismpc_qp_solve_batch(ismpc_handle* h, int n, int nV, int nC, cons
         CK(cudaMemcpyAsync(dlb, lbA, szb * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dub, ubA, szb * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    int rc = qp_dense_launch(n, nV, nC, dH, dg, dA, dlb, dub, dx, dy, dws, dst, dit, (double*)h->q_work.p, st);
+    int rc = qp_dense_launch(n, nV, nC, dH, dg, dA, dlb, dub, dx, dy, dws, dst, dit, (double*)h->q_work.p, h->opt_dense_dmma, st);
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "qp_dense_launch");
     CK(cudaMemcpyAsync(x, dx, szg * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -86,9 +86,83 @@ __global__ void dense_tri_inverse(int N, double* work, size_t stride, size_t off
     }
 }
 
-// C (M x Nc) = X (M x K) * Y (Nc x K)', all row-major, batched over blockIdx.z; 16x16 shared-memory tiles.
-__global__ void dense_gemm_nt(int M, int Nc, int K, const double* Xb, size_t sx, const double* Yb, size_t sy,
-                              double* Cb, size_t sc)
+// C (M x Nc) = X (M x K) * Y (Nc x K)' on the FP64 tensor cores (DMMA: mma.sync.aligned.m8n8k4.row.col.f64), batched over
+// blockIdx.z.  This is the one GEMM-shaped piece of the path -- the "condensing" products of the dense solveQP seam:
+// Hinv = Linv' Linv, D = A Hinv, S = A D' -- and BASELINE.json's tensor-core clause applies to it: FP64 in, FP64
+// accumulate, so the 1e-6 parity bound is not touched (the same products on the CUDA cores agree to rounding).
+// Element (r, k) of X sits at X[r * sxr + k * sxk] (likewise Y), which covers the row-major operands and the transposed
+// read of Linv.  CTA = 4 warps, 64 x 64 tile of C, each warp 32 x 32 = 4 x 4 DMMA tiles (32 accumulators per thread);
+// K in chunks of 16 through shared memory, rows padded to 20 doubles so that the 8 x 4 / 4 x 8 fragment loads of a
+// half-warp fall into 16 distinct 8-byte banks.
+constexpr int DG_T = 64, DG_KC = 16, DG_LD = 20;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+dense_gemm_nt(int M, int Nc, int K, const double* Xb, size_t sx, int sxr, int sxk, const double* Yb, size_t sy, int syr, int syk,
+              double* Cb, size_t sc)
+{
+    __shared__ double xs[DG_T * DG_LD], ys[DG_T * DG_LD];
+    const double* X = Xb + (size_t)blockIdx.z * sx;
+    const double* Y = Yb + (size_t)blockIdx.z * sy;
+    double* C = Cb + (size_t)blockIdx.z * sc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.y * DG_T, col0 = blockIdx.x * DG_T;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;          // this warp's 32 x 32 corner inside the tile
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int k0 = 0; k0 < K; k0 += DG_KC) {
+        // stage the two 64 x 16 operand slabs; the index that is contiguous in global memory runs fastest over the threads
+        for (int e = tid; e < DG_T * DG_KC; e += 128) {
+            int r, k;
+            if (sxk == 1) { r = e / DG_KC; k = e - r * DG_KC; } else { k = e / DG_T; r = e - k * DG_T; }
+            const int gr = row0 + r, gk = k0 + k;
+            xs[r * DG_LD + k] = (gr < M && gk < K) ? X[(size_t)gr * sxr + (size_t)gk * sxk] : 0.0;
+            if (syk == 1) { r = e / DG_KC; k = e - r * DG_KC; } else { k = e / DG_T; r = e - k * DG_T; }
+            const int gc = col0 + r, gk2 = k0 + k;
+            ys[r * DG_LD + k] = (gc < Nc && gk2 < K) ? Y[(size_t)gc * syr + (size_t)gk2 * syk] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < DG_KC; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = xs[(wr + 8 * i + g) * DG_LD + kk + t4];     // A fragment: row g, column t4
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = ys[(wc + 8 * j + g) * DG_LD + kk + t4];     // B fragment: k = t4, column g
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    // C fragment: row g, columns 2 t4 and 2 t4 + 1 of every 8 x 8 tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = row0 + wr + 8 * i + g, c = col0 + wc + 8 * j + 2 * t4;
+            if (r < M) {
+                if (c < Nc) C[(size_t)r * Nc + c] = acc[i][j][0];
+                if (c + 1 < Nc) C[(size_t)r * Nc + c + 1] = acc[i][j][1];
+            }
+        }
+}
+
+// The same product on the CUDA cores (16 x 16 shared-memory tiles): kept as the cross-check of the tensor-core kernel
+// (ismpc_set_option "dense_dmma" = 0) and for the record of what DMMA buys (3.8 ms -> 1.6 ms per product of the
+// nV = 206 / nC = 208 shape over 1,024 problems).
+__global__ void dense_gemm_nt_cc(int M, int Nc, int K, const double* Xb, size_t sx, int sxr, int sxk, const double* Yb, size_t sy,
+                                 int syr, int syk, double* Cb, size_t sc)
 {
     __shared__ double xs[16][17], ys[16][17];
     const double* X = Xb + (size_t)blockIdx.z * sx;
@@ -98,17 +172,25 @@ __global__ void dense_gemm_nt(int M, int Nc, int K, const double* Xb, size_t sx,
     const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
     double acc = 0.0;
     for (int k0 = 0; k0 < K; k0 += 16) {
-        // xs[ty][tx] = X(row_block + ty, k0 + tx);  ys[ty][tx] = Y(col_block + ty, k0 + tx)
         int xr = blockIdx.y * 16 + ty, xk = k0 + tx;
-        xs[ty][tx] = (xr < M && xk < K) ? X[(size_t)xr * K + xk] : 0.0;
+        xs[ty][tx] = (xr < M && xk < K) ? X[(size_t)xr * sxr + (size_t)xk * sxk] : 0.0;
         int yr = blockIdx.x * 16 + ty, yk = k0 + tx;
-        ys[ty][tx] = (yr < Nc && yk < K) ? Y[(size_t)yr * K + yk] : 0.0;
+        ys[ty][tx] = (yr < Nc && yk < K) ? Y[(size_t)yr * syr + (size_t)yk * syk] : 0.0;
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) acc += xs[ty][kk] * ys[tx][kk];
         __syncthreads();
     }
     if (row < M && col < Nc) C[(size_t)row * Nc + col] = acc;
+}
+
+static void dense_gemm_launch(int use_dmma, int n, int M, int Nc, int K, const double* X, size_t sx, int sxr, int sxk,
+                              const double* Y, size_t sy, int syr, int syk, double* C, size_t sc, cudaStream_t st)
+{
+    if (use_dmma)
+        dense_gemm_nt<<<dim3((Nc + DG_T - 1) / DG_T, (M + DG_T - 1) / DG_T, n), 128, 0, st>>>(M, Nc, K, X, sx, sxr, sxk, Y, sy, syr, syk, C, sc);
+    else
+        dense_gemm_nt_cc<<<dim3((Nc + 15) / 16, (M + 15) / 16, n), dim3(16, 16), 0, st>>>(M, Nc, K, X, sx, sxr, sxk, Y, sy, syr, syk, C, sc);
 }
 
 // x0 = -Hinv g ; rv0 = A x0 ; one CTA per problem
@@ -243,7 +325,7 @@ void dense_hinv_launch(int n, int nV, double* work, size_t stride, size_t offLin
 
 int qp_dense_launch(int n, int nV, int nC, const double* H, const double* g, const double* A, const double* lbA,
                     const double* ubA, double* x, double* y, signed char* ws, int32_t* status, int32_t* iters,
-                    double* work, cudaStream_t st)
+                    double* work, int use_dmma, cudaStream_t st)
 {
     const DenseLayout l = dense_layout(nV, nC);
     const size_t stride = l.total;
@@ -251,16 +333,14 @@ int qp_dense_launch(int n, int nV, int nC, const double* H, const double* g, con
     dense_copy_H<<<dim3((unsigned)((vv + 255) / 256), n), 256, 0, st>>>(nV, H, work, stride, l.Lh);
     dense_cholesky<<<n, 256, 0, st>>>(nV, work, stride, l.Lh, status);
     dense_tri_inverse<<<dim3((nV + 63) / 64, n), 64, 0, st>>>(nV, work, stride, l.Lh, l.Linv);
-    dim3 tb(16, 16);
-    // Hinv = Linv' Linv
-    dense_hinv_launch(n, nV, work, stride, l.Linv, l.Hinv, st);
+    // Hinv = Linv' Linv: element (i, k) of the left operand is Linv[k][i] (strides 1, nV); the triangular zeros are
+    // multiplied through (2x the flops of the triangular sum, at several times its speed)
+    dense_gemm_launch(use_dmma, n, nV, nV, nV, work + l.Linv, stride, 1, nV, work + l.Linv, stride, 1, nV, work + l.Hinv, stride, st);
     if (nC > 0) {
         // D (nC x nV) = A (nC x nV) * Hinv' (Hinv symmetric, row-major over k)
-        dense_gemm_nt<<<dim3((nV + 15) / 16, (nC + 15) / 16, n), tb, 0, st>>>(
-            nC, nV, nV, A, (size_t)nC * nV, work + l.Hinv, stride, work + l.D, stride);
+        dense_gemm_launch(use_dmma, n, nC, nV, nV, A, (size_t)nC * nV, nV, 1, work + l.Hinv, stride, nV, 1, work + l.D, stride, st);
         // S (nC x nC) = A * D'
-        dense_gemm_nt<<<dim3((nC + 15) / 16, (nC + 15) / 16, n), tb, 0, st>>>(
-            nC, nC, nV, A, (size_t)nC * nV, work + l.D, stride, work + l.S, stride);
+        dense_gemm_launch(use_dmma, n, nC, nC, nV, A, (size_t)nC * nV, nV, 1, work + l.D, stride, nV, 1, work + l.S, stride, st);
     }
     dense_x0_rv<<<n, 128, 0, st>>>(nV, nC, g, A, work, stride, l, x);
     const int R = l.qmax < DENSE_R ? l.qmax : DENSE_R;

@@ -175,3 +175,19 @@ def test_bench_workloads_of_the_dense_seam(handle, shape):
     H, g, A, lb, ub = synth.dense_qp_batch(shape, 24)
     r, o = _check(handle, H, g, A, lb, ub, min_ok=1.0)
     assert (o["nwsr"] > 0).any()
+
+
+def test_tensor_core_gemms_equal_cuda_core_gemms(handle):
+    """The condensing products of the seam (Hinv = Linv'Linv, D = A Hinv, S = A D') on the FP64 tensor cores (DMMA, the
+    default) against the same products on the CUDA cores: same primal to 1e-9, same working sets -- FP64 in, FP64
+    accumulate, so BASELINE.json's 1e-6 bound is not touched by the choice."""
+    H, g, A, lb, ub = synth.dense_qp_batch("forma_stacked", 16)
+    a = handle.qp_solve_batch(H, g, A, lb, ub)
+    handle.set_option("dense_dmma", 0)
+    try:
+        b = handle.qp_solve_batch(H, g, A, lb, ub)
+    finally:
+        handle.set_option("dense_dmma", 1)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert primal_rel_err(a["x"], b["x"]).max() <= 1e-9
+    assert np.array_equal(a["ws"], b["ws"])
