@@ -388,6 +388,16 @@ int ismpc_kf_init(ismpc_kf_state_t* state, int n, const float* state0_xyz /* n x
 int ismpc_kf_filter_batch(ismpc_handle* h, int n, int n_steps, const ismpc_kf_model_t* model, ismpc_kf_state_t* state,
                           const ismpc_kf_sample_t* samples, float* zmp_opt, int mem, void* stream);
 
+/* The same filter with state, covariance and gains carried in FP64 (the model and the samples stay the reference's
+ * floats): the reference's single-precision standard-form update sigma - (K C) sigma loses the weakly observable states
+ * to rounding over a few hundred steps; this entry point is the variant for long runs.  joseph = 0: the reference's
+ * update in FP64 (pinned against an FP64 restatement of StateFiltering.cpp:97-133, tests/test_kf.py); joseph = 1: Joseph
+ * form (I - KC) sigma (I - KC)' + K R K', symmetric positive semi-definite by construction.
+ * zmp_opt (nullable): n x n_steps x 2 doubles. */
+typedef struct { double state[3][5]; double sigma[3][25]; } ismpc_kf_state64_t;
+int ismpc_kf_filter_batch_f64(ismpc_handle* h, int n, int n_steps, const ismpc_kf_model_t* model, ismpc_kf_state64_t* state,
+                              const ismpc_kf_sample_t* samples, double* zmp_opt, int joseph, int mem, void* stream);
+
 /* solveQP(H, f, A, lbA, ubA) (AMR_code_DART/utils.cpp:89-139) for n independent dense QPs of one shape:
  * min 1/2 x'Hx + g'x  s.t. lbA <= A x <= ubA.  H: n x nV x nV, g: n x nV, A: n x nC x nV (row-major),
  * lbA/ubA: n x nC.  x: n x nV.  y_opt (nullable): n x nC constraint duals (qpOASES sign);

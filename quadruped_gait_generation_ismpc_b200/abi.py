@@ -42,17 +42,18 @@ KF_MODEL = np.dtype([("h_com", "f4"), ("mass", "f4"), ("sampling_time", "f4"), (
                      ("q_process", "f4", (3, 4)), ("q_measurement", "f4", (3, 9))], align=True)
 KF_STATE = np.dtype([("state", "f4", (3, 5)), ("sigma", "f4", (3, 25))], align=True)
 KF_SAMPLE = np.dtype([("meas", "f4", (3, 3)), ("input", "f4", 3)], align=True)
+KF_STATE64 = np.dtype([("state", "f8", (3, 5)), ("sigma", "f8", (3, 25))], align=True)
 
 SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
          "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
          "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32, "ismpc_plan_model_t": 48, "ismpc_plan_req_t": 16, "ismpc_kf_model_t": 172, "ismpc_kf_state_t": 360,
-         "ismpc_kf_sample_t": 48}
+         "ismpc_kf_sample_t": 48, "ismpc_kf_state64_t": 720}
 DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
           "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
           "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
           "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH, "ismpc_feet_model_t": FEET_MODEL,
           "ismpc_feet_inst_t": FEET_INST, "ismpc_plan_model_t": PLAN_MODEL, "ismpc_plan_req_t": PLAN_REQ,
-          "ismpc_kf_model_t": KF_MODEL, "ismpc_kf_state_t": KF_STATE, "ismpc_kf_sample_t": KF_SAMPLE}
+          "ismpc_kf_model_t": KF_MODEL, "ismpc_kf_state_t": KF_STATE, "ismpc_kf_sample_t": KF_SAMPLE, "ismpc_kf_state64_t": KF_STATE64}
 
 # status bits
 ST_OK, ST_Z_FAIL, ST_X_FAIL, ST_Y_FAIL, ST_WINDOW, ST_XY_SKIPPED, ST_NAN_GUARD, ST_QP_FAIL = 0, 1, 2, 4, 8, 16, 32, 64

@@ -20,7 +20,7 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
            "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan",
            "ismpc_handle_stream", "ismpc_wait", "ismpc_host_alloc", "ismpc_host_free", "ismpc_formc_rollout_ex",
-           "ismpc_forma_rollout_ex2"]
+           "ismpc_forma_rollout_ex2", "ismpc_kf_filter_batch_f64"]
 
 _lib = None
 
@@ -85,6 +85,7 @@ def lib():
     L.ismpc_plan_generate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_kf_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.ismpc_kf_filter_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ismpc_kf_filter_batch_f64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.ismpc_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
     L.ismpc_handle_stream.restype = C.c_void_p
     L.ismpc_handle_stream.argtypes = [C.c_void_p]
@@ -285,6 +286,17 @@ class Handle:
         rc = self._L.ismpc_kf_filter_batch(self._h, n, n_steps, _ptr(model), _ptr(state), _ptr(samples), _ptr(zmp),
                                            abi.MEM_HOST, None)
         self._check(rc, "ismpc_kf_filter_batch")
+        return state, zmp
+
+    def kf_filter_batch_f64(self, model, state, samples, joseph=False, want_zmp=True):
+        """FP64-carried filter: state (n,) KF_STATE64 (copied, returned advanced); samples (n, n_steps) KF_SAMPLE."""
+        n, n_steps = samples.shape
+        state = state.copy()
+        samples = np.ascontiguousarray(samples)
+        zmp = np.zeros((n, n_steps, 2)) if want_zmp else None
+        rc = self._L.ismpc_kf_filter_batch_f64(self._h, n, n_steps, _ptr(model), _ptr(state), _ptr(samples), _ptr(zmp),
+                                               1 if joseph else 0, abi.MEM_HOST, None)
+        self._check(rc, "ismpc_kf_filter_batch_f64")
         return state, zmp
 
     # ---- footstep-plan generators -------------------------------------------------------------------

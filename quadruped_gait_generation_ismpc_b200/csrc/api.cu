@@ -779,6 +779,38 @@ extern "C" int ismpc_kf_filter_batch(ismpc_handle* h, int n, int n_steps, const 
     return ISMPC_OK;
 }
 
+extern "C" int ismpc_kf_filter_batch_f64(ismpc_handle* h, int n, int n_steps, const ismpc_kf_model_t* model,
+                                         ismpc_kf_state64_t* state, const ismpc_kf_sample_t* samples, double* zmp_opt, int joseph,
+                                         int mem, void* stream)
+{
+    if (!h || !model) return ISMPC_ERR_ARG;
+    if (n < 0 || n > h->max_batch || n_steps < 0 || !state || !samples) return ISMPC_ERR_ARG;
+    if (!(model->sampling_time > 0.0f) || !(model->mass > 0.0f)) return ISMPC_ERR_MODEL;
+    if (n == 0 || n_steps == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mem == ISMPC_MEM_DEVICE) {
+        int rc = kf_filter64_launch(n, n_steps, *model, state, samples, zmp_opt, joseph != 0, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "kf_filter64_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
+    const size_t bs = (size_t)n * sizeof(ismpc_kf_state64_t), bu = (size_t)n * n_steps * sizeof(ismpc_kf_sample_t);
+    const size_t bz = (size_t)n * n_steps * 2 * sizeof(double);
+    if (h->f_inst.ensure(bs) || h->f_plan.ensure(bu) || (zmp_opt && h->f_out.ensure(bz))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpyAsync(h->f_inst.p, state, bs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->f_plan.p, samples, bu, cudaMemcpyHostToDevice, st));
+    int rc = kf_filter64_launch(n, n_steps, *model, (ismpc_kf_state64_t*)h->f_inst.p, (const ismpc_kf_sample_t*)h->f_plan.p,
+                                zmp_opt ? (double*)h->f_out.p : nullptr, joseph != 0, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "kf_filter64_launch");
+    CK(cudaMemcpyAsync(state, h->f_inst.p, bs, cudaMemcpyDeviceToHost, st));
+    if (zmp_opt) CK(cudaMemcpyAsync(zmp_opt, h->f_out.p, bz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Generic dense QP (solveQP seam)
 // ---------------------------------------------------------------------------------------------------

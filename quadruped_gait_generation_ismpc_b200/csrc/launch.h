@@ -45,6 +45,8 @@ int plan_generate_launch(int n, const ismpc_plan_model_t& m, const ismpc_plan_re
                          int rows, cudaStream_t st);
 int kf_filter_launch(int n, int n_steps, const ismpc_kf_model_t& m, ismpc_kf_state_t* state, const ismpc_kf_sample_t* samples,
                      float* zmp, cudaStream_t st);
+int kf_filter64_launch(int n, int n_steps, const ismpc_kf_model_t& m, ismpc_kf_state64_t* state, const ismpc_kf_sample_t* samples,
+                       double* zmp, int joseph, cudaStream_t st);
 int feet_place_launch(int n, int n_ticks, const ismpc_feet_model_t& m, const ismpc_feet_inst_t* inst,
                       const int32_t* fs_timing, int timing_len, const double* pred_traj, double* foot_plan,
                       int foot_plan_rows, cudaStream_t st);
