@@ -200,6 +200,12 @@ void ismpc_host_free(void* p);
  *                         "forma_reg": 1 = the working-set iteration keeps its rows in registers where the shape allows
  *                         (C <= 128, F <= 3; default), 0 = shared-memory walk.
  *                         The ISMPC_FORMA_{PDAS,WARM,R,WPC,REG} environment variables set these defaults when a handle is created.
+ *   "formc_pdl":          1 = ismpc_formc_solve_batch launches its tick kernel as a PROGRAMMATIC DEPENDENT of the previous kernel
+ *                         on the stream: the tick's CTAs start filling SM slots while the previous tick's slowest CTAs
+ *                         still run (the tick of 1,024 instances is latency-bound: median CTA 6.8 us, slowest 9.2 us).
+ *                         The caller thereby DECLARES consecutive calls on that stream independent: a call must not read
+ *                         device buffers the previous call writes, nor share its output buffers.  Default 0: calls
+ *                         on a stream are strictly ordered (a tick may consume the previous tick's output).
  *   "dense_dmma":         ismpc_qp_solve_batch: 1 = condensing GEMMs on the FP64 tensor cores (DMMA, default), 0 = CUDA cores.
  * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);

@@ -33,6 +33,7 @@ struct ismpc_handle {
     char err[256] = {0};
     int opt_formc_cluster = 0;     // 0 = automatic
     int opt_formc_variant = 0;     // 0 = by batch size, 2 = two warps per instance, 1 / 16 = one warp (register budgets)
+    int opt_formc_pdl = 0;         // tick launches as programmatic dependents of the previous kernel on the stream
     int opt_dense_dmma = 1;        // dense seam: condensing GEMMs on the FP64 tensor cores (DMMA); 0 = CUDA cores
     int opt_formc_kernel = 0;      // 0 = automatic (warp-per-instance where it covers the horizon), 1 = CTA/cluster-per-instance, 2 = warp
     int c_ctas_per_sm = 1;
@@ -165,6 +166,7 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     if (strcmp(name, "forma_reg") == 0) { h->a_tune.reg = value != 0; return ISMPC_OK; }
     if (strcmp(name, "forma_R") == 0) { if (value < 0) return ISMPC_ERR_ARG; h->a_tune.R = value; return ISMPC_OK; }
     if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 2) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
+    if (strcmp(name, "formc_pdl") == 0) { h->opt_formc_pdl = value != 0; return ISMPC_OK; }
     if (strcmp(name, "dense_dmma") == 0) { h->opt_dense_dmma = value != 0; return ISMPC_OK; }
     if (strcmp(name, "formc_kernel") == 0) {
         if (value < 0 || value > 2) return ISMPC_ERR_ARG;
@@ -270,7 +272,7 @@ static int formc_launch_tick(ismpc_handle* h, const FormCArgs& a, int n, cudaStr
     int rc = formc_warp_prepare(h, wa, a, n);
     if (rc) return rc;
     int grid = 0;
-    return formc_tick_warp_launch(wa, n, h->w_res, h->opt_formc_variant, &grid, st);
+    return formc_tick_warp_launch(wa, n, h->w_res, h->opt_formc_variant, h->opt_formc_pdl, &grid, st);
 }
 
 static int formc_launch_rollout(ismpc_handle* h, const FormCArgs& a, int n, ismpc_state_t* state_io, ismpc_walk_t* walk_io,

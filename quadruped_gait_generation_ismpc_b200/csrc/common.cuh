@@ -34,6 +34,12 @@ struct DasTimer {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch (sm_90+): launch_dependents lets the NEXT kernel on the stream -- if it was launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization -- start filling SM slots as this grid's CTAs retire; dependency_wait
+// blocks until the PREVIOUS grid has completed and its memory is visible.  Both are no-ops in ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; for x normal and finite (callers check their pivots).
 __device__ __forceinline__ double fast_rcp(double x)
 {

@@ -286,6 +286,7 @@ __device__ __forceinline__ void formc_tick_pair(const FormCWarpShared& sm, doubl
                     riccati_solve(sm, N, E, lane, dt, mass, g, z0 + dt * zd0, zd0);
                 }
             }
+            pdl_dependency_wait();         // the workspace slice is shared with the previous launch on this handle (no-op unless launched as its programmatic dependent)
             for (int e = 0; e < E; ++e) if (lane * E + e < N) ws[lane * E + e] = sm.f[e * 32 + lane];
             __syncwarp();
             status |= formc_vertical_general(N, T, c1, mdl.fz_max, ws, c_lo, ne, &it_z, &zstate);

@@ -118,6 +118,7 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
     const int N = a.model.N;
     FormCWarpShared sm;
     formc_warp_carve(smem_d, formc_warp_epl(N), sm);
+    pdl_launch_dependents();
     if (lane == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
     __syncwarp();
     uint32_t parity = 0;
@@ -150,6 +151,7 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
     FormCWarpShared sm;
     formc_warp_carve(smem_d, E, sm);
     double* red = smem_d + (FORMC_WARP_VECS * E * 32 + 2);
+    pdl_launch_dependents();
     if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
     __syncthreads();
     uint32_t parity = 0;
@@ -330,22 +332,34 @@ int formc_warp_resident(int N, int sm_count, int res[5])
 
 // One 32-thread CTA per instance up to what stays resident, grid-stride beyond that (bounds the workspace of the
 // general vertical path).
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int* grid_out, cudaStream_t st)
+// pdl != 0: the launch carries cudaLaunchAttributeProgrammaticStreamSerialization -- this tick's CTAs may start while the
+// previous kernel on the stream still has CTAs running (see ismpc_set_option "formc_pdl").
+template <class K>
+static int formc_launch_ex(K kern, int grid, int block, size_t smem, cudaStream_t st, int pdl, const FormCWarpArgs& a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int pdl, int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
     if (variant == 2 || (variant == 0 && n <= res[3])) {
         const int grid = n < res[3] ? n : res[3];
         *grid_out = grid;
-        formc_tick_pair_kernel<<<grid, 64, formc_pair_smem_bytes(a.base.model.N), st>>>(a);
-        return (int)cudaGetLastError();
+        return formc_launch_ex(formc_tick_pair_kernel, grid, 64, formc_pair_smem_bytes(a.base.model.N), st, pdl, a);
     }
     const bool big = variant == 16 || (variant == 0 && n > res[0]);
     const int cap = big ? res[1] : res[0];
     const int grid = n < cap ? n : cap;
     *grid_out = grid;
-    if (big) formc_tick_warp_kernel<16><<<grid, 32, smem, st>>>(a);
-    else formc_tick_warp_kernel<1><<<grid, 32, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    if (big) return formc_launch_ex(formc_tick_warp_kernel<16>, grid, 32, smem, st, pdl, a);
+    return formc_launch_ex(formc_tick_warp_kernel<1>, grid, 32, smem, st, pdl, a);
 }
 
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,

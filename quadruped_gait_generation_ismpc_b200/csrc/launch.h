@@ -26,7 +26,7 @@ int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, d
 int formc_law_launch(const ismpc_formc_model_t& m, int n_pat, const double* ric, double* law, cudaStream_t st, long long* launches);
 int formc_warp_supported(int N);
 int formc_warp_resident(int N, int sm_count, int res[5]);   // 0 or a cudaError_t
-int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int* grid_out, cudaStream_t st);
+int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int pdl, int* grid_out, cudaStream_t st);
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,
                               const ismpc_push_t* push, int n_ticks, double* traj, int32_t* status, int32_t* trace, int n,
                               const int res[5], int variant, cudaStream_t st);

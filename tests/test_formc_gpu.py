@@ -405,3 +405,40 @@ def test_out_of_range_plan_rows_are_flagged_not_read(handle):
     for i in (3, 10, 20):
         assert r["status"][i] & abi.ST_WINDOW
         assert np.array_equal(r["state"]["com_pos"][i], state["com_pos"][i])
+
+
+def test_programmatic_dependent_launch_gives_the_same_records(handle):
+    """`formc_pdl` = 1: consecutive ticks on one stream are launched as programmatic dependents (a tick's CTAs start while
+    the previous tick's last CTAs still run).  Twelve independent batches back to back -- a third of the instances on the
+    general vertical path, whose per-CTA workspace is shared between consecutive launches of a handle and is therefore
+    fenced with griddepcontrol.wait -- give bit for bit the records of strictly ordered launches."""
+    import torch
+    model = abi.formc_model()
+    handle.formc_set_model(model); handle.formc_prepare_gait(35, 10)
+    n, nb = 1024, 12
+    dev = torch.device("cuda", 0)
+    batches = [synth.formc_batch(n, seed=300 + b, z_spread=0.06 if b % 3 == 0 else 0.01) for b in range(nb)]
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    d = [[to_dev(x) for x in b] for b in batches]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(pdl):
+        handle.set_option("formc_pdl", pdl)
+        outs = [torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev) for _ in range(nb)]
+        try:
+            for rep in range(3):
+                for b in range(nb):
+                    handle.formc_solve_batch_raw(n, d[b][0].data_ptr(), d[b][1].data_ptr(), d[b][2].data_ptr(), d[b][3].data_ptr(),
+                                                 batches[b][3].shape[0], outs[b].data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
+            torch.cuda.synchronize()
+        finally:
+            handle.set_option("formc_pdl", 0)
+        return [np.frombuffer(o.cpu().numpy().tobytes(), dtype=abi.FORMC_OUT) for o in outs]
+
+    a, b = run(0), run(1)
+    assert any((x["iters"][:, 0] > 0).any() for x in a), "vacuous: the general vertical path never ran"
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
