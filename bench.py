@@ -37,10 +37,10 @@ L2_BYTES = 126 * 1024 * 1024
 # state 72 + walk 24 + inst 40 + 7 plan rows x 32 (the rows the 2N window touches) + out 128
 B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 # executed FP64 flops per instance-tick: counted by ncu on the committed capture (2 per DFMA, 1 per DMUL/DADD, thread
-# level, predicated-on), profiles/r1z_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
+# level, predicated-on), profiles/r2_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
 FLOP_FORMC_FALLBACK = 28000
 F_REF_FORMC = 2 * 0.96e6 + 0.49e6
-NCU_JSON = os.path.join(ROOT, "profiles", "r1z_formc_tick_pair_ncu.json")
+NCU_JSON = os.path.join(ROOT, "profiles", "r2_formc_tick_pair_ncu.json")
 
 
 def load_ncu():
