@@ -65,17 +65,29 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
     const double wbox = pb.hi_[0] - pb.lo_[0];
 #pragma unroll
     for (int e = 0; e < E; ++e) { const int i = r0 + e; stv[e] = i < C ? (int)st_s[i] : 0; }
+    // coefficient of footstep f in ZMP row i (column f+1 of `mapping`): (p == f+1 ? w : 0) + (p == f ? 1-w : 0).  Tabulated once
+    // per solve in the three vectors that are free until the solve ends (x, rv, scr) -- recomputing them from (p, w) with
+    // select chains wherever they are used was a quarter of the iteration's instructions.
+    double* mct[3] = {sm.x, sm.rv, pb.scr};
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = r0 + e;
+        if (i < C) {
+            const int p = (int)pb.mp[i]; const double w = pb.mw[i];
+#pragma unroll
+            for (int f = 0; f < FT; ++f) mct[f][i] = (p == f + 1 ? w : 0.0) + (p == f ? 1.0 - w : 0.0);
+        }
+    }
+    __syncwarp();
 #define FORMA_REG_LOAD_ROWS()                                                                          \
-    double lo[E], PAv[E], mwv[E];                                                                      \
-    int mpv[E];                                                                                        \
+    double lo[E], PAv[E], mcv[E][FT];                                                                  \
     _Pragma("unroll") for (int e = 0; e < E; ++e) {                                                    \
         const int ic = r0 + e < C ? r0 + e : C - 1;      /* rows past C mirror the last row; never active, never tested */ \
-        lo[e] = pb.lo_[ic]; PAv[e] = pb.PA[ic]; mwv[e] = pb.mw[ic]; mpv[e] = (int)pb.mp[ic];           \
+        lo[e] = pb.lo_[ic]; PAv[e] = pb.PA[ic];                                                        \
+        _Pragma("unroll") for (int f = 0; f < FT; ++f) mcv[e][f] = mct[f][ic];                         \
     }                                                                                                  \
     auto hi_of = [&](int e) -> double { return lo[e] + wbox; };                                        \
-    auto mc = [&](int e, int f) -> double {      /* coefficient of footstep f in ZMP row e (column f+1 of `mapping`) */ \
-        return (mpv[e] == f + 1 ? mwv[e] : 0.0) + (mpv[e] == f ? 1.0 - mwv[e] : 0.0);                  \
-    };                                                                                                 \
+    auto mc = [&](int e, int f) -> double { return mcv[e][f]; };                                       \
     auto beta = [&](int e) -> double { return stv[e] < 0 ? lo[e] : lo[e] + wbox; };
     int kst = (lane < F) ? (int)st_s[C + lane] : 0;      // kinematic row `lane`
     double qpl[FT];                                      // Qf * footstep target
