@@ -40,19 +40,21 @@ B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 # level, predicated-on), profiles/r2_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
 FLOP_FORMC_FALLBACK = 28000
 F_REF_FORMC = 2 * 0.96e6 + 0.49e6
-NCU_JSON = os.path.join(ROOT, "profiles", "r2_formc_tick_pair_ncu.json")
+NCU_JSON = {"formc_tick_pair_kernel": os.path.join(ROOT, "profiles", "r2_formc_tick_pair_ncu.json"),
+            "formc_tick_warp_kernel<16>": os.path.join(ROOT, "profiles", "r2_formc_tick_warp16_ncu.json")}
 
 
-def load_ncu():
+def load_ncu(kernel="formc_tick_pair_kernel"):
     """Figures of the dominant kernel from the committed `ncu --set full` capture of this very workload:
     dram_bytes_per_launch = dram__bytes_read.sum + dram__bytes_write.sum, fp64_flop_per_instance_tick."""
-    if os.path.exists(NCU_JSON):
-        return json.load(open(NCU_JSON))
+    p = NCU_JSON.get(kernel)
+    if p and os.path.exists(p):
+        return json.load(open(p))
     return {}
 
 
-def load_traffic():
-    v = load_ncu().get("dram_bytes_per_launch")
+def load_traffic(kernel="formc_tick_pair_kernel"):
+    v = load_ncu(kernel).get("dram_bytes_per_launch")
     return int(v) if v is not None else None
 
 
@@ -307,7 +309,45 @@ def main():
         h.set_option("formc_pdl", 0)
         print("bench.py: programmatic-dependent-launch arm skipped (%s)" % e, file=sys.stderr)
     use_pdl = bool(pdl_ms) and pdl_equal
-    total_ms_max = statistics.median(pdl_ms) if use_pdl else serial_ms
+    # ---- ... and with the THROUGHPUT build of the tick kernel (formc_variant = 16: one warp per instance held to 128
+    # registers, 16 resident warps per SM -- two 1,024-instance ticks fit on the GPU side by side, where the two-warp latency
+    # build fills it with one): the configuration for a stream of independent batches, and the stated mode of `value`.
+    # Its records are compared with strictly ordered launches of the same build. ----
+    thr_ms = []
+    thr_equal = None
+    try:
+        h.set_option("formc_variant", 16)
+        for k in range(min(K, 4)):
+            slots[(W + k) % n_slots]["out"].zero_()
+            step(W + k)
+        torch.cuda.synchronize()
+        ref16 = [slots[(W + k) % n_slots]["out"].clone() for k in range(min(K, 4))]
+        h.set_option("formc_pdl", 1)
+        gt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gt, stream=cs):
+            sp = torch.cuda.current_stream().cuda_stream
+            for k in range(K):
+                step(W + k, on=sp)
+        h.set_option("formc_pdl", 0); h.set_option("formc_variant", 0)
+        gt.replay(); barrier()
+        thr_equal = all(bool(torch.equal(ref16[k], slots[(W + k) % n_slots]["out"])) for k in range(len(ref16)))
+        for r in range(R):
+            flush_l2(r)
+            barrier()
+            g0.record(); gt.replay(); g1.record()
+            barrier()
+            thr_ms.append(sharding.max_over_ranks(g0.elapsed_time(g1), device=dev))
+    except Exception as e:
+        h.set_option("formc_pdl", 0); h.set_option("formc_variant", 0)
+        print("bench.py: throughput-build arm skipped (%s)" % e, file=sys.stderr)
+    use_thr = bool(thr_ms) and thr_equal
+    headline_ms = thr_ms if use_thr else (pdl_ms if use_pdl else graph_ms)
+    headline_kernel = "formc_tick_warp_kernel<16>" if use_thr else "formc_tick_pair_kernel"
+    headline_mode = ("throughput build (formc_variant = 16: one warp per instance, 16 resident warps per SM) launched as programmatic "
+                     "dependents (formc_pdl = 1): the K steps are independent batches, two ticks run side by side" if use_thr else
+                     "two-warp latency build launched as programmatic dependents (formc_pdl = 1): the K steps are independent "
+                     "batches, a tick starts under the tail of the previous one" if use_pdl else "strictly ordered launches")
+    total_ms_max = statistics.median(headline_ms)
     value = 3.0 * n * world * K / (total_ms_max * 1e-3)
     # one tick as a one-node graph, replayed on its own: what a caller that launches a tick and waits for it sees
     g1t = torch.cuda.CUDAGraph()
@@ -356,7 +396,7 @@ def main():
     # the timed region is K launches of the dominant kernel back to back on one stream and nothing else:
     # its CUDA-event time / K is that kernel's average launch duration (launch gaps included)
     kernel_ms = total_ms_max / K
-    FLOP_FORMC = float(load_ncu().get("fp64_flop_per_instance_tick", FLOP_FORMC_FALLBACK))
+    FLOP_FORMC = float(load_ncu(headline_kernel).get("fp64_flop_per_instance_tick", FLOP_FORMC_FALLBACK))
 
     # ---- e2e: the C ABI with HOST buffers (pinned), copies inside the timed region -------------------------
     # The serving loop a caller runs, in the reference's host language: host/FormCPipeline.hpp over the C ABI
@@ -380,7 +420,7 @@ def main():
         o1 = st.nbytes; o2 = o1 + wk.nbytes
         d["pack_res_ptr"] = (t.data_ptr(), t.data_ptr() + o1, t.data_ptr() + o2)
         pinned.append(d)
-    h2d = pinned[0]["pack_res"].numel(); d2h = n * abi.FORMC_OUT.itemsize
+    h2d_dma = pinned[0]["pack_res"].numel(); d2h = n * abi.FORMC_OUT.itemsize
     h.formc_set_plan(all_plans)
 
     def e2e_sync_step(k, out):
@@ -398,6 +438,21 @@ def main():
             e2e_sync_step(k, out_sync)
         sync_s.append(sharding.max_over_ranks(time.perf_counter() - t0, device=dev))
     e2e_sync_s = statistics.median(sync_s)
+    # ... and the packed call with the constants resident: one 128-byte record per instance each way, read / written in
+    # place by the kernel (the latency a single Controller-style caller sees per tick of its fleet)
+    st0, wk0, ins0, _ = host_batches[0]
+    h.formc_set_instances(ins0)                     # (batch 0's plan rows start at row 0 of the resident table)
+    tk_sync = torch.from_numpy(abi.pack_ticks(st0, wk0).view(np.uint8).reshape(-1).copy()).pin_memory()
+    for k in range(W):
+        h.formc_solve_batch_packed_raw(n, tk_sync.data_ptr(), None, None, 0, out_sync.data_ptr(), mem=abi.MEM_HOST, stream=stream)
+    sync_p = []
+    for r in range(min(R, 3)):
+        t0 = time.perf_counter()
+        for k in range(K):
+            h.formc_solve_batch_packed_raw(n, tk_sync.data_ptr(), None, None, 0, out_sync.data_ptr(), mem=abi.MEM_HOST, stream=stream)
+        sync_p.append(sharding.max_over_ranks(time.perf_counter() - t0, device=dev))
+    e2e_sync_packed_s = statistics.median(sync_p)
+    h.formc_set_instances(None)
 
     import ctypes as C
     hostlib = C.CDLL(os.path.join(os.path.dirname(binding.LIB_PATH), "libismpc_host.so"))
@@ -409,6 +464,10 @@ def main():
     hostlib.ismpc_host_pool_launches.restype = C.c_longlong
     hostlib.ismpc_host_pool_launches.argtypes = [C.c_void_p]
     hostlib.ismpc_host_last_error.restype = C.c_char_p
+    hostlib.ismpc_host_pool_set_instances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    hostlib.ismpc_host_pool_run_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hostlib.ismpc_host_pool_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    hostlib.ismpc_host_pool_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
     cores_per_rank = max(1, (os.cpu_count() or 1) // world)
     T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "2" if cores_per_rank >= 4 else "1"))   # host threads, one pipeline each
@@ -417,38 +476,77 @@ def main():
     if not pool:
         raise RuntimeError("ismpc_host_pool_create: " + hostlib.ismpc_host_last_error().decode())
     hostlib.ismpc_host_pool_set_spin_us(pool, 200000)     # parked workers poll: a repeat never starts with a futex wake-up
-    blocks = (C.c_void_p * len(pinned))(*[d["pack_res"].data_ptr() for d in pinned])
     csum = C.c_longlong(0); el = C.c_double(0.0)
-    out_cpp = np.zeros((T_HOST, D_HOST, n), dtype=abi.FORMC_OUT)
-    l_before = hostlib.ismpc_host_pool_launches(pool)
     # warm-up rounded up to whole rounds of the threads, and at least one call on every handle (a handle's first call
     # allocates its staging and workspace and queries occupancy: milliseconds that do not belong in the timed region)
     WC = max(-(-W // T_HOST) * T_HOST, T_HOST * D_HOST)
-    if hostlib.ismpc_host_pool_run(pool, 0, WC, blocks, len(pinned), C.byref(csum), None, None) != 0:
-        raise RuntimeError("ismpc_host_pool_run: " + hostlib.ismpc_host_last_error().decode())
+    # (a) e2e, the headline: PACKED tick records (ismpc_formc_solve_batch_packed).  Every slot of the pool serves one fleet
+    # of n robots whose constants (ismpc_formc_set_instances) and footstep plans (ismpc_formc_set_plan) are resident -- they
+    # are constructor data / globals of the reference -- and every step moves what solve() takes and returns per tick: one
+    # 128-byte {State, WalkState} record per instance in, one 128-byte result record out, between PINNED HOST buffers and
+    # the GPU.  With pinned buffers the kernel itself reads and writes them over PCIe (one 128-byte read and one posted
+    # write per instance; a DMA copy of this size occupies a copy engine for ~6 us whatever its size, profiles/README.md),
+    # so a step is one kernel launch.  A fleet's tick records are 4 successive ticks of its closed loop, used in rotation.
+    BLK = 4
+    fleet_ptrs, fleet_keep = [], []
+    for slot in range(T_HOST * D_HOST):
+        st, wk, ins, pl = host_batches[slot % len(host_batches)]
+        ins_res = ins.copy(); ins_res["plan_first_row"] += sum(b[3].shape[0] for b in host_batches[:slot % len(host_batches)])
+        if hostlib.ismpc_host_pool_set_instances(pool, slot // D_HOST, slot % D_HOST, ins_res.ctypes.data) != 0:
+            raise RuntimeError("ismpc_host_pool_set_instances: " + hostlib.ismpc_host_last_error().decode())
+        for j in range(BLK):
+            r_ = h.formc_rollout(st, wk, ins_res, all_plans, j, want_traj=False) if j else dict(state=st, walk=wk)
+            t_ = torch.from_numpy(abi.pack_ticks(r_["state"], r_["walk"]).view(np.uint8).reshape(-1).copy()).pin_memory()
+            fleet_keep.append((t_, r_["state"], r_["walk"], ins_res)); fleet_ptrs.append(t_.data_ptr())
+    tick_blocks = (C.c_void_p * len(fleet_ptrs))(*fleet_ptrs)
+    h2d = n * abi.FORMC_TICK.itemsize
+    if T_HOST * D_HOST >= 8:
+        # eight or more ticks in flight: the throughput build of the tick kernel (one warp per instance, 16 resident warps
+        # per SM) lets two ticks run side by side; the two-warp latency build fills the GPU with one tick
+        hostlib.ismpc_host_pool_set_option(pool, b"formc_variant", 16)
+    out_cpp = np.zeros((T_HOST, D_HOST, n), dtype=abi.FORMC_OUT)
+    l_before = hostlib.ismpc_host_pool_launches(pool)
+    if hostlib.ismpc_host_pool_run_packed(pool, 0, WC, tick_blocks, BLK, C.byref(csum), None, None) != 0:
+        raise RuntimeError("ismpc_host_pool_run_packed: " + hostlib.ismpc_host_last_error().decode())
     e2e_runs = []
-    k_next = WC
+    host_wait, host_submit = [], []
     for r in range(R):
         barrier()
-        rc_cpp = hostlib.ismpc_host_pool_run(pool, k_next, K, blocks, len(pinned), C.byref(csum), out_cpp.ctypes.data, C.byref(el))
+        rc_cpp = hostlib.ismpc_host_pool_run_packed(pool, 0, K, tick_blocks, BLK, C.byref(csum), out_cpp.ctypes.data, C.byref(el))
         if rc_cpp != 0:
-            raise RuntimeError("ismpc_host_pool_run: " + hostlib.ismpc_host_last_error().decode())
+            raise RuntimeError("ismpc_host_pool_run_packed: " + hostlib.ismpc_host_last_error().decode())
         e2e_runs.append(sharding.max_over_ranks(el.value, device=dev))
-        k_next += K
+        w_, s_ = C.c_double(0.0), C.c_double(0.0)
+        hostlib.ismpc_host_pool_stats(pool, C.byref(w_), C.byref(s_))
+        host_wait.append(w_.value); host_submit.append(s_.value)
     e2e_cpp_s = statistics.median(e2e_runs)
     e2e_cpp_launches = hostlib.ismpc_host_pool_launches(pool) - l_before
-    # the records of the last step against a synchronous call on the same pinned block
-    k_last = k_next - 1
-    t_last = (k_last - (k_next - K)) % T_HOST
-    cpp_equal = None; bad_cpp = None
-    e2e_sync_step(k_last, out_sync)
-    ref_last = np.frombuffer(out_sync.numpy().tobytes(), dtype=abi.FORMC_OUT)
-    for s_ in range(D_HOST):                                   # the slot that holds it is one of the thread's D slots
-        if out_cpp[t_last, s_].tobytes() == ref_last.tobytes():
-            cpp_equal = True
-            bad_cpp = int(((out_cpp[t_last, s_]["status"] & 7) != 0).sum())
-    if cpp_equal is None:
-        cpp_equal = False
+    # the records of the last tick every slot served, against a synchronous three-array call on the same values
+    cpp_equal = True; bad_cpp = 0
+    per_thread = [len(range(t_, K, T_HOST)) for t_ in range(T_HOST)]
+    for slot in range(T_HOST * D_HOST):
+        t_, s_ = slot // D_HOST, slot % D_HOST
+        served = len(range(s_, per_thread[t_], D_HOST))          # ticks slot s_ of thread t_ served in the last run
+        if served == 0:
+            continue
+        _, st_l, wk_l, ins_l = fleet_keep[slot * BLK + (served - 1) % BLK]
+        h.set_option("formc_variant", 16 if T_HOST * D_HOST >= 8 else 0)          # the build the pool's handles use
+        ref_l = h.formc_solve_batch(st_l, wk_l, ins_l, None, want_primal=False, want_active=False)["out"]
+        h.set_option("formc_variant", 0)
+        cpp_equal = cpp_equal and out_cpp[t_, s_].tobytes() == ref_l.tobytes()
+        bad_cpp = max(bad_cpp, int(((out_cpp[t_, s_]["status"] & 7) != 0).sum()))
+    # (b) the same loop with the three arrays of ismpc_formc_solve_batch moved by the copy engines (one copy in, one copy
+    # out per step; the instance records travel with every step): what the packed path replaced, kept beside it
+    hostlib.ismpc_host_pool_set_option(pool, b"formc_variant", 0)
+    blocks = (C.c_void_p * len(pinned))(*[d["pack_res"].data_ptr() for d in pinned])
+    hostlib.ismpc_host_pool_run(pool, 0, WC, blocks, len(pinned), C.byref(csum), None, None)
+    dma_runs = []
+    for r in range(min(R, 3)):
+        barrier()
+        if hostlib.ismpc_host_pool_run(pool, WC + r * K, K, blocks, len(pinned), C.byref(csum), None, C.byref(el)) != 0:
+            raise RuntimeError("ismpc_host_pool_run: " + hostlib.ismpc_host_last_error().decode())
+        dma_runs.append(sharding.max_over_ranks(el.value, device=dev))
+    e2e_dma_s = statistics.median(dma_runs)
     hostlib.ismpc_host_pool_destroy(pool)
     clk = clocks.stop()
 
@@ -465,11 +563,16 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(n),
-                "repeats": {"timed_replays_of_the_K_step_graph_ms": spread(pdl_ms if use_pdl else graph_ms),
-                            "all_ms": pdl_ms if use_pdl else graph_ms, "value_is": "3 x instances x n_gpus x K / median",
-                            "mode": ("programmatic dependent launch (formc_pdl = 1): the K steps are independent batches, a tick "
-                                     "starts under the tail of the previous one" if use_pdl else "strictly ordered launches"),
-                            "records_equal_strictly_ordered_arm": pdl_equal},
+                "repeats": {"timed_replays_of_the_K_step_graph_ms": spread(headline_ms),
+                            "all_ms": headline_ms, "value_is": "3 x instances x n_gpus x K / median",
+                            "mode": headline_mode,
+                            "records_equal_strictly_ordered_launches_of_the_same_build": thr_equal if use_thr else pdl_equal},
+                "latency_build_pdl": (None if not pdl_ms else
+                                      {"value": 3.0 * n * world * K / (statistics.median(pdl_ms) * 1e-3), "unit": "QP solves/s",
+                                       "ms_per_step": statistics.median(pdl_ms) / K, "repeats_ms": spread(pdl_ms),
+                                       "records_equal_strictly_ordered_arm": pdl_equal,
+                                       "how": "the same graph with the two-warp latency build (formc_tick_pair_kernel) launched as "
+                                              "programmatic dependents"}),
                 "strictly_ordered": {"value": 3.0 * n * world * K / (serial_ms * 1e-3), "unit": "QP solves/s",
                                      "ms_per_step": serial_ms / K, "repeats_ms": spread(graph_ms),
                                      "how": "the same CUDA graph with formc_pdl = 0: every tick waits for the previous tick's last "
@@ -479,24 +582,37 @@ def main():
                         "last_step_equals_synchronous_call": cpp_equal,
                         "repeats_s": spread(e2e_runs),
                         "how": "C++ host loop (host/FormCPipeline.hpp, the reference's host language) over the C ABI: "
-                               "ismpc_formc_solve_batch(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d persistent host threads x %d "
-                               "handles / streams (that many calls in flight); every step copies its state / walk-state / instance "
-                               "records in (one pinned block, one copy) and its result records out, and the loop reads every "
-                               "result; the footstep plans are resident in the handles (ismpc_formc_set_plan), as they are "
-                               "constructor data of the reference's MPCSolver; K steps per repeat timed by the pool's own clock "
-                               "(first submit -> last result read), max over ranks, median of %d repeats" % (T_HOST, D_HOST, R),
-                        "kernel_launches": int(e2e_cpp_launches)},
+                               "ismpc_formc_solve_batch_packed(ISMPC_MEM_HOST_ASYNC), pinned host buffers, %d persistent host threads x "
+                               "%d handles / streams (that many calls in flight, one fleet of %d robots per handle); every step moves "
+                               "one 128-byte {State, WalkState} record per instance host -> GPU and one 128-byte result record per "
+                               "instance GPU -> host, inside the timed region, by the kernel's own loads / stores over PCIe (zero copy: "
+                               "no copy engine), and the loop reads every result; the footstep plans and the per-instance constants "
+                               "are resident in the handles (ismpc_formc_set_plan / ismpc_formc_set_instances), as they are constructor "
+                               "data / globals of the reference's MPCSolver; K steps per repeat timed by the pool's own clock (first "
+                               "submit -> last result read), max over ranks, median of %d repeats" % (T_HOST, D_HOST, n, R),
+                        "kernel_launches": int(e2e_cpp_launches),
+                        "host_threads_busy": {"in_driver_calls_frac": statistics.median(host_submit) / (T_HOST * e2e_cpp_s),
+                                              "waiting_for_the_gpu_frac": statistics.median(host_wait) / (T_HOST * e2e_cpp_s),
+                                              "note": "per host thread, of the timed region (rank 0): a thread that mostly waits "
+                                                      "means the GPU side (PCIe reads + kernels) is the slower party"}},
+                "e2e_dma_copies": {"value": 3.0 * n * world * K / e2e_dma_s, "unit": "QP solves/s",
+                                   "h2d_bytes_per_step": int(h2d_dma), "d2h_bytes_per_step": int(d2h),
+                                   "how": "the same loop over ismpc_formc_solve_batch (three arrays incl. the instance records, one "
+                                          "cudaMemcpyAsync in and one out per step): what round 1 measured as e2e"},
                 "e2e_sync": {"value": 3.0 * n * world * K / e2e_sync_s, "unit": "QP solves/s",
                              "how": "one synchronous ismpc_formc_solve_batch(ISMPC_MEM_HOST) call per step from Python (what a "
                                     "single Controller-style caller sees)",
-                             "ms_per_step": e2e_sync_s / K * 1e3},
+                             "ms_per_step": e2e_sync_s / K * 1e3,
+                             "packed": {"value": 3.0 * n * world * K / e2e_sync_packed_s, "ms_per_step": e2e_sync_packed_s / K * 1e3,
+                                        "how": "one synchronous ismpc_formc_solve_batch_packed(ISMPC_MEM_HOST) call per step, constants "
+                                               "and plans resident, pinned buffers read / written in place by the kernel"}},
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": load_traffic(), "peak_source": peak_src,
-                             "kernel": "formc_tick_pair_kernel", "kernel_ms": kernel_ms,
+                             "frac": achieved / hbm_peak, "traffic": load_traffic(headline_kernel), "peak_source": peak_src,
+                             "kernel": headline_kernel, "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_instance_tick": B_ALG_FORMC,
-                             "note": "the kernel is bound by the dependent-issue latency of one warp pair per instance, not "
+                             "note": "the kernel is bound by the dependent-issue latency of one warp (pair) per instance, not "
                                      "by HBM or FP64 throughput (DESIGN.md section 4); both fractions are small by construction"},
                 "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
                                   "peak": fp64_peak, "unit": "TFLOP/s",

@@ -206,6 +206,8 @@ void ismpc_host_free(void* p);
  *                         The caller thereby DECLARES consecutive calls on that stream independent: a call must not read
  *                         device buffers the previous call writes, nor share its output buffers.  Default 0: calls
  *                         on a stream are strictly ordered (a tick may consume the previous tick's output).
+ *   "host_zero_copy":     ismpc_formc_solve_batch_packed with host buffers: 1 (default; ISMPC_HOST_ZERO_COPY sets the default at
+ *                         creation) = the kernel reads / writes pinned host buffers itself, 0 = staging buffers and copies.
  *   "dense_dmma":         ismpc_qp_solve_batch: 1 = condensing GEMMs on the FP64 tensor cores (DMMA, default), 0 = CUDA cores.
  * See DESIGN.md section 4. */
 int ismpc_set_option(ismpc_handle* h, const char* name, int value);
@@ -250,6 +252,38 @@ int ismpc_formc_solve_batch(ismpc_handle* h, int n,
                             const double* plan_xyzt, int plan_rows,
                             ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt,
                             int mem, void* stream);
+
+/* The per-tick arguments of solve() as ONE record per instance: `State` (the members solve() touches) and `WalkState`
+ * side by side, padded to 128 bytes -- the size a PCIe transaction, an L2 line and the result record have.  With the
+ * footstep plans (ismpc_formc_set_plan) and the per-instance constants (ismpc_formc_set_instances) resident in the handle,
+ * a tick moves exactly this record in and ismpc_formc_out_t out. */
+typedef struct {
+    ismpc_state_t state;        /* 72 bytes */
+    ismpc_walk_t walk;          /* 24 bytes */
+    double reserved[4];         /* pads the record to 128 bytes; ignored */
+} ismpc_formc_tick_t;
+
+/* Optional: hands the per-instance constants (`ismpc_formc_inst_t`: globals of the reference, parameters.cpp:9-45 -- they do
+ * not change from tick to tick) to the handle once; afterwards ismpc_formc_solve_batch, ismpc_formc_solve_batch_packed and
+ * the rollouts accept inst = NULL for calls with n <= the n given here.  n = 0 forgets them.  mem = ISMPC_MEM_HOST or
+ * ISMPC_MEM_DEVICE says where `inst` lives; the call synchronises.  With host memory the gait of instance 0 is prepared
+ * as ismpc_formc_prepare_gait would. */
+int ismpc_formc_set_instances(ismpc_handle* h, const ismpc_formc_inst_t* inst, int n, int mem);
+
+/* ismpc_formc_solve_batch with the per-tick arguments packed: tick[i] = {state, walk} of instance i (128-byte records;
+ * the array must be 16-byte aligned).  inst / plan_xyzt may be NULL (= the resident ones), results are bit-identical to
+ * ismpc_formc_solve_batch on the same values.  Needs the warp-per-instance kernel family (N <= ISMPC_MAX_N and
+ * "formc_kernel" != 1; ISMPC_ERR_ARG otherwise).
+ * Host-memory modes, option "host_zero_copy" = 1 (default): when `tick` / `out` are pinned host memory the device can
+ * address (ismpc_host_alloc, cudaHostAlloc, cudaHostRegister), 128-byte aligned and at most 8 MB, no copy engine is
+ * involved: every instance's CTA reads its record with ONE 128-byte PCIe read and writes its result with one 128-byte
+ * posted write, and the call is a single kernel launch (a 139 KB DMA copy occupies a copy engine for ~6 us on a B200
+ * box whatever its size, more than the transfer itself; two such copies per tick were the slower party of the serving
+ * loop).  Pageable or unaligned buffers, and "host_zero_copy" = 0, go through staging buffers and copies as before. */
+int ismpc_formc_solve_batch_packed(ismpc_handle* h, int n, const ismpc_formc_tick_t* tick,
+                                   const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
+                                   ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt,
+                                   int mem, void* stream);
 
 /* Closed loop: n_ticks consecutive ticks on the device, state/walk advanced in place exactly as
  * Controller::update would (Controller.cpp:503-504: ++controlIter, mpcIter; sim_time += 1), no host

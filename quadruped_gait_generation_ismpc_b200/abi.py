@@ -18,6 +18,7 @@ FORMC_INST = np.dtype([("com_height", "f8"), ("box_w", "f8"), ("box_w_init", "f8
                        ("S", "i4"), ("F_ds", "i4"), ("plan_first_row", "i4"), ("n_steps", "i4")], align=True)
 FORMC_OUT = np.dtype([("next", STATE), ("zmp_in", "f8", 2), ("fz0", "f8"), ("lambda0", "f8"),
                       ("kkt_res", "f8"), ("status", "i4"), ("iters", "i4", 3)], align=True)
+FORMC_TICK = np.dtype([("state", STATE), ("walk", WALK), ("reserved", "f8", 4)], align=True)      # ismpc_formc_tick_t, 128 bytes
 FORMA_MODEL = np.dtype([("dt", "f8"), ("g_eta", "f8"), ("q_zdot", "f8"), ("q_foot", "f8"),
                         ("disp_forw", "f8"), ("disp_forw_dummy", "f8"), ("disp_L", "f8"),
                         ("C", "i4"), ("P", "i4"), ("F", "i4"), ("reserved", "i4")], align=True)
@@ -45,11 +46,11 @@ KF_SAMPLE = np.dtype([("meas", "f4", (3, 3)), ("input", "f4", 3)], align=True)
 KF_STATE64 = np.dtype([("state", "f8", (3, 5)), ("sigma", "f8", (3, 25))], align=True)
 
 SIZES = {"ismpc_state_t": 72, "ismpc_walk_t": 24, "ismpc_formc_model_t": 72, "ismpc_formc_inst_t": 40,
-         "ismpc_formc_out_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
+         "ismpc_formc_out_t": 128, "ismpc_formc_tick_t": 128, "ismpc_forma_model_t": 72, "ismpc_forma_inst_t": 136,
          "ismpc_forma_out_t": 192, "ismpc_push_t": 32, "ismpc_feet_model_t": 56, "ismpc_feet_inst_t": 32, "ismpc_plan_model_t": 48, "ismpc_plan_req_t": 16, "ismpc_kf_model_t": 172, "ismpc_kf_state_t": 360,
          "ismpc_kf_sample_t": 48, "ismpc_kf_state64_t": 720}
 DTYPES = {"ismpc_state_t": STATE, "ismpc_walk_t": WALK, "ismpc_formc_model_t": FORMC_MODEL,
-          "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT,
+          "ismpc_formc_inst_t": FORMC_INST, "ismpc_formc_out_t": FORMC_OUT, "ismpc_formc_tick_t": FORMC_TICK,
           "ismpc_forma_model_t": FORMA_MODEL, "ismpc_forma_inst_t": FORMA_INST,
           "ismpc_forma_out_t": FORMA_OUT, "ismpc_push_t": PUSH, "ismpc_feet_model_t": FEET_MODEL,
           "ismpc_feet_inst_t": FEET_INST, "ismpc_plan_model_t": PLAN_MODEL, "ismpc_plan_req_t": PLAN_REQ,
@@ -108,3 +109,10 @@ def kf_model(h_com=0.69, mass=50.0, sampling_time=0.01, g=9.81, q_process=1e-2, 
     m["q_process"][0] = np.tile((np.eye(2) * q_process).reshape(-1), (3, 1))
     m["q_measurement"][0] = np.tile((np.eye(3) * q_measurement).reshape(-1), (3, 1))
     return m
+
+
+def pack_ticks(state, walk):
+    """ismpc_formc_tick_t records from the state / walk arrays of a batch."""
+    t = np.zeros(len(state), dtype=FORMC_TICK)
+    t["state"] = state; t["walk"] = walk
+    return t

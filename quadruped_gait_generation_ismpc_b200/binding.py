@@ -20,7 +20,8 @@ EXPORTS = ["ismpc_version", "ismpc_error_string", "ismpc_create", "ismpc_destroy
            "ismpc_feet_export", "ismpc_formc_prepare_gait", "ismpc_plan_rows", "ismpc_plan_valid_rows",
            "ismpc_plan_generate", "ismpc_kf_init", "ismpc_kf_filter_batch", "ismpc_formc_set_plan",
            "ismpc_handle_stream", "ismpc_wait", "ismpc_host_alloc", "ismpc_host_free", "ismpc_formc_rollout_ex",
-           "ismpc_forma_rollout_ex2", "ismpc_kf_filter_batch_f64"]
+           "ismpc_forma_rollout_ex2", "ismpc_kf_filter_batch_f64", "ismpc_formc_set_instances",
+           "ismpc_formc_solve_batch_packed"]
 
 _lib = None
 
@@ -71,6 +72,8 @@ def lib():
     L.ismpc_formc_set_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.ismpc_formc_set_model.argtypes = [C.c_void_p, C.c_void_p]
     L.ismpc_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.ismpc_formc_set_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ismpc_formc_solve_batch_packed.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     L.ismpc_formc_rollout_ex.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
     L.ismpc_forma_rollout_ex2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
@@ -200,6 +203,36 @@ class Handle:
                                              _ptr(out), _ptr(primal), _ptr(active), mem,
                                              C.c_void_p(stream) if stream else None)
         self._check(rc, "ismpc_formc_solve_batch")
+
+    def formc_set_instances(self, inst, mem=abi.MEM_HOST, n=None):
+        """Per-instance constants resident in the handle (inst=None forgets them); afterwards inst=None in the tick calls."""
+        if inst is None:
+            self._check(self._L.ismpc_formc_set_instances(self._h, None, 0, abi.MEM_HOST), "ismpc_formc_set_instances")
+            return
+        if isinstance(inst, np.ndarray):
+            inst = np.ascontiguousarray(inst); n = len(inst)
+        self._check(self._L.ismpc_formc_set_instances(self._h, _ptr(inst), int(n), mem), "ismpc_formc_set_instances")
+
+    def formc_solve_batch_packed(self, tick, inst, plan, want_primal=True, want_active=True):
+        """Host-memory call with packed tick records (abi.FORMC_TICK); inst / plan None = the resident ones."""
+        n = len(tick)
+        N = int(self.formc["N"][0])
+        rows = 0
+        if plan is not None:
+            plan = np.ascontiguousarray(plan, dtype=np.float64); rows = plan.shape[0]
+        out = np.zeros(n, dtype=abi.FORMC_OUT)
+        primal = np.zeros((n, 3 * N)) if want_primal else None
+        active = np.zeros((n, 3 * N), dtype=np.int8) if want_active else None
+        rc = self._L.ismpc_formc_solve_batch_packed(self._h, n, _ptr(tick), _ptr(inst), _ptr(plan), rows, _ptr(out),
+                                                    _ptr(primal), _ptr(active), abi.MEM_HOST, None)
+        self._check(rc, "ismpc_formc_solve_batch_packed")
+        return dict(out=out, primal=primal, active=active)
+
+    def formc_solve_batch_packed_raw(self, n, tick, inst, plan, plan_rows, out, primal=None, active=None,
+                                     mem=abi.MEM_DEVICE, stream=None):
+        rc = self._L.ismpc_formc_solve_batch_packed(self._h, n, _ptr(tick), _ptr(inst), _ptr(plan), plan_rows, _ptr(out),
+                                                    _ptr(primal), _ptr(active), mem, C.c_void_p(stream) if stream else None)
+        self._check(rc, "ismpc_formc_solve_batch_packed")
 
     def formc_rollout(self, state, walk, inst, plan, n_ticks, push=None, want_traj=True, want_trace=False):
         """want_trace: also return the per-tick status words (n x n_ticks int32, ismpc_formc_rollout_ex)."""

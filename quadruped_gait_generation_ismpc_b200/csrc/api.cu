@@ -42,7 +42,10 @@ struct ismpc_handle {
     bool formc_ready = false;
     ismpc_formc_model_t cm{};
     DevBuf c_tables, c_work, c_info, c_ptab;
-    DevBuf c_ric_none, c_ric_gait, c_law_none, c_law_gait, c_ws, c_plan;
+    DevBuf c_ric_none, c_ric_gait, c_law_none, c_law_gait, c_ws, c_plan, c_inst;
+    int inst_res_n = 0;            // instance records resident in c_inst (ismpc_formc_set_instances), 0 = none
+    int opt_host_zero_copy = 1;    // packed host-memory ticks: the kernel reads / writes the caller's pinned buffers itself
+    DevBuf s_tick;                 // staging of the packed tick records when they cannot be read in place
     int plan_res_rows = 0;         // rows of the resident footstep-plan table (ismpc_formc_set_plan), 0 = none   // Riccati tables (warp kernels) and the per-warp workspace of their general path
     int gait_S = 0, gait_F = 0;            // prepared gait (projector tables in c_ptab), 0 = none
     int ric_S = 0, ric_F = 0;              // prepared gait of the Riccati tables (c_ric_gait), 0 = none
@@ -102,6 +105,8 @@ extern "C" int ismpc_create(ismpc_handle** out, int device, int max_batch)
     h->a_tune.R = env_int("ISMPC_FORMA_R", 0); h->a_tune.warps_per_cta = env_int("ISMPC_FORMA_WPC", 0);
     h->a_tune.pdas = env_int("ISMPC_FORMA_PDAS", 1) != 0; h->a_tune.warm = env_int("ISMPC_FORMA_WARM", 1) != 0;
     h->a_tune.reg = env_int("ISMPC_FORMA_REG", 1) != 0;
+    h->opt_host_zero_copy = env_int("ISMPC_HOST_ZERO_COPY", 1) != 0;
+    { const int v = env_int("ISMPC_FORMC_VARIANT", 0); if (v == 0 || v == 1 || v == 2 || v == 16) h->opt_formc_variant = v; }
     *out = h;
     return ISMPC_OK;
 }
@@ -110,7 +115,7 @@ extern "C" int ismpc_destroy(ismpc_handle* h)
 {
     if (!h) return ISMPC_ERR_ARG;
     cudaSetDevice(h->device);
-    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->c_plan, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout, &h->s_in,
+    DevBuf* all[] = {&h->c_tables, &h->c_work, &h->c_info, &h->c_ptab, &h->c_ric_none, &h->c_ric_gait, &h->c_law_none, &h->c_law_gait, &h->c_ws, &h->c_plan, &h->c_inst, &h->s_tick, &h->s_state, &h->s_walk, &h->s_cinst, &h->s_cout, &h->s_in,
                      &h->s_plan, &h->s_primal, &h->s_active, &h->s_push, &h->s_traj, &h->s_status,
                      &h->s_ainst, &h->s_aout, &h->s_timing, &h->a_Lwork, &h->a_queue, &h->q_in, &h->q_out, &h->q_work, &h->s_pred, &h->f_inst, &h->f_plan, &h->f_out, &h->s_trace};
     for (DevBuf* b : all) b->release();
@@ -167,6 +172,7 @@ extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
     if (strcmp(name, "forma_R") == 0) { if (value < 0) return ISMPC_ERR_ARG; h->a_tune.R = value; return ISMPC_OK; }
     if (strcmp(name, "forma_warps_per_cta") == 0) { if (value < 0 || value > 2) return ISMPC_ERR_ARG; h->a_tune.warps_per_cta = value; return ISMPC_OK; }
     if (strcmp(name, "formc_pdl") == 0) { h->opt_formc_pdl = value != 0; return ISMPC_OK; }
+    if (strcmp(name, "host_zero_copy") == 0) { h->opt_host_zero_copy = value != 0; return ISMPC_OK; }
     if (strcmp(name, "dense_dmma") == 0) { h->opt_dense_dmma = value != 0; return ISMPC_OK; }
     if (strcmp(name, "formc_kernel") == 0) {
         if (value < 0 || value > 2) return ISMPC_ERR_ARG;
@@ -230,7 +236,7 @@ static void formc_fill_args(ismpc_handle* h, FormCArgs& a, int n)
 {
     const size_t NN = (size_t)h->cm.N * h->cm.N;
     const double* T = (const double*)h->c_tables.p;
-    a.n = n; a.model = h->cm;
+    a.n = n; a.model = h->cm; a.tick = nullptr;
     a.T.Hinv = T; a.T.G = T + NN; a.T.M = T + 2 * NN;
     a.T.P = (h->gait_S + h->gait_F > 0) ? (const double*)h->c_ptab.p : nullptr;
     a.T.gS = h->gait_S; a.T.gF = h->gait_F;
@@ -341,7 +347,8 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
     const bool plan_res = plan_xyzt == nullptr;
     if (plan_res) plan_rows = h->plan_res_rows;
-    if (n < 0 || n > h->max_batch || !state || !walk || !inst || !out || plan_rows <= 0)
+    const bool inst_res = inst == nullptr;
+    if (n < 0 || n > h->max_batch || !state || !walk || (inst_res && n > h->inst_res_n) || !out || plan_rows <= 0)
         return ISMPC_ERR_ARG;
     if (n == 0) return ISMPC_OK;
     CK(cudaSetDevice(h->device));
@@ -350,7 +357,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     FormCArgs a;
     formc_fill_args(h, a, n);
     if (mem == ISMPC_MEM_DEVICE) {
-        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt; a.plan_rows = plan_rows;
+        a.state = state; a.walk = walk; a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt; a.plan_rows = plan_rows;
         a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
         int rc = formc_launch_tick(h, a, n, st);
         h->launches += 1;
@@ -358,7 +365,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
-    if (h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+    if (!inst_res && h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
         int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);      // host buffers: the gait can be read here
         if (prc != ISMPC_OK) return prc;
         formc_fill_args(h, a, n);
@@ -368,7 +375,7 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     // (pinned) allocation the tick's inputs move in ONE copy instead of three (each small copy costs ~2 us of API and
     // DMA set-up, about a quarter of the kernel)
     const size_t b_state = (size_t)n * sizeof(ismpc_state_t), b_walk = (size_t)n * sizeof(ismpc_walk_t),
-                 b_inst = (size_t)n * sizeof(ismpc_formc_inst_t);
+                 b_inst = inst_res ? 0 : (size_t)n * sizeof(ismpc_formc_inst_t);
     if (h->s_in.ensure(mb * (sizeof(ismpc_state_t) + sizeof(ismpc_walk_t) + sizeof(ismpc_formc_inst_t))) ||
         h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t)) ||
         (!plan_res && h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double))))
@@ -376,16 +383,16 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     if (primal_opt && h->s_primal.ensure(mb * 3 * N * sizeof(double))) return ISMPC_ERR_ALLOC;
     if (active_opt && h->s_active.ensure(mb * 3 * N)) return ISMPC_ERR_ALLOC;
     char* d_in = (char*)h->s_in.p;
-    if ((const char*)walk == (const char*)state + b_state && (const char*)inst == (const char*)walk + b_walk) {
+    if ((const char*)walk == (const char*)state + b_state && (inst_res || (const char*)inst == (const char*)walk + b_walk)) {
         CK(cudaMemcpyAsync(d_in, state, b_state + b_walk + b_inst, cudaMemcpyHostToDevice, st));
     } else {
         CK(cudaMemcpyAsync(d_in, state, b_state, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_in + b_state, walk, b_walk, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_in + b_state + b_walk, inst, b_inst, cudaMemcpyHostToDevice, st));
+        if (!inst_res) CK(cudaMemcpyAsync(d_in + b_state + b_walk, inst, b_inst, cudaMemcpyHostToDevice, st));
     }
     if (!plan_res) CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     a.state = (const ismpc_state_t*)d_in; a.walk = (const ismpc_walk_t*)(d_in + b_state);
-    a.inst = (const ismpc_formc_inst_t*)(d_in + b_state + b_walk); a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
+    a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : (const ismpc_formc_inst_t*)(d_in + b_state + b_walk); a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
     a.plan_rows = plan_rows;
     a.out = (ismpc_formc_out_t*)h->s_cout.p;
     a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
@@ -394,6 +401,110 @@ extern "C" int ismpc_formc_solve_batch(ismpc_handle* h, int n, const ismpc_state
     h->launches += 1;
     if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
     CK(cudaMemcpyAsync(out, h->s_cout.p, n * sizeof(ismpc_formc_out_t), cudaMemcpyDeviceToHost, st));
+    if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * 3 * N, cudaMemcpyDeviceToHost, st));
+    if (mem == ISMPC_MEM_HOST) CK(cudaStreamSynchronize(st));
+    return ISMPC_OK;
+}
+
+extern "C" int ismpc_formc_set_instances(ismpc_handle* h, const ismpc_formc_inst_t* inst, int n, int mem)
+{
+    if (!h || n < 0 || n > h->max_batch || (n > 0 && !inst) || (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_DEVICE)) return ISMPC_ERR_ARG;
+    if (n == 0) { h->inst_res_n = 0; return ISMPC_OK; }
+    CK(cudaSetDevice(h->device));
+    if (mem == ISMPC_MEM_HOST && h->formc_ready && h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 &&
+        inst[0].F_ds >= 0) {
+        int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);
+        if (prc != ISMPC_OK) return prc;
+    }
+    if (h->c_inst.ensure((size_t)h->max_batch * sizeof(ismpc_formc_inst_t))) return ISMPC_ERR_ALLOC;
+    CK(cudaMemcpy(h->c_inst.p, inst, (size_t)n * sizeof(ismpc_formc_inst_t),
+                  mem == ISMPC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    h->inst_res_n = n;
+    return ISMPC_OK;
+}
+
+// Device address of a host buffer the kernels may touch in place: pinned (cudaHostAlloc / cudaHostRegister), 128-byte
+// aligned, at most ZC_MAX_BYTES (larger transfers are the copy engines' business); nullptr otherwise.
+static void* zero_copy_address(const void* p, size_t bytes)
+{
+    constexpr size_t ZC_MAX_BYTES = 8u << 20;
+    if (!p || ((uintptr_t)p & 127u) != 0 || bytes > ZC_MAX_BYTES) return nullptr;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return (pa.type == cudaMemoryTypeHost && pa.devicePointer) ? pa.devicePointer : nullptr;
+}
+
+extern "C" int ismpc_formc_solve_batch_packed(ismpc_handle* h, int n, const ismpc_formc_tick_t* tick,
+                                              const ismpc_formc_inst_t* inst, const double* plan_xyzt, int plan_rows,
+                                              ismpc_formc_out_t* out, double* primal_opt, int8_t* active_opt, int mem,
+                                              void* stream)
+{
+    if (!h) return ISMPC_ERR_ARG;
+    if (!h->formc_ready) return ISMPC_ERR_MODEL;
+    const bool plan_res = plan_xyzt == nullptr, inst_res = inst == nullptr;
+    if (plan_res) plan_rows = h->plan_res_rows;
+    if (n < 0 || n > h->max_batch || !tick || ((uintptr_t)tick & 15u) != 0 || (inst_res && n > h->inst_res_n) || !out ||
+        plan_rows <= 0 || !formc_use_warp(h))
+        return ISMPC_ERR_ARG;
+    if (n == 0) return ISMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cm.N;
+    FormCArgs a;
+    formc_fill_args(h, a, n);
+    a.state = nullptr; a.walk = nullptr; a.plan_rows = plan_rows;
+    if (mem == ISMPC_MEM_DEVICE) {
+        a.tick = tick; a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : inst;
+        a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt;
+        a.out = out; a.primal = primal_opt; a.active = (signed char*)active_opt;
+        int rc = formc_launch_tick(h, a, n, st);
+        h->launches += 1;
+        if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
+        return ISMPC_OK;
+    }
+    if (mem != ISMPC_MEM_HOST && mem != ISMPC_MEM_HOST_ASYNC) return ISMPC_ERR_ARG;
+    if (!inst_res && h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+        int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);
+        if (prc != ISMPC_OK) return prc;
+        formc_fill_args(h, a, n);
+        a.state = nullptr; a.walk = nullptr; a.plan_rows = plan_rows;
+    }
+    const size_t mb = (size_t)h->max_batch;
+    const size_t b_tick = (size_t)n * sizeof(ismpc_formc_tick_t), b_out = (size_t)n * sizeof(ismpc_formc_out_t);
+    // in place where the buffers allow it (see the header): one 128-byte PCIe read and one posted 128-byte write per
+    // instance, issued by the instance's own CTA, instead of two DMA copies around the kernel
+    const ismpc_formc_tick_t* tick_dev = h->opt_host_zero_copy ? (const ismpc_formc_tick_t*)zero_copy_address(tick, b_tick) : nullptr;
+    ismpc_formc_out_t* out_dev = h->opt_host_zero_copy ? (ismpc_formc_out_t*)zero_copy_address(out, b_out) : nullptr;
+    if (!tick_dev) {
+        if (h->s_tick.ensure(mb * sizeof(ismpc_formc_tick_t))) return ISMPC_ERR_ALLOC;
+        CK(cudaMemcpyAsync(h->s_tick.p, tick, b_tick, cudaMemcpyHostToDevice, st));
+        tick_dev = (const ismpc_formc_tick_t*)h->s_tick.p;
+    }
+    if (!out_dev) {
+        if (h->s_cout.ensure(mb * sizeof(ismpc_formc_out_t))) return ISMPC_ERR_ALLOC;
+        out_dev = (ismpc_formc_out_t*)h->s_cout.p;
+    }
+    if (!inst_res) {
+        if (h->s_cinst.ensure(mb * sizeof(ismpc_formc_inst_t))) return ISMPC_ERR_ALLOC;
+        CK(cudaMemcpyAsync(h->s_cinst.p, inst, (size_t)n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
+    }
+    if (!plan_res) {
+        if (h->s_plan.ensure((size_t)plan_rows * 4 * sizeof(double))) return ISMPC_ERR_ALLOC;
+        CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (primal_opt && h->s_primal.ensure(mb * 3 * N * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (active_opt && h->s_active.ensure(mb * 3 * N)) return ISMPC_ERR_ALLOC;
+    a.tick = tick_dev;
+    a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : (const ismpc_formc_inst_t*)h->s_cinst.p;
+    a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
+    a.out = out_dev;
+    a.primal = primal_opt ? (double*)h->s_primal.p : nullptr;
+    a.active = active_opt ? (signed char*)h->s_active.p : nullptr;
+    int rc = formc_launch_tick(h, a, n, st);
+    h->launches += 1;
+    if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_tick_launch");
+    if ((void*)out_dev == h->s_cout.p) CK(cudaMemcpyAsync(out, h->s_cout.p, b_out, cudaMemcpyDeviceToHost, st));
     if (primal_opt) CK(cudaMemcpyAsync(primal_opt, h->s_primal.p, (size_t)n * 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (active_opt) CK(cudaMemcpyAsync(active_opt, h->s_active.p, (size_t)n * 3 * N, cudaMemcpyDeviceToHost, st));
     if (mem == ISMPC_MEM_HOST) CK(cudaStreamSynchronize(st));

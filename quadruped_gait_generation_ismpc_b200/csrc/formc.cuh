@@ -301,6 +301,7 @@ struct FormCArgs {
     const ismpc_state_t* state;
     const ismpc_walk_t* walk;
     const ismpc_formc_inst_t* inst;
+    const ismpc_formc_tick_t* tick;   // non-null (warp kernel family only): state / walk come packed, one 128-byte record per instance
     const double* plan;
     int plan_rows;
     ismpc_formc_out_t* out;

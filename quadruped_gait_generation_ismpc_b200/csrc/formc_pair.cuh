@@ -16,7 +16,7 @@
 
 namespace ismpc {
 
-constexpr int FORMC_PAIR_RED = 32;      // doubles exchanged between the two warps ([16..) : the rollout's state hand-over)
+constexpr int FORMC_PAIR_RED = 48;      // doubles exchanged between the two warps ([16..32): the rollout's state hand-over / the tick's result staging, [32..48): the tick's packed input record)
 
 // CTA barrier of the two warps (a named barrier: the two warps reach it from different code paths)
 __device__ __forceinline__ void pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }

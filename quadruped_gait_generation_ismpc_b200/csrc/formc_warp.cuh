@@ -104,7 +104,7 @@ __host__ __device__ inline int formc_warp_epl(int N) { return (N + 31) >> 5; }
 __host__ __device__ inline size_t formc_law_pattern_doubles(int N) { return (size_t)FORMC_LAW_W * formc_warp_epl(N) * 32; }
 __host__ __device__ inline size_t formc_warp_smem_bytes(int N)
 {
-    return (size_t)FORMC_WARP_VECS * formc_warp_epl(N) * 32 * sizeof(double) + 16;   // + mbarrier
+    return (size_t)FORMC_WARP_VECS * formc_warp_epl(N) * 32 * sizeof(double) + 16 + 128 + 128;   // + mbarrier + staging of the result record (store_record_warp) + of the packed input record (load_tick_record)
 }
 
 struct FormCWarpShared {     // [e*32 + lane] each

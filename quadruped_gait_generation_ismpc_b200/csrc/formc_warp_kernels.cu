@@ -98,17 +98,53 @@ int formc_riccati_launch(const ismpc_formc_model_t& m, int S, int F, int none, d
     return (int)cudaGetLastError();
 }
 
+// 128-byte result record, held by lane `owner` of the calling warp: staged in shared memory and written by eight lanes as
+// ONE 128-byte transaction (the record array is 128-byte aligned: cudaMalloc / cudaHostAlloc; a call with host buffers
+// lets the kernel write straight into the caller's pinned memory, where a full-line posted write is what PCIe moves
+// best).  stg: 128 bytes of shared memory, 16-byte aligned, private to the warp.  All 32 lanes call.
+__device__ __forceinline__ void store_record_warp(ismpc_formc_out_t* dst, const ismpc_formc_out_t& r, double* stg, int lane,
+                                                  int owner)
+{
+    static_assert(sizeof(ismpc_formc_out_t) == 128, "record layout");
+    double2* s2 = reinterpret_cast<double2*>(stg);
+    if (lane == owner) {
+        const double2* s = reinterpret_cast<const double2*>(&r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s2[k] = s[k];
+    }
+    __syncwarp();
+    if (lane < 8) reinterpret_cast<double2*>(dst)[lane] = s2[lane];
+    __syncwarp();
+}
+
+// 128-byte record, 16-byte aligned (cudaMalloc / array of 128-byte records): eight 16-byte stores by one lane
 __device__ __forceinline__ void store_record(ismpc_formc_out_t* dst, const ismpc_formc_out_t& r)
 {
-    // 128-byte record, 16-byte aligned (cudaMalloc / array of 128-byte records): eight 16-byte stores by one lane
     const double2* s = reinterpret_cast<const double2*>(&r);
     double2* d = reinterpret_cast<double2*>(dst);
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(ismpc_formc_out_t) / 16); ++k) d[k] = s[k];
 }
 
+// PACKED builds of the tick kernels (ismpc_formc_solve_batch_packed): state and walk state of an instance come as one
+// 128-byte record (ismpc_formc_tick_t, 16-byte aligned).  Eight threads fetch 16 bytes each -- ONE 128-byte transaction,
+// which is what matters when the array is pinned host memory and the read crosses PCIe (a struct read through
+// warp-uniform loads is six separate 16-byte requests, and PCIe reads are request-rate bound) -- into shared memory;
+// after the caller's barrier every thread takes its copy from there.  The result record goes out the same way
+// (store_record_warp).  stg: 128 bytes of shared memory, 16-byte aligned.
+__device__ __forceinline__ void load_tick_record_issue(const ismpc_formc_tick_t* tick, int inst, double* stg, int tid)
+{
+    static_assert(sizeof(ismpc_formc_tick_t) == 128, "record layout");
+    if (tid < 8) reinterpret_cast<double2*>(stg)[tid] = reinterpret_cast<const double2*>(tick + inst)[tid];
+}
+__device__ __forceinline__ void load_tick_record_take(const double* stg, ismpc_state_t& st, ismpc_walk_t& wk)
+{
+    const ismpc_formc_tick_t* t = reinterpret_cast<const ismpc_formc_tick_t*>(stg);
+    st = t->state; wk = t->walk;
+}
+
 // Fused tick: one warp (a 32-thread CTA) per instance, grid-stride over the batch.
-template <int MINB>
+template <int MINB, bool PACKED>
 __global__ void __launch_bounds__(32, MINB)
 formc_tick_warp_kernel(FormCWarpArgs wa)
 {
@@ -126,15 +162,20 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
 #ifdef ISMPC_PHASE_TIMING
     if (lane == 0 && blockIdx.x < 8192) { g_trace[3 * blockIdx.x] = dbg_globaltimer(); g_trace[3 * blockIdx.x + 2] = dbg_smid(); }
 #endif
+    double* stg_out = smem_d + (FORMC_WARP_VECS * formc_warp_epl(N) * 32 + 2);
+    double* stg_in = stg_out + 16;
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
-        const ismpc_state_t st = a.state[inst];
-        const ismpc_walk_t wk = a.walk[inst];
+        ismpc_state_t st; ismpc_walk_t wk;
+        if constexpr (PACKED) load_tick_record_issue(a.tick, inst, stg_in, lane);
+        else { st = a.state[inst]; wk = a.walk[inst]; }
         const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
+        if constexpr (PACKED) { __syncwarp(); load_tick_record_take(stg_in, st, wk); __syncwarp(); }
         ismpc_formc_out_t r;
         formc_tick_warp(sm, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
                         a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
                         a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
-        if (lane == 0) store_record(a.out + inst, r);
+        if constexpr (PACKED) store_record_warp(a.out + inst, r, stg_out, lane, 0);
+        else if (lane == 0) store_record(a.out + inst, r);
     }
 #ifdef ISMPC_PHASE_TIMING
     if (lane == 0 && blockIdx.x < 8192) g_trace[3 * blockIdx.x + 1] = dbg_globaltimer();
@@ -142,7 +183,8 @@ formc_tick_warp_kernel(FormCWarpArgs wa)
 }
 
 // Latency build of the tick: two warps (one 64-thread CTA) per instance, see formc_pair.cuh.
-__global__ void __launch_bounds__(64, 7)
+template <bool PACKED>
+__global__ void __launch_bounds__(64, 7)      // 7 CTAs per SM: every instance of a 1,024-instance tick is resident (144 registers through __maxnreg__ drops residency to 6 CTAs: 14.8 instead of 10.6 us per tick)
 formc_tick_pair_kernel(FormCWarpArgs wa)
 {
     extern __shared__ __align__(16) double smem_d[];
@@ -152,6 +194,8 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
     formc_warp_carve(smem_d, E, sm);
     double* red = smem_d + (FORMC_WARP_VECS * E * 32 + 2);
     pdl_launch_dependents();
+    // (packed build: the first instance's record is requested before the set-up barrier, which then also publishes it)
+    if constexpr (PACKED) { if ((int)blockIdx.x < a.n) load_tick_record_issue(a.tick, blockIdx.x, red + 32, threadIdx.x); }
     if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
     __syncthreads();
     uint32_t parity = 0;
@@ -160,14 +204,19 @@ formc_tick_pair_kernel(FormCWarpArgs wa)
     if (threadIdx.x == 0 && blockIdx.x < 8192) { g_trace[3 * blockIdx.x] = dbg_globaltimer(); g_trace[3 * blockIdx.x + 2] = dbg_smid(); }
 #endif
     for (int inst = blockIdx.x; inst < a.n; inst += gridDim.x) {
-        const ismpc_state_t st = a.state[inst];
-        const ismpc_walk_t wk = a.walk[inst];
+        ismpc_state_t st; ismpc_walk_t wk;
+        if constexpr (PACKED) {
+            if (inst != (int)blockIdx.x) { load_tick_record_issue(a.tick, inst, red + 32, threadIdx.x); __syncthreads(); }
+            load_tick_record_take(red + 32, st, wk);
+        } else { st = a.state[inst]; wk = a.walk[inst]; }
         const ismpc_formc_inst_t in = formc_checked_inst(a.inst[inst], a.plan_rows);
         ismpc_formc_out_t r;
         formc_tick_pair(sm, red, a.model, a.T, wa.R, st, wk, in, a.plan, ws, r,
                         a.primal ? a.primal + (size_t)inst * 3 * N : nullptr,
                         a.active ? a.active + (size_t)inst * 3 * N : nullptr, parity);
-        if (threadIdx.x == 32) store_record(a.out + inst, r);
+        if constexpr (PACKED) {
+            if (threadIdx.x >= 32) store_record_warp(a.out + inst, r, red + 16, threadIdx.x - 32, 0);  // [16..32) of the exchange area: the rollout's hand-over, free in the tick
+        } else if (threadIdx.x == 32) store_record(a.out + inst, r);
     }
 #ifdef ISMPC_PHASE_TIMING
     if (threadIdx.x == 32 && blockIdx.x < 8192) g_trace[3 * blockIdx.x + 1] = dbg_globaltimer();
@@ -306,10 +355,13 @@ static int formc_warp_configure()
 {
     const size_t smem = formc_warp_smem_bytes(ISMPC_MAX_N), pair = formc_pair_smem_bytes(ISMPC_MAX_N);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_warp_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(formc_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(formc_tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(formc_tick_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(formc_rollout_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair)) != cudaSuccess) return (int)e;
     return 0;
 }
@@ -322,10 +374,10 @@ int formc_warp_resident(int N, int sm_count, int res[5])
     const int rc = formc_warp_configure();
     if (rc) return rc;
     int b = 0;
-    res[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<1>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
-    res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<1, true>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_warp_kernel<16, true>, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[2] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_warp_kernel, 32, smem) == cudaSuccess && b > 0 ? b : 1) * sm_count;
-    res[3] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
+    res[3] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_tick_pair_kernel<true>, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     res[4] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, formc_rollout_pair_kernel, 64, formc_pair_smem_bytes(N)) == cudaSuccess && b > 0 ? b : 1) * sm_count;
     return 0;
 }
@@ -349,17 +401,23 @@ static int formc_launch_ex(K kern, int grid, int block, size_t smem, cudaStream_
 int formc_tick_warp_launch(const FormCWarpArgs& a, int n, const int res[5], int variant, int pdl, int* grid_out, cudaStream_t st)
 {
     const size_t smem = formc_warp_smem_bytes(a.base.model.N);
+    const bool packed = a.base.tick != nullptr;
     if (variant == 2 || (variant == 0 && n <= res[3])) {
         const int grid = n < res[3] ? n : res[3];
         *grid_out = grid;
-        return formc_launch_ex(formc_tick_pair_kernel, grid, 64, formc_pair_smem_bytes(a.base.model.N), st, pdl, a);
+        if (packed) return formc_launch_ex(formc_tick_pair_kernel<true>, grid, 64, formc_pair_smem_bytes(a.base.model.N), st, pdl, a);
+        return formc_launch_ex(formc_tick_pair_kernel<false>, grid, 64, formc_pair_smem_bytes(a.base.model.N), st, pdl, a);
     }
     const bool big = variant == 16 || (variant == 0 && n > res[0]);
     const int cap = big ? res[1] : res[0];
     const int grid = n < cap ? n : cap;
     *grid_out = grid;
-    if (big) return formc_launch_ex(formc_tick_warp_kernel<16>, grid, 32, smem, st, pdl, a);
-    return formc_launch_ex(formc_tick_warp_kernel<1>, grid, 32, smem, st, pdl, a);
+    if (packed) {
+        if (big) return formc_launch_ex(formc_tick_warp_kernel<16, true>, grid, 32, smem, st, pdl, a);
+        return formc_launch_ex(formc_tick_warp_kernel<1, true>, grid, 32, smem, st, pdl, a);
+    }
+    if (big) return formc_launch_ex(formc_tick_warp_kernel<16, false>, grid, 32, smem, st, pdl, a);
+    return formc_launch_ex(formc_tick_warp_kernel<1, false>, grid, 32, smem, st, pdl, a);
 }
 
 int formc_rollout_warp_launch(const FormCWarpArgs& a, ismpc_state_t* state_io, ismpc_walk_t* walk_io,

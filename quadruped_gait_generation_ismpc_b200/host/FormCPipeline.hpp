@@ -78,6 +78,36 @@ public:
         check(ismpc_formc_solve_batch(q.h, n_, st, wk, in, nullptr, 0, q.out, nullptr, nullptr, ISMPC_MEM_HOST_ASYNC, q.stream),
               q.h, "ismpc_formc_solve_batch");
     }
+    // tuning knob on every handle of the pipeline (ismpc_set_option), e.g. "formc_variant" = 16: the throughput build of
+    // the tick kernel, the right one when 8 or more ticks are in flight on a GPU
+    void set_option(const char* name, int value)
+    {
+        for (Slot& q : slots_) check(ismpc_set_option(q.h, name, value), q.h, "ismpc_set_option");
+    }
+    // ---- packed mode: the per-instance constants are handed to the slot's handle once (they are globals of the
+    // reference, parameters.cpp:9-45), a tick then moves one 128-byte record per instance in and one out; with pinned
+    // buffers (the slot's own staging is) the library lets the kernel read and write them in place, and a tick is a
+    // single kernel launch -- no copy engine involved (ismpc_b200.h: ismpc_formc_solve_batch_packed) ----
+    void set_instances(int s, const ismpc_formc_inst_t* inst)
+    {
+        check(ismpc_formc_set_instances(slots_[s].h, inst, n_, ISMPC_MEM_HOST), slots_[s].h, "ismpc_formc_set_instances");
+    }
+    ismpc_formc_tick_t* tick(int s)          // the slot's pinned staging for packed records (allocated on first use)
+    {
+        Slot& q = slots_[s];
+        if (!q.tick) {
+            q.tick = static_cast<ismpc_formc_tick_t*>(ismpc_host_alloc((size_t)n_ * sizeof(ismpc_formc_tick_t)));
+            if (!q.tick) throw std::runtime_error("FormCPipeline: ismpc_host_alloc failed");
+        }
+        return q.tick;
+    }
+    void submit_packed(int s) { submit_packed_from(s, tick(s)); }
+    void submit_packed_from(int s, const ismpc_formc_tick_t* tk)
+    {
+        Slot& q = slots_[s];
+        check(ismpc_formc_solve_batch_packed(q.h, n_, tk, nullptr, nullptr, 0, q.out, nullptr, nullptr, ISMPC_MEM_HOST_ASYNC, q.stream),
+              q.h, "ismpc_formc_solve_batch_packed");
+    }
     long long kernel_launches() const
     {
         long long t = 0;
@@ -88,13 +118,14 @@ public:
 private:
     struct Slot {
         ismpc_handle* h = nullptr; void* stream = nullptr; char* in = nullptr; ismpc_formc_out_t* out = nullptr;
+        ismpc_formc_tick_t* tick = nullptr;
         Slot() = default;
         Slot(const Slot&) = delete;
         Slot& operator=(const Slot&) = delete;
         ~Slot()
         {
             if (h) { if (stream) ismpc_wait(h, stream); ismpc_destroy(h); }
-            ismpc_host_free(in); ismpc_host_free(out);
+            ismpc_host_free(in); ismpc_host_free(out); ismpc_host_free(tick);
         }
     };
     static void check(int rc, ismpc_handle* h, const char* what)

@@ -125,6 +125,7 @@ struct HostPool {
     std::vector<std::thread> workers;
     std::vector<long long> sums;
     std::vector<std::string> errs;
+    std::vector<double> wait_s, submit_s;      // per thread, last run: seconds inside ismpc_wait / inside ismpc_formc_solve_batch
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<long long> generation{0};
@@ -135,6 +136,7 @@ struct HostPool {
     int k0 = 0, steps = 0, n_blocks = 0;
     const void* const* in_blocks = nullptr;
     ismpc_formc_out_t* out_copy = nullptr;
+    bool packed = false;             // in_blocks are packed tick records: n_blocks per slot, slot-major (slot = t * depth + s)
 
     void work(int t)
     {
@@ -144,15 +146,36 @@ struct HostPool {
         sums[(size_t)t] = 0; errs[(size_t)t].clear();
         try {
             int submitted = 0;
+            double t_wait = 0.0, t_submit = 0.0;
+            auto now = [] { return std::chrono::steady_clock::now(); };
             for (int k = k0 + t; k < k0 + steps; k += T, ++submitted) {
+                const auto a0 = now();
                 const int s = p.acquire();
+                const auto a1 = now();
                 if (submitted >= p.depth()) sums[(size_t)t] += p.out(s)[0].status;      // the result of the step that used the slot
+                if (packed) {
+                    // every slot serves its own fleet (resident constants and plans); the fleet's tick records rotate
+                    // over the n_blocks pinned blocks the caller prepared for it
+                    const size_t slot = (size_t)t * (size_t)p.depth() + (size_t)s;
+                    const int visit = (k - k0) / (T * p.depth());
+                    p.submit_packed_from(s, static_cast<const ismpc_formc_tick_t*>(in_blocks[slot * (size_t)n_blocks + (size_t)(visit % n_blocks)]));
+                    const auto a2p = now();
+                    t_wait += std::chrono::duration<double>(a1 - a0).count();
+                    t_submit += std::chrono::duration<double>(a2p - a1).count();
+                    continue;
+                }
                 const char* b = static_cast<const char*>(in_blocks[k % n_blocks]);
                 p.submit_from(s, reinterpret_cast<const ismpc_state_t*>(b),
                               reinterpret_cast<const ismpc_walk_t*>(b + n * sizeof(ismpc_state_t)),
                               reinterpret_cast<const ismpc_formc_inst_t*>(b + n * (sizeof(ismpc_state_t) + sizeof(ismpc_walk_t))));
+                const auto a2 = now();
+                t_wait += std::chrono::duration<double>(a1 - a0).count();
+                t_submit += std::chrono::duration<double>(a2 - a1).count();
             }
+            const auto a3 = now();
             p.wait_all();
+            t_wait += std::chrono::duration<double>(now() - a3).count();
+            wait_s[(size_t)t] = t_wait; submit_s[(size_t)t] = t_submit;
             for (int s = 0; s < p.depth(); ++s) sums[(size_t)t] += p.out(s)[0].status;   // ... and of the last `depth` steps
             if (out_copy)
                 for (int s = 0; s < p.depth(); ++s)
@@ -207,6 +230,7 @@ extern "C" void* ismpc_host_pool_create(int device, int n, int threads, int dept
         for (int t = 0; t < threads; ++t)
             hp->pipes.emplace_back(new FormCPipeline(device, n, depth, *model, S, F_ds, plan_xyzt, plan_rows, /*own_staging=*/false));
         hp->sums.assign((size_t)threads, 0); hp->errs.assign((size_t)threads, std::string());
+        hp->wait_s.assign((size_t)threads, 0.0); hp->submit_s.assign((size_t)threads, 0.0);
         for (int t = 1; t < threads; ++t) hp->workers.emplace_back(&HostPool::worker_main, hp.get(), t);
         return hp.release();
     } catch (const std::exception& e) {
@@ -228,14 +252,70 @@ extern "C" long long ismpc_host_pool_launches(void* pv)
     return t;
 }
 
+// Where the host threads spent the last run: seconds blocked in ismpc_wait (the GPU side -- copies and kernels -- was the
+// slower party) and seconds inside ismpc_formc_solve_batch (driver calls: the host was), summed over the pool's threads.
+extern "C" void ismpc_host_pool_stats(void* pv, double* wait_s, double* submit_s)
+{
+    HostPool& hp = *static_cast<HostPool*>(pv);
+    double w = 0.0, s = 0.0;
+    for (size_t t = 0; t < hp.pipes.size(); ++t) { w += hp.wait_s[t]; s += hp.submit_s[t]; }
+    if (wait_s) *wait_s = w;
+    if (submit_s) *submit_s = s;
+}
+
 // Steps k0 .. k0+steps-1: thread t takes steps k0+t, k0+t+T, ...  out_copy_opt: T x depth x n records (the result records
 // of every pipeline's slots after the run).  elapsed_s_opt: wall-clock seconds from before the first submit until the
 // last result has been read.  Returns 0, or -1 with the first error in ismpc_host_last_error().
+static int pool_run(void* pv, int k0, int steps, const void* const* in_blocks, int n_blocks, long long* checksum,
+                    ismpc_formc_out_t* out_copy_opt, double* elapsed_s_opt, bool packed);
+
 extern "C" int ismpc_host_pool_run(void* pv, int k0, int steps, const void* const* in_blocks, int n_blocks,
                                    long long* checksum, ismpc_formc_out_t* out_copy_opt, double* elapsed_s_opt)
 {
+    return pool_run(pv, k0, steps, in_blocks, n_blocks, checksum, out_copy_opt, elapsed_s_opt, false);
+}
+
+// Packed mode.  ismpc_host_pool_set_instances gives slot `s` of thread `t` its fleet's constants (n records); the plans
+// of all fleets are in the table the pool was created with.  ismpc_host_pool_run_packed: tick_blocks holds
+// blocks_per_slot pinned arrays of n ismpc_formc_tick_t for every slot, slot-major (slot = t * depth + s); the j-th tick
+// a slot serves takes block j % blocks_per_slot.  Otherwise as ismpc_host_pool_run.
+extern "C" int ismpc_host_pool_set_instances(void* pv, int t, int s, const ismpc_formc_inst_t* inst)
+{
+    HostPool& hp = *static_cast<HostPool*>(pv);
+    try {
+        if (t < 0 || t >= (int)hp.pipes.size() || s < 0 || s >= hp.pipes[(size_t)t]->depth()) throw std::runtime_error("bad slot");
+        hp.pipes[(size_t)t]->set_instances(s, inst);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int ismpc_host_pool_set_option(void* pv, const char* name, int value)
+{
+    HostPool& hp = *static_cast<HostPool*>(pv);
+    try {
+        for (auto& p : hp.pipes) p->set_option(name, value);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int ismpc_host_pool_run_packed(void* pv, int k0, int steps, const void* const* tick_blocks, int blocks_per_slot,
+                                          long long* checksum, ismpc_formc_out_t* out_copy_opt, double* elapsed_s_opt)
+{
+    return pool_run(pv, k0, steps, tick_blocks, blocks_per_slot, checksum, out_copy_opt, elapsed_s_opt, true);
+}
+
+static int pool_run(void* pv, int k0, int steps, const void* const* in_blocks, int n_blocks, long long* checksum,
+                    ismpc_formc_out_t* out_copy_opt, double* elapsed_s_opt, bool packed)
+{
     HostPool& hp = *static_cast<HostPool*>(pv);
     const int T = (int)hp.pipes.size();
+    hp.packed = packed;
     hp.k0 = k0; hp.steps = steps; hp.in_blocks = in_blocks; hp.n_blocks = n_blocks; hp.out_copy = out_copy_opt;
     hp.done.store(0, std::memory_order_release);
     const auto t0 = std::chrono::steady_clock::now();

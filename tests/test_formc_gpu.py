@@ -304,6 +304,80 @@ def test_resident_plan_equals_plan_per_call(handle):
         handle.formc_solve_batch(state, walk, inst, None)
 
 
+@pytest.mark.parametrize("variant", [2, 1, 16])
+def test_packed_tick_records_and_resident_instances(handle, variant):
+    """ismpc_formc_solve_batch_packed (state and walk state in one 128-byte record per instance) and
+    ismpc_formc_set_instances (the per-instance constants resident in the handle) give bit-identical records, primal
+    vectors and working sets to the three-array call -- from pageable host memory (staged by copies), from pinned host
+    memory (read and written in place by the kernel), with zero copy switched off, and from device memory; in all three
+    builds of the warp kernel family."""
+    import torch
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    handle.set_option("formc_variant", variant)
+    try:
+        state, walk, inst, plan = synth.formc_batch(200, seed=77, k0_cap=400)
+        a = handle.formc_solve_batch(state, walk, inst, plan)
+        tick = abi.pack_ticks(state, walk)
+        assert tick.dtype.itemsize == 128
+
+        def same(b):
+            assert a["out"].tobytes() == b["out"].tobytes()
+            assert np.array_equal(a["primal"], b["primal"]) and np.array_equal(a["active"], b["active"])
+
+        same(handle.formc_solve_batch_packed(tick, inst, plan))                      # pageable, nothing resident
+        handle.formc_set_plan(plan); handle.formc_set_instances(inst)
+        same(handle.formc_solve_batch_packed(tick, None, None))                      # pageable, constants and plans resident
+        same(handle.formc_solve_batch(state, walk, None, None))                      # three arrays, constants resident
+        # pinned buffers: the kernel reads the tick records and writes the result records in place
+        n = len(tick)
+        t_pin = torch.from_numpy(tick.view(np.uint8).reshape(-1).copy()).pin_memory()
+        o_pin = torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8).pin_memory()
+        assert t_pin.data_ptr() % 128 == 0 and o_pin.data_ptr() % 128 == 0
+        for zc in (1, 0):
+            handle.set_option("host_zero_copy", zc)
+            o_pin.zero_()
+            l0 = handle.kernel_launches
+            handle.formc_solve_batch_packed_raw(n, t_pin.data_ptr(), None, None, 0, o_pin.data_ptr(), mem=abi.MEM_HOST)
+            assert handle.kernel_launches == l0 + 1
+            assert o_pin.numpy().tobytes() == a["out"].tobytes(), "pinned buffers, host_zero_copy = %d" % zc
+        handle.set_option("host_zero_copy", 1)
+        # an unaligned pinned array cannot be read in place: staged, same records
+        t_off = torch.zeros(n * 128 + 16, dtype=torch.uint8).pin_memory()
+        t_off[16:] = t_pin
+        o_pin.zero_()
+        handle.formc_solve_batch_packed_raw(n, t_off.data_ptr() + 16, None, None, 0, o_pin.data_ptr(), mem=abi.MEM_HOST)
+        assert o_pin.numpy().tobytes() == a["out"].tobytes()
+        # device memory
+        dev = torch.device("cuda", 0)
+        t_dev = t_pin.to(dev); o_dev = torch.zeros_like(o_pin, device=dev)
+        handle.formc_solve_batch_packed_raw(n, t_dev.data_ptr(), None, None, 0, o_dev.data_ptr(), mem=abi.MEM_DEVICE)
+        torch.cuda.synchronize()
+        assert o_dev.cpu().numpy().tobytes() == a["out"].tobytes()
+        # more instances than the resident constants cover, or constants forgotten: refused
+        handle.formc_set_instances(inst[:50])
+        with pytest.raises(Exception):
+            handle.formc_solve_batch_packed(tick, None, None)
+        handle.formc_set_instances(None)
+        with pytest.raises(Exception):
+            handle.formc_solve_batch_packed(tick[:10], None, None)
+    finally:
+        handle.set_option("formc_variant", 0); handle.set_option("host_zero_copy", 1)
+        handle.formc_set_plan(None); handle.formc_set_instances(None)
+
+
+def test_packed_call_needs_the_warp_kernel_family(handle):
+    model = abi.formc_model()
+    handle.formc_set_model(model)
+    state, walk, inst, plan = synth.formc_batch(8, seed=78)
+    handle.set_option("formc_kernel", 1)
+    try:
+        with pytest.raises(Exception):
+            handle.formc_solve_batch_packed(abi.pack_ticks(state, walk), inst, plan)
+    finally:
+        handle.set_option("formc_kernel", 0)
+
+
 @pytest.mark.parametrize("N", [37, 101, 512])
 def test_ragged_and_maximum_horizons(handle, N):
     """Horizons that do not fill the lanes evenly (37 = 32 + 5 with two samples per lane, 101 = 25 full lanes + 1) and the

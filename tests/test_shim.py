@@ -134,6 +134,51 @@ def test_cpp_serving_loop_equals_direct_calls(handle):
         handle.formc_set_plan(None)
 
 
+@pytest.mark.gpu
+def test_cpp_serving_loop_packed_equals_direct_calls(handle):
+    """The packed serving loop (one fleet per slot: constants and plans resident, one 128-byte record per instance and
+    tick, read / written in place by the kernel): the records of the last tick of every slot equal a synchronous
+    three-array call on the same values."""
+    import ctypes as C
+    import torch
+    L = _hostlib()
+    L.ismpc_host_pool_create.restype = C.c_void_p
+    L.ismpc_host_pool_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ismpc_host_pool_destroy.argtypes = [C.c_void_p]
+    L.ismpc_host_pool_set_instances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ismpc_host_pool_run_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n, T, D, R = 192, 2, 3, 2
+    model = abi.formc_model()
+    fleets = [synth.formc_batch(n, seed=90 + f, n_steps=40) for f in range(T * D)]
+    plans = np.concatenate([f[3] for f in fleets])
+    handle.formc_set_model(model)
+    pool = L.ismpc_host_pool_create(0, n, T, D, model.ctypes.data, 35, 10, plans.ctypes.data, plans.shape[0])
+    assert pool, L.ismpc_host_last_error()
+    keep, ptrs, insts = [], [], []
+    try:
+        for slot, (st, wk, ins, pl) in enumerate(fleets):
+            ins = ins.copy(); ins["plan_first_row"] += slot * pl.shape[0]
+            insts.append(ins)
+            assert L.ismpc_host_pool_set_instances(pool, slot // D, slot % D, ins.ctypes.data) == 0, L.ismpc_host_last_error()
+            for j in range(R):                               # R successive ticks of the fleet's closed loop
+                r = handle.formc_rollout(st, wk, ins, plans, j, want_traj=False) if j else dict(state=st, walk=wk)
+                tk = abi.pack_ticks(r["state"], r["walk"])
+                t = torch.from_numpy(tk.view(np.uint8).reshape(-1).copy()).pin_memory()
+                keep.append((t, r["state"], r["walk"])); ptrs.append(t.data_ptr())
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        steps = T * D * 3                                     # every slot serves three ticks: blocks 0, 1, 0
+        out = np.zeros((T, D, n), dtype=abi.FORMC_OUT)
+        csum = C.c_longlong(0); el = C.c_double(0.0)
+        assert L.ismpc_host_pool_run_packed(pool, 0, steps, arr, R, C.byref(csum), out.ctypes.data, C.byref(el)) == 0, \
+            L.ismpc_host_last_error()
+    finally:
+        L.ismpc_host_pool_destroy(pool)
+    for slot in range(T * D):
+        _, st, wk = keep[slot * R + (2 % R)]
+        ref = handle.formc_solve_batch(st, wk, insts[slot], plans, want_primal=False, want_active=False)
+        assert out[slot // D, slot % D].tobytes() == ref["out"].tobytes(), "slot %d" % slot
+
+
 def _build_pipeline_example(d):
     exe = os.path.join(d, "pipeline_example")
     libdir = os.path.dirname(binding.LIB_PATH)
