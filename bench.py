@@ -168,6 +168,38 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def pin_to_gpu_numa_node(local, world):
+    """Host threads of a rank run on the CPUs next to the rank's GPU (its PCIe root's NUMA node, from sysfs); ranks whose
+    GPUs share a node take disjoint slices of its CPUs.  Set before any thread exists, so every thread of the process
+    (the serving loop's workers included) inherits it.  Returns what was done, for the bench line."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                           text=True, timeout=30).stdout
+        bus = {}
+        for ln in q.strip().splitlines():
+            i, b = [x.strip() for x in ln.split(",")]
+            bus[int(i)] = b.lower().replace("00000000:", "0000:")
+
+        def cpus_of(i):
+            txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bus[i]).read().strip()
+            out = []
+            for part in txt.split(","):
+                a, _, b = part.partition("-")
+                out += list(range(int(a), int(b or a) + 1))
+            return out
+        mine = cpus_of(local)
+        allowed = sorted(os.sched_getaffinity(0))
+        mine = [c for c in mine if c in allowed] or allowed
+        sharers = [i for i in range(world) if i in bus and cpus_of(i) == cpus_of(local)] or [local]
+        k, m = sharers.index(local), len(sharers)
+        per = max(1, len(mine) // m)
+        sl = mine[k * per:(k + 1) * per] or mine
+        os.sched_setaffinity(0, sl)
+        return {"gpu": local, "numa_cpus": len(mine), "ranks_sharing_the_node": m, "cpus_of_this_rank": sl}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def spread(xs):
     xs = sorted(float(x) for x in xs)
     return {"n": len(xs), "median": statistics.median(xs), "min": xs[0], "max": xs[-1]}
@@ -189,12 +221,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = pin_to_gpu_numa_node(local, world) if os.environ.get("ISMPC_BENCH_PIN", "1") != "0" else None
     import torch
     import torch.distributed as dist
     from quadruped_gait_generation_ismpc_b200 import abi, binding, sharding, synth
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -496,8 +529,8 @@ def main():
             raise RuntimeError("ismpc_host_pool_set_instances: " + hostlib.ismpc_host_last_error().decode())
         for j in range(BLK):
             r_ = h.formc_rollout(st, wk, ins_res, all_plans, j, want_traj=False) if j else dict(state=st, walk=wk)
-            t_ = torch.from_numpy(abi.pack_ticks(r_["state"], r_["walk"]).view(np.uint8).reshape(-1).copy()).pin_memory()
-            fleet_keep.append((t_, r_["state"], r_["walk"], ins_res)); fleet_ptrs.append(t_.data_ptr())
+            t_ = binding.PinnedBuffer(n * abi.FORMC_TICK.itemsize, fill=abi.pack_ticks(r_["state"], r_["walk"]))   # ismpc_host_alloc
+            fleet_keep.append((t_, r_["state"], r_["walk"], ins_res)); fleet_ptrs.append(t_.ptr)
     tick_blocks = (C.c_void_p * len(fleet_ptrs))(*fleet_ptrs)
     h2d = n * abi.FORMC_TICK.itemsize
     if T_HOST * D_HOST >= 8:
@@ -591,6 +624,7 @@ def main():
                                "data / globals of the reference's MPCSolver; K steps per repeat timed by the pool's own clock (first "
                                "submit -> last result read), max over ranks, median of %d repeats" % (T_HOST, D_HOST, n, R),
                         "kernel_launches": int(e2e_cpp_launches),
+                        "cpu_affinity_rank0": affinity,
                         "host_threads_busy": {"in_driver_calls_frac": statistics.median(host_submit) / (T_HOST * e2e_cpp_s),
                                               "waiting_for_the_gpu_frac": statistics.median(host_wait) / (T_HOST * e2e_cpp_s),
                                               "note": "per host thread, of the timed region (rank 0): a thread that mostly waits "

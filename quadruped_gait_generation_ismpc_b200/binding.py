@@ -100,6 +100,33 @@ def lib():
     return L
 
 
+class PinnedBuffer:
+    """Pinned host memory from ismpc_host_alloc (what a C / C++ caller uses for the buffers of the host-memory modes): the
+    library knows these ranges and lets the kernels of the packed calls read / write them in place without asking the
+    driver about the pointer.  .array is a uint8 numpy view, .ptr the address."""
+
+    def __init__(self, nbytes, fill=None):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().ismpc_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise IsmpcError("ismpc_host_alloc(%d) failed" % self.nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+        if fill is not None:
+            self.array[:] = np.ascontiguousarray(fill).view(np.uint8).reshape(-1)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().ismpc_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _ptr(a):
     """Pointer of a numpy array (host), an int (device address) or None."""
     if a is None:

@@ -2,7 +2,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 #include "formc.cuh"
 #include "formc_warp.cuh"
 #include "forma.cuh"
@@ -144,14 +146,46 @@ extern "C" int ismpc_wait(ismpc_handle* h, void* stream)
     return ISMPC_OK;
 }
 
+// Pinned host ranges the library knows the device can address in place (allocated by ismpc_host_alloc): looked up per
+// call by the zero-copy path instead of asking the driver (cudaPointerGetAttributes costs about as much as a kernel
+// launch).  Under unified addressing the device address of cudaHostAlloc memory is the host address.
+namespace {
+struct HostRange { const char* p; size_t bytes; };
+std::mutex g_host_mu;
+std::vector<HostRange> g_host_ranges;
+bool host_range_known(const void* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    for (const HostRange& r : g_host_ranges)
+        if ((const char*)p >= r.p && (const char*)p + bytes <= r.p + r.bytes) return true;
+    return false;
+}
+}  // namespace
+
 extern "C" void* ismpc_host_alloc(size_t bytes)
 {
     void* p = nullptr;
-    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d == p) {      // unified addressing: usable in place by its host address
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_host_ranges.push_back({(const char*)p, bytes});
+    } else {
+        (void)cudaGetLastError();
+    }
     return p;
 }
 
-extern "C" void ismpc_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void ismpc_host_free(void* p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        for (size_t i = 0; i < g_host_ranges.size(); ++i)
+            if (g_host_ranges[i].p == (const char*)p) { g_host_ranges.erase(g_host_ranges.begin() + (long)i); break; }
+    }
+    cudaFreeHost(p);
+}
 
 extern "C" int ismpc_set_option(ismpc_handle* h, const char* name, int value)
 {
@@ -430,6 +464,7 @@ static void* zero_copy_address(const void* p, size_t bytes)
 {
     constexpr size_t ZC_MAX_BYTES = 8u << 20;
     if (!p || ((uintptr_t)p & 127u) != 0 || bytes > ZC_MAX_BYTES) return nullptr;
+    if (host_range_known(p, bytes)) return const_cast<void*>(p);
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
     return (pa.type == cudaMemoryTypeHost && pa.devicePointer) ? pa.devicePointer : nullptr;
