@@ -793,13 +793,43 @@ def bench_group(torch, G, n, K, W, R, model, host_batches):
             ts.append(time.perf_counter() - t0)
         t = statistics.median(ts)
         out = np.frombuffer(C.string_at(out_p, N * abi.FORMC_OUT.itemsize), dtype=abi.FORMC_OUT)
+        res["host_buffer_ticks_copies"] = {"value": 3.0 * N * K / t, "unit": "QP solves/s", "ms_per_step": t / K * 1e3,
+                                           "instances_per_step": N, "repeats_s": spread(ts),
+                                           "failed_instances_last_step": int(((out["status"] & 7) != 0).sum()),
+                                           "h2d_bytes_per_step": int(N * (abi.STATE.itemsize + abi.WALK.itemsize + abi.FORMC_INST.itemsize)),
+                                           "d2h_bytes_per_step": int(N * abi.FORMC_OUT.itemsize),
+                                           "how": "ismpc_group_formc_solve_batch: one synchronous call per step, every device copies "
+                                                  "its shard in, solves, copies its records out (three arrays, copy engines)"}
+        # the same ticks with packed records and the constants resident per shard: each device's kernel reads / writes the
+        # pinned host arrays in place (what host/MPCSolverMultiGpu.hpp::solve does)
+        st, wk, ins, pl = host_batches[0]
+        g.formc_set_instances(np.tile(ins, G))
+        tks = []
+        for b in range(2):
+            tk = abi.pack_ticks(np.tile(host_batches[0][0], G), np.tile(host_batches[0][1], G))
+            if b:
+                tk["state"]["com_vel"] *= 0.5             # a second, different block of tick records for the same fleet
+            tks.append(binding.PinnedBuffer(tk.nbytes, fill=tk))
+        for k in range(max(W, 2)):
+            g.formc_solve_batch_packed_raw(N, tks[k % 2].ptr, out_p)
+        ts = []
+        for r in range(R):
+            t0 = time.perf_counter()
+            for k in range(K):
+                g.formc_solve_batch_packed_raw(N, tks[k % 2].ptr, out_p)
+            ts.append(time.perf_counter() - t0)
+        t = statistics.median(ts)
+        out = np.frombuffer(C.string_at(out_p, N * abi.FORMC_OUT.itemsize), dtype=abi.FORMC_OUT)
         res["host_buffer_ticks"] = {"value": 3.0 * N * K / t, "unit": "QP solves/s", "ms_per_step": t / K * 1e3,
                                     "instances_per_step": N, "repeats_s": spread(ts),
                                     "failed_instances_last_step": int(((out["status"] & 7) != 0).sum()),
-                                    "h2d_bytes_per_step": int(N * (abi.STATE.itemsize + abi.WALK.itemsize + abi.FORMC_INST.itemsize)),
+                                    "h2d_bytes_per_step": int(N * abi.FORMC_TICK.itemsize),
                                     "d2h_bytes_per_step": int(N * abi.FORMC_OUT.itemsize),
-                                    "how": "ismpc_group_formc_solve_batch: one synchronous call per step, every device moves and "
-                                           "solves its shard concurrently"}
+                                    "how": "ismpc_group_formc_solve_batch_packed: one synchronous call per step; every device's "
+                                           "kernel reads its shard's 128-byte tick records from, and writes its result records "
+                                           "to, the caller's pinned arrays in place (one launch per device and step)"}
+        for t_ in tks:
+            t_.close()
         for ptrs in blocks:
             for p in ptrs:
                 L.ismpc_host_free(p)

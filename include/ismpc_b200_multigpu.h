@@ -51,6 +51,13 @@ int ismpc_group_formc_configure(ismpc_group* g, const ismpc_formc_model_t* model
 int ismpc_group_formc_solve_batch(ismpc_group* g, int n_total, const ismpc_state_t* state, const ismpc_walk_t* walk,
                                   const ismpc_formc_inst_t* inst, ismpc_formc_out_t* out);
 
+/* The same with packed tick records (ismpc_formc_solve_batch_packed): ismpc_group_formc_set_instances hands every device
+ * the constants of its shard of the n_total instances once; a tick then moves one 128-byte {State, WalkState} record per
+ * instance in and one result record out -- read and written in place by each device's kernel when `tick` / `out` are
+ * pinned (ismpc_host_alloc) and 128-byte aligned, one kernel launch per device and tick. */
+int ismpc_group_formc_set_instances(ismpc_group* g, int n_total, const ismpc_formc_inst_t* inst);
+int ismpc_group_formc_solve_batch_packed(ismpc_group* g, int n_total, const ismpc_formc_tick_t* tick, ismpc_formc_out_t* out);
+
 /* Closed loop with the state resident per GPU: scatter once, advance with no communication, gather once.
  * push (nullable): n_total entries, ticks counted from the scatter. */
 int ismpc_group_formc_scatter(ismpc_group* g, int n_total, const ismpc_state_t* state, const ismpc_walk_t* walk,

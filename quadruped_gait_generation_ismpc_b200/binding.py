@@ -428,7 +428,7 @@ MG_LIB_PATH = os.path.join(_HERE, "lib", "libismpc_b200_mg.so")
 MG_EXPORTS = ["ismpc_group_create", "ismpc_group_destroy", "ismpc_group_size", "ismpc_group_last_error",
               "ismpc_group_kernel_launches", "ismpc_group_handle", "ismpc_group_shard", "ismpc_group_formc_configure",
               "ismpc_group_formc_solve_batch", "ismpc_group_formc_scatter", "ismpc_group_formc_rollout", "ismpc_group_wait",
-              "ismpc_group_formc_gather"]
+              "ismpc_group_formc_gather", "ismpc_group_formc_set_instances", "ismpc_group_formc_solve_batch_packed"]
 GATHER_NCCL, GATHER_HOST = 0, 1
 _mglib = None
 
@@ -454,6 +454,8 @@ def mglib():
     L.ismpc_group_formc_configure.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.ismpc_group_formc_solve_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
     L.ismpc_group_formc_scatter.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.ismpc_group_formc_set_instances.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ismpc_group_formc_solve_batch_packed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ismpc_group_formc_rollout.argtypes = [C.c_void_p, C.c_int]
     L.ismpc_group_wait.argtypes = [C.c_void_p]
     L.ismpc_group_formc_gather.argtypes = [C.c_void_p] + [C.c_void_p] * 3
@@ -515,6 +517,19 @@ class Group:
     def formc_solve_batch_raw(self, n, state, walk, inst, out):
         self._check(self._L.ismpc_group_formc_solve_batch(self._g, n, _ptr(state), _ptr(walk), _ptr(inst), _ptr(out)),
                     "ismpc_group_formc_solve_batch")
+
+    def formc_set_instances(self, inst):
+        inst = np.ascontiguousarray(inst)
+        self._check(self._L.ismpc_group_formc_set_instances(self._g, len(inst), _ptr(inst)), "ismpc_group_formc_set_instances")
+
+    def formc_solve_batch_packed(self, tick, out=None):
+        n = len(tick)
+        out = np.zeros(n, dtype=abi.FORMC_OUT) if out is None else out
+        self._check(self._L.ismpc_group_formc_solve_batch_packed(self._g, n, _ptr(tick), _ptr(out)), "ismpc_group_formc_solve_batch_packed")
+        return out
+
+    def formc_solve_batch_packed_raw(self, n, tick, out):
+        self._check(self._L.ismpc_group_formc_solve_batch_packed(self._g, n, _ptr(tick), _ptr(out)), "ismpc_group_formc_solve_batch_packed")
 
     def formc_scatter(self, state, walk, inst, push=None):
         self._check(self._L.ismpc_group_formc_scatter(self._g, len(state), _ptr(state), _ptr(walk), _ptr(inst), _ptr(push)),

@@ -232,6 +232,40 @@ extern "C" int ismpc_group_formc_solve_batch(ismpc_group* g, int n_total, const 
     });
 }
 
+extern "C" int ismpc_group_formc_set_instances(ismpc_group* g, int n_total, const ismpc_formc_inst_t* inst)
+{
+    if (!g || n_total < 0 || (n_total > 0 && !inst)) return ISMPC_ERR_ARG;
+    const int G = (int)g->shards.size();
+    if ((n_total + G - 1) / G > g->max_batch) return ISMPC_ERR_ARG;
+    g->err.clear();
+    return g->run([=](Shard& s) -> int {
+        int first, count;
+        shard_of(n_total, G, s.rank, &first, &count);
+        int rc = ismpc_formc_set_instances(s.h, count > 0 ? inst + first : nullptr, count, ISMPC_MEM_HOST);
+        if (rc != ISMPC_OK) return g->fail(rc, "ismpc_formc_set_instances", &s);
+        return ISMPC_OK;
+    });
+}
+
+extern "C" int ismpc_group_formc_solve_batch_packed(ismpc_group* g, int n_total, const ismpc_formc_tick_t* tick,
+                                                    ismpc_formc_out_t* out)
+{
+    if (!g || n_total < 0 || !tick || !out) return ISMPC_ERR_ARG;
+    const int G = (int)g->shards.size();
+    if ((n_total + G - 1) / G > g->max_batch) return ISMPC_ERR_ARG;
+    g->err.clear();
+    return g->run([=](Shard& s) -> int {
+        int first, count;
+        shard_of(n_total, G, s.rank, &first, &count);
+        if (count == 0) return ISMPC_OK;
+        int rc = ismpc_formc_solve_batch_packed(s.h, count, tick + first, nullptr, nullptr, 0, out + first, nullptr, nullptr,
+                                                ISMPC_MEM_HOST_ASYNC, s.stream);
+        if (rc != ISMPC_OK) return g->fail(rc, "ismpc_formc_solve_batch_packed", &s);
+        if ((rc = ismpc_wait(s.h, s.stream)) != ISMPC_OK) return g->fail(rc, "ismpc_wait", &s);
+        return ISMPC_OK;
+    });
+}
+
 extern "C" int ismpc_group_formc_scatter(ismpc_group* g, int n_total, const ismpc_state_t* state, const ismpc_walk_t* walk,
                                          const ismpc_formc_inst_t* inst, const ismpc_push_t* push)
 {

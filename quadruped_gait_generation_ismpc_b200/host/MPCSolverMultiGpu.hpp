@@ -62,7 +62,7 @@ public:
         if (rc != ISMPC_OK) throw std::runtime_error(std::string("ismpc_group_create: ") + ismpc_error_string(rc));
         try {
             configure(ftsp_and_timings);
-            st_.resize((size_t)n_); wk_.resize((size_t)n_); inst_.resize((size_t)n_); out_.resize((size_t)n_);
+            st_.resize((size_t)n_); wk_.resize((size_t)n_); inst_.resize((size_t)n_); out_.resize((size_t)n_); tick_.resize((size_t)n_);
             for (int i = 0; i < n_; ++i) {
                 inst_[i].com_height = p.comTargetHeight; inst_[i].box_w = p.footConstraintSquareWidth;
                 inst_[i].box_w_init = 2.0; inst_[i].S = p.S(); inst_[i].F_ds = p.F();
@@ -85,7 +85,11 @@ public:
     void solve(std::vector<StateT>& robots, const std::vector<WalkStateT>& walk, const MatrixT& ftsp_and_timings)
     {
         pack(robots, walk, ftsp_and_timings);
-        check(ismpc_group_formc_solve_batch(g_, n_, st_.data(), wk_.data(), inst_.data(), out_.data()), "ismpc_group_formc_solve_batch");
+        // per-instance constants resident per shard, the tick moves one packed 128-byte record per robot in and one out
+        // (pinned arrays: read / written in place by each device's kernel, one launch per device)
+        if (inst_dirty_) { check(ismpc_group_formc_set_instances(g_, n_, inst_.data()), "ismpc_group_formc_set_instances"); inst_dirty_ = false; }
+        for (int i = 0; i < n_; ++i) { tick_[i].state = st_[i]; tick_[i].walk = wk_[i]; }
+        check(ismpc_group_formc_solve_batch_packed(g_, n_, tick_.data(), out_.data()), "ismpc_group_formc_solve_batch_packed");
         for (int i = 0; i < n_; ++i)
             for (int c = 0; c < 3; ++c) { robots[i].comPos(c) = out_[i].next.com_pos[c]; robots[i].comVel(c) = out_[i].next.com_vel[c]; }
     }
@@ -133,7 +137,7 @@ private:
             bool changed = (int)f.rows() != plan_rows_ || f.cols() < 4;
             for (int i = 0; i < plan_rows_ && !changed; ++i)
                 for (int c = 0; c < 4; ++c) if (plan_[(size_t)i * 4 + c] != f(i, c)) { changed = true; break; }
-            if (changed) { configure(f); for (int i = 0; i < n_; ++i) inst_[i].n_steps = plan_rows_; }
+            if (changed) { configure(f); for (int i = 0; i < n_; ++i) inst_[i].n_steps = plan_rows_; inst_dirty_ = true; }
         }
         for (int i = 0; i < n_; ++i) {
             for (int c = 0; c < 3; ++c) {
@@ -153,6 +157,8 @@ private:
     PinnedArray<ismpc_walk_t> wk_;
     PinnedArray<ismpc_formc_inst_t> inst_;
     PinnedArray<ismpc_formc_out_t> out_;
+    PinnedArray<ismpc_formc_tick_t> tick_;
+    bool inst_dirty_ = true;
     PinnedArray<int32_t> status_;
 };
 
