@@ -269,12 +269,14 @@ __device__ inline bool warp_gauss_jordan(double* K, int dim)
 
 // ---- peeling step of the structured working-set iteration, on the shared-memory copies of the state (out of line: it
 // runs in a fraction of the iterations and is large) ----
-// When nothing is violated and the only rows with a wrong-sign multiplier are ends of runs, the plain rule peels the runs
+// When the only rows with a wrong-sign multiplier are ends of runs, the plain rule peels the runs
 // one row per iteration (the next end row turns wrong once its neighbour is gone: a third of the cold mid-gait QPs spent
 // 20-45 iterations that way).  With nu and the footsteps frozen, the multiplier a run would have at its end if it stopped
 // at row e is closed form (segment constant of the new free stretch against the one-row segment before e), so the run is
 // cut back in one step to the first row whose multiplier keeps its sign.  The next solve corrects nu; overshoot shows up
-// as violated rows and is re-added wholesale.   st: working set, nxt: staged new state (0 = wrong end row; cut rows are
+// as violated rows and is re-added wholesale.  (Violated rows may enter in the same iteration: holding the cut back until
+// nothing is violated cost the slowest cold mid-gait QPs three more iterations, 14 -> 11 per axis over 2,048 + 4,096
+// recorded QPs, none slower.)   st: working set, nxt: staged new state (0 = wrong end row; cut rows are
 // marked 3), cseg: segment constant per row.
 template <int NX, class XF>
 __device__ __forceinline__ void forma_peel_body(const FormAProb& pb, signed char* st, int* nxt, const double* cseg,
@@ -600,13 +602,13 @@ __device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& p
         __syncwarp();
         const unsigned end_mask = __ballot_sync(ISMPC_FULL_MASK, wrong_end);
         // ---- peeling step ----
-        // When nothing is violated and the only rows with a wrong-sign multiplier are ends of runs, the plain rule peels
+        // When the only rows with a wrong-sign multiplier are ends of runs (violated rows may enter alongside), the plain rule peels
         // the runs one row per iteration (the next end row turns wrong once its neighbour is gone: a third of the
         // cold mid-gait QPs spent 20-45 iterations that way).  With nu and the footsteps frozen, the multiplier a run
         // would have at its end if it stopped at row e is closed form (segment constant of the new free stretch against
         // the one-row segment before e), so the run is cut back in one step to the first row whose multiplier keeps
         // its sign.  The next solve corrects nu; overshoot shows up as violated rows and is re-added wholesale.
-        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, viol | wrong_in)) {
+        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, wrong_in)) {
             double xf3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
             for (int f = 0; f < (FT < 3 ? FT : 3); ++f) xf3[f] = xf[f];

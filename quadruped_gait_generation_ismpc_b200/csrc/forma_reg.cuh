@@ -291,7 +291,7 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
         const int st_up = __shfl_up_sync(ISMPC_FULL_MASK, stv[E - 1], 1), st_dn = __shfl_down_sync(ISMPC_FULL_MASK, stv[0], 1);
         const int st_prev = lane == 0 ? 0 : st_up, st_next = lane == 31 ? 0 : st_dn;
         int s1v[E];
-        int changed = 0, wrong_end = 0, viol = 0, wrong_in = 0;
+        int changed = 0, wrong_end = 0, wrong_in = 0;
         {
             int kp = kp0;
             double bp = bp0, PAp = PAp0, mxp = mxp0;
@@ -306,7 +306,6 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
                         if (lo[e] - r > 1e-10 * (1.0 + fabs(lo[e]))) s1 = -1;
                         else if (r - hie > 1e-10 * (1.0 + fabs(hie))) s1 = +1;
                     }
-                    viol |= s1 != 0;
                 } else {
                     const double y = cseg[e] - (e + 1 < E ? cseg[e + 1 < E ? e + 1 : e] : c_after);     // dt * multiplier
                     if (s0 < 0 ? y > 0.0 : y < 0.0) s1 = s0;
@@ -332,7 +331,6 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
             if (s0 == 0) {
                 if (klo - r > 1e-10 * (1.0 + fabs(klo))) s1 = -1;
                 else if (r - khi > 1e-10 * (1.0 + fabs(khi))) s1 = +1;
-                viol |= s1 != 0;
             } else if (s0 < 0 ? kap > 0.0 : kap < 0.0) s1 = s0;
             changed |= s1 != s0;
             sm.rv[C + f] = r;
@@ -345,7 +343,7 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
         // ---- peeling step (see forma_pdas): a run whose end row has a wrong-sign multiplier is cut back in one step to
         // the first row whose multiplier keeps its sign, with nu and the footsteps frozen ----
 #ifdef ISMPC_FORMA_PEEL_CALL
-        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, viol | wrong_in)) {
+        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, wrong_in)) {
             // out of line, on shared-memory copies of the state (forma_peel_smem): stage, call, take the cuts back
             int* nxt = sm.das.wid;
 #pragma unroll
@@ -361,7 +359,7 @@ __device__ __forceinline__ int forma_pdas_reg(const FormAShared& sm, const FormA
             for (int e = 0; e < E; ++e) { const int i = r0 + e; if (i < C) s1v[e] = nxt[i]; }
         }
 #else
-        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, viol | wrong_in)) {
+        if (end_mask != 0u && !__any_sync(ISMPC_FULL_MASK, wrong_in)) {
             unsigned todo = end_mask;
             while (todo) {
                 const int L = __ffs(todo) - 1; todo &= todo - 1;

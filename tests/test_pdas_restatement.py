@@ -70,7 +70,7 @@ def pdas(Hd, g, aeq, beq, Ain, lo, hi, C_, peel=True, maxit=200):
             sl = st[i - 1] if i > 0 else 0; sr = st[i + 1] if i + 1 < C_ else 0
             if sl != st[i] or sr != st[i]:
                 ends[i] = (sl != st[i], sr != st[i])
-        if peel and ends and nviol == 0 and len(ends) == len(wz):
+        if peel and ends and len(ends) == len(wz):                 # (violated rows may enter in the same iteration)
             # peeling step: with nu and the footsteps frozen, cut each run back to the first row whose multiplier would
             # keep its sign (closed-form segment constants)
             nu = -mu0
