@@ -37,11 +37,11 @@ L2_BYTES = 126 * 1024 * 1024
 # state 72 + walk 24 + inst 40 + 7 plan rows x 32 (the rows the 2N window touches) + out 128
 B_ALG_FORMC = 72 + 24 + 40 + 7 * 32 + 128
 # executed FP64 flops per instance-tick: counted by ncu on the committed capture (2 per DFMA, 1 per DMUL/DADD, thread
-# level, predicated-on), profiles/r2_formc_tick_pair_ncu.json; the fallback is the hand count of DESIGN.md section 4
+# level, predicated-on), profiles/r2f_formc_tick_*_ncu.json; the fallback is the hand count of DESIGN.md section 4
 FLOP_FORMC_FALLBACK = 28000
 F_REF_FORMC = 2 * 0.96e6 + 0.49e6
-NCU_JSON = {"formc_tick_pair_kernel": os.path.join(ROOT, "profiles", "r2_formc_tick_pair_ncu.json"),
-            "formc_tick_warp_kernel<16>": os.path.join(ROOT, "profiles", "r2_formc_tick_warp16_ncu.json")}
+NCU_JSON = {"formc_tick_pair_kernel": os.path.join(ROOT, "profiles", "r2f_formc_tick_pair_ncu.json"),
+            "formc_tick_warp_kernel<16>": os.path.join(ROOT, "profiles", "r2f_formc_tick_warp16_ncu.json")}
 
 
 def load_ncu(kernel="formc_tick_pair_kernel"):
@@ -647,7 +647,11 @@ def main():
                              "kernel": headline_kernel, "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_instance_tick": B_ALG_FORMC,
                              "note": "the kernel is bound by the dependent-issue latency of one warp (pair) per instance, not "
-                                     "by HBM or FP64 throughput (DESIGN.md section 4); both fractions are small by construction"},
+                                     "by HBM or FP64 throughput (DESIGN.md section 4); both fractions are small by construction.  "
+                                     "kernel_ms = timed region / K: with programmatic dependent launch consecutive ticks overlap on "
+                                     "the GPU, so this is the interval between tick completions; one launch on its own lasts longer "
+                                     "(profiles/r2f_launches_bench.csv: ~15 us for the throughput build, ~12 us for the latency "
+                                     "build, serialised under ncu) -- the strictly_ordered arm is the serialised chain"},
                 "roofline_fp64": {"bound": "fp64", "achieved": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12,
                                   "peak": fp64_peak, "unit": "TFLOP/s",
                                   "frac": FLOP_FORMC * n / (kernel_ms * 1e-3) / 1e12 / fp64_peak,

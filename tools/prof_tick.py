@@ -24,6 +24,27 @@ def to_dev(a):
 
 
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if which == "formcp":
+    # packed tick records in pinned host memory, read / written in place by the kernel (ismpc_formc_solve_batch_packed)
+    h.formc_set_model(abi.formc_model())
+    if os.environ.get("ISMPC_VARIANT"):
+        h.set_option("formc_variant", int(os.environ["ISMPC_VARIANT"]))
+    h.formc_prepare_gait(35, 10)
+    st, wk, ins, pl = synth.formc_batch(n)
+    h.formc_set_plan(pl); h.formc_set_instances(ins)
+    tk = binding.PinnedBuffer(n * 128, fill=abi.pack_ticks(st, wk))
+    ob = binding.PinnedBuffer(n * 128)
+    s_ = torch.cuda.current_stream().cuda_stream
+    for r in range(reps):
+        burst = int(os.environ.get("ISMPC_BURST", "20"))
+        e0.record()
+        for _ in range(burst):
+            h.formc_solve_batch_packed_raw(n, tk.ptr, None, None, 0, ob.ptr, mem=abi.MEM_HOST_ASYNC, stream=s_)
+        e1.record(); e1.synchronize()
+        print("formc packed tick (pinned host records in place) n=%d: %.1f us per launch (%d back-to-back)" % (n, e0.elapsed_time(e1) * 1e3 / burst, burst))
+    o = np.frombuffer(ob.array.tobytes(), dtype=abi.FORMC_OUT)
+    print("failed instances:", int(((o["status"] & 7) != 0).sum()))
+    sys.exit(0)
 if which == "formc":
     h.formc_set_model(abi.formc_model())
     if os.environ.get("ISMPC_FORMC_KERNEL"):
