@@ -656,9 +656,9 @@ __device__ __forceinline__ void forma_selfcheck(const FormAShared& sm, int C, in
 // (shapes the register build does not cover: C > 128 or F > 3, or `forma_reg` = 0) and the dual active set that
 // backs both up.  On entry the bounds are in shifted coordinates iff use_pdas != 0.  Returns status bits.
 template <int FT>
-__device__ __noinline__ int forma_solve_slow(const FormAShared* smp, const FormAProb* pbp, double beq, double cur, int warm,
-                                             int use_pdas, int tried_reg, const double* rg, int* iters_io, double* eqv_out,
-                                             double* viol_out)
+__device__ __forceinline__ int forma_solve_slow_body(const FormAShared* smp, const FormAProb* pbp, double beq, double cur, int warm,
+                                                     int use_pdas, int tried_reg, const double* rg, int* iters_io,
+                                                     double* eqv_out, double* viol_out)
 {
     const FormAShared& sm = *smp;
     FormAProb pb = *pbp;
@@ -717,10 +717,22 @@ __device__ __noinline__ int forma_solve_slow(const FormAShared* smp, const FormA
     return status;
 }
 
+template <int FT>
+__device__ __noinline__ int forma_solve_slow(const FormAShared* smp, const FormAProb* pbp, double beq, double cur, int warm,
+                                             int use_pdas, int tried_reg, const double* rg, int* iters_io, double* eqv_out,
+                                             double* viol_out)
+{
+    return forma_solve_slow_body<FT>(smp, pbp, beq, cur, warm, use_pdas, tried_reg, rg, iters_io, eqv_out, viol_out);
+}
+
 // One tick for one (instance, axis) by one warp.  Returns status bits; writes x (primal) in sm.x.
+// HOT: the build of the kernels for the shapes the register-resident iteration covers (C <= 128, F <= 3): that iteration
+// inline, everything else behind one out-of-line call.  !HOT (longer horizons, more footsteps, `forma_reg` = 0): the
+// shared-memory walk IS the hot path and is inlined with the kernel's full register budget -- behind the out-of-line
+// call and the 128-register cap it ran 1.25-1.4x slower (C = 200: 218 vs 157 us per 1,024-instance tick).
 // in: the instance (by reference; read only), plan: this instance's fs_plan rows, ft: its fs_timing.
 // warm != 0: sm.das.state holds a working-set guess (previous tick's set shifted by one tick).
-template <int FT>
+template <int FT, bool HOT>
 __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_model_t& mdl,
                                       const ismpc_forma_inst_t& in, const double* st3 /*x,xd,xz of this axis*/,
                                       double cur, double fs_store, int j, int fs_counter, int first_ramp,
@@ -854,7 +866,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
         if (lane == 0) { sm.lo[C] -= cur; sm.hi[C] -= cur; }
         for (int f = lane; f < F; f += 32) sm.z[f] = sm.z[C + f] - cur;
         __syncwarp();
-        if constexpr (FT <= 3) {
+        if constexpr (HOT && FT <= 3) {
             if ((use_pdas & 2) && C <= 128) {
                 // ---- hot path: the working-set iteration with this lane's rows in registers (forma_reg.cuh) ----
                 tried_reg = 1;
@@ -879,10 +891,14 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
     if (!solved) {
         // (copies: the out-of-line call takes addresses, and the hot path's own structs must not escape to local memory --
         // when they did, every shared-memory access of the iteration became a generic load behind a pointer re-read)
-        FormAShared smc = sm; FormAProb pbc = pb;
-        int it_c = iters; double eqv_c = 0.0, viol_c = 0.0;
-        status |= forma_solve_slow<FT>(&smc, &pbc, beq, cur, warm, use_pdas, tried_reg, rg, &it_c, &eqv_c, &viol_c);
-        iters = it_c; eqv = eqv_c; viol = viol_c;
+        if constexpr (HOT) {
+            FormAShared smc = sm; FormAProb pbc = pb;
+            int it_c = iters; double eqv_c = 0.0, viol_c = 0.0;
+            status |= forma_solve_slow<FT>(&smc, &pbc, beq, cur, warm, use_pdas, tried_reg, rg, &it_c, &eqv_c, &viol_c);
+            iters = it_c; eqv = eqv_c; viol = viol_c;
+        } else {
+            status |= forma_solve_slow_body<FT>(&sm, &pb, beq, cur, warm, use_pdas, tried_reg, rg, &iters, &eqv, &viol);
+        }
     }
     *iters_out = iters;
     *kkt_out = fmax(fabs(eqv - beq), fmax(viol, 0.0));

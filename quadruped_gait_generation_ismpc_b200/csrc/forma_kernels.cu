@@ -44,8 +44,8 @@ __device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in
     return ft[1] > ft[0];
 }
 
-template <int FT>
-__global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_tick_kernel(FormAArgs a)
+template <int FT, bool HOT>
+__global__ void __maxnreg__(HOT ? FORMA_MAX_REGS : 255) forma_tick_kernel(FormAArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = warp_id(), lane = lane_id();
@@ -74,7 +74,7 @@ __global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_tick_kernel(Fo
         const int32_t* ft = a.fs_timing + in.timing_first;
         double s3[3] = {in.st[axis * 3 + 0], in.st[axis * 3 + 1], in.st[axis * 3 + 2]};
         int iters; double kkt;
-        int status = forma_tick_axis<FT>(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
+        int status = forma_tick_axis<FT, HOT>(sm, a.model, in, s3, in.cur_fs[axis], in.fs_store[axis], in.j, in.fs_counter,
                                          in.cl_first_ramp, plan, ft, axis, 0, a.use_pdas, rg, &iters, &kkt);
         DasTimer tme; tme.start();
         const double eta = sqrt(a.model.g_eta / in.height);
@@ -114,8 +114,8 @@ struct FormARolloutArgs {
     int32_t* trace;        // nullable, n x n_ticks x 2: status of every tick, per axis (x, y)
 };
 
-template <int FT>
-__global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_rollout_kernel(FormARolloutArgs ra)
+template <int FT, bool HOT>
+__global__ void __maxnreg__(HOT ? FORMA_MAX_REGS : 255) forma_rollout_kernel(FormARolloutArgs ra)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FormAArgs& a = ra.base;
@@ -149,7 +149,7 @@ __global__ void __maxnreg__(FT <= 3 ? FORMA_MAX_REGS : 255) forma_rollout_kernel
         for (int tick = 0; tick < ra.n_ticks; ++tick) {
             if (fsc == pu.fs && ct >= pu.ct0 && ct < pu.ct1) s3[1] += a.model.dt * (axis == 0 ? pu.ax : pu.ay); // bang.m:104-114
             int iters; double kkt;
-            const int tick_status = forma_tick_axis<FT>(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis,
+            const int tick_status = forma_tick_axis<FT, HOT>(sm, a.model, in, s3, cur, store, j, fsc, first_ramp, plan, ft, axis,
                                                         a.warm_start && tick > 0, a.use_pdas, rg, &iters, &kkt);
             acc |= tick_status;
             if (ra.trace && lane == 0) ra.trace[((size_t)inst * ra.n_ticks + tick) * 2 + axis] = tick_status;
@@ -234,21 +234,27 @@ void forma_plan(const ismpc_forma_model_t& m, int sm_count, long long items, con
     while (R > 1 && forma_warp_smem_bytes(C, F, R) * wpc + hdr > lim) --R;
     p->R = R; p->warps_per_cta = wpc;
     p->smem = forma_warp_smem_bytes(C, F, R) * wpc + hdr;
+    // build of the kernels: 0 = <3, HOT> (register-resident iteration: C <= 128, F <= 3, `forma_reg` on), 1 = <3, cold>,
+    // 2 = <ISMPC_MAX_FSTEPS, cold>
+    p->kernel = (F <= 3 && C <= 128 && tune.reg) ? 0 : (F <= 3 ? 1 : 2);
     int per_sm = 0;
-    if (occ && occ->per_sm > 0 && occ->F3 == (F <= 3) && occ->wpc == wpc && occ->smem == p->smem) per_sm = occ->per_sm;
+    if (occ && occ->per_sm > 0 && occ->F3 == p->kernel && occ->wpc == wpc && occ->smem == p->smem) per_sm = occ->per_sm;
     if (per_sm <= 0) {
         // what the GPU really keeps resident (registers and shared memory), asked of the runtime
         int b = 0;
         cudaError_t e;
-        if (F <= 3) {
-            cudaFuncSetAttribute(forma_tick_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<3>, 32 * wpc, p->smem);
+        if (p->kernel == 0) {
+            cudaFuncSetAttribute(forma_tick_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<3, true>, 32 * wpc, p->smem);
+        } else if (p->kernel == 1) {
+            cudaFuncSetAttribute(forma_tick_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<3, false>, 32 * wpc, p->smem);
         } else {
-            cudaFuncSetAttribute(forma_tick_kernel<ISMPC_MAX_FSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<ISMPC_MAX_FSTEPS>, 32 * wpc, p->smem);
+            cudaFuncSetAttribute(forma_tick_kernel<ISMPC_MAX_FSTEPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, forma_tick_kernel<ISMPC_MAX_FSTEPS, false>, 32 * wpc, p->smem);
         }
         per_sm = (e == cudaSuccess && b > 0) ? b : 1;
-        if (occ) { occ->per_sm = per_sm; occ->F3 = (F <= 3); occ->wpc = wpc; occ->smem = p->smem; }
+        if (occ) { occ->per_sm = per_sm; occ->F3 = p->kernel; occ->wpc = wpc; occ->smem = p->smem; }
     }
     long long ctas = (items + wpc - 1) / wpc;
     long long resident = (long long)per_sm * sm_count;
@@ -263,7 +269,7 @@ int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStrea
 {
     FormAArgs a = a_in;
     a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = 0;
-    auto kern = a.model.F <= 3 ? forma_tick_kernel<3> : forma_tick_kernel<ISMPC_MAX_FSTEPS>;
+    auto kern = p.kernel == 0 ? forma_tick_kernel<3, true> : p.kernel == 1 ? forma_tick_kernel<3, false> : forma_tick_kernel<ISMPC_MAX_FSTEPS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
@@ -278,7 +284,7 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
 {
     FormAArgs a = a_in;
     a.R = p.R; a.warps_per_cta = p.warps_per_cta; a.use_pdas = p.use_pdas; a.warm_start = p.warm_start;
-    auto kern = a.model.F <= 3 ? forma_rollout_kernel<3> : forma_rollout_kernel<ISMPC_MAX_FSTEPS>;
+    auto kern = p.kernel == 0 ? forma_rollout_kernel<3, true> : p.kernel == 1 ? forma_rollout_kernel<3, false> : forma_rollout_kernel<ISMPC_MAX_FSTEPS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(a.queue, 0, sizeof(int), st);
