@@ -372,8 +372,8 @@ constexpr int PDAS_DAMP_AFTER = 12;
 constexpr int PDAS_MAX_ITERS = 80;
 
 template <int FT>
-__device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
-                                 const double* planf, const double* rg, int maxit, int* iters_out)
+__device__ __forceinline__ int forma_pdas_body(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
+                                               const double* planf, const double* rg, int maxit, int* iters_out)
 {
     constexpr int NS = 2 + 2 * FT + FT * (FT + 1) / 2;
     const int lane = lane_id();
@@ -612,8 +612,11 @@ __device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& p
             double xf3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
             for (int f = 0; f < (FT < 3 ? FT : 3); ++f) xf3[f] = xf[f];
-            if constexpr (FT <= 3) forma_peel_smem(&pb, st, nxt, cseg, rg, nu, xf3[0], xf3[1], xf3[2], end_mask, qz_dt);
-            else forma_peel_smem_wide<FT>(&pb, st, nxt, cseg, rg, nu, xf, end_mask, qz_dt);
+            // (a copy goes to the out-of-line call: the address of `pb` itself must not escape, or the struct moves to
+            // local memory and every shared-memory access of the iteration becomes a generic load behind a pointer re-read)
+            const FormAProb pbc = pb;
+            if constexpr (FT <= 3) forma_peel_smem(&pbc, st, nxt, cseg, rg, nu, xf3[0], xf3[1], xf3[2], end_mask, qz_dt);
+            else forma_peel_smem_wide<FT>(&pbc, st, nxt, cseg, rg, nu, xf, end_mask, qz_dt);
         }
         {
             const bool damp = it >= PDAS_DAMP_AFTER && end_mask != 0u;
@@ -636,6 +639,16 @@ __device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& p
     return rc;
 }
 
+// Out of line for the builds whose hot path is the register-resident iteration (the shared-memory walk is their rare
+// retry); the builds for longer horizons / more footsteps inline forma_pdas_body -- behind a call the structs arrive by
+// address and every shared-memory access is a generic load.
+template <int FT>
+__device__ __noinline__ int forma_pdas(const FormAShared& sm, const FormAProb& pb, double beq, double shift,
+                                       const double* planf, const double* rg, int maxit, int* iters_out)
+{
+    return forma_pdas_body<FT>(sm, pb, beq, shift, planf, rg, maxit, iters_out);
+}
+
 }  // namespace ismpc
 #include "forma_reg.cuh"
 namespace ismpc {
@@ -655,16 +668,16 @@ __device__ __forceinline__ void forma_selfcheck(const FormAShared& sm, int C, in
 // small enough for the instruction cache and the register budget: the shared-memory build of the structured solve
 // (shapes the register build does not cover: C > 128 or F > 3, or `forma_reg` = 0) and the dual active set that
 // backs both up.  On entry the bounds are in shifted coordinates iff use_pdas != 0.  Returns status bits.
-template <int FT>
-__device__ __forceinline__ int forma_solve_slow_body(const FormAShared* smp, const FormAProb* pbp, double beq, double cur, int warm,
-                                                     int use_pdas, int tried_reg, const double* rg, int* iters_io,
-                                                     double* eqv_out, double* viol_out)
+// (by reference / by value, never through pointers to the caller's structs: an address taken of them sends them to local
+// memory, and every shared-memory access behind them turns into a generic load)
+template <int FT, bool INL>
+__device__ __forceinline__ int forma_solve_slow_body(const FormAShared& sm, const FormAProb pb, double beq, double cur, int warm,
+                                                     int use_pdas, int tried_reg, const double* rg, int& iters_io,
+                                                     double& eqv_out, double& viol_out)
 {
-    const FormAShared& sm = *smp;
-    FormAProb pb = *pbp;
     const int lane = lane_id();
     const int C = pb.C, F = pb.F, n = C + F;
-    int status = 0, iters = *iters_io;
+    int status = 0, iters = iters_io;
     double eqv = 0.0, viol = 0.0;
     bool solved = false;
     if (use_pdas && !tried_reg) {
@@ -675,7 +688,8 @@ __device__ __forceinline__ int forma_solve_slow_body(const FormAShared* smp, con
                 __syncwarp();
             }
             int it2 = 0;
-            rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
+            if constexpr (INL) rc = forma_pdas_body<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
+            else rc = forma_pdas<FT>(sm, pb, beq, cur, sm.z, rg, PDAS_MAX_ITERS, &it2);
             iters += it2;
         }
         if (rc == 0) {
@@ -702,18 +716,19 @@ __device__ __forceinline__ int forma_solve_slow_body(const FormAShared* smp, con
         if (use_pdas) status |= ISMPC_ST_GI_FALLBACK;
         DasWork w = sm.das;
         w.q = 0; w.neq = 0;
-        int rc = das_add_equality(pb, w, sm.x, sm.z, n, 0.0, beq);
+        FormAProb pbd = pb;              // (the dual active set takes the problem by reference: a copy, so that pb does not escape)
+        int rc = das_add_equality(pbd, w, sm.x, sm.z, n, 0.0, beq);
         if (rc < 0) status |= ISMPC_ST_QP_FAIL;
         w.neq = w.q;
         int it2 = 0;
-        rc = das_solve(pb, w, sm.x, sm.rv, sm.z, 6 * n + 50, &it2);
+        rc = das_solve(pbd, w, sm.x, sm.rv, sm.z, 6 * n + 50, &it2);
         iters += it2;
         if (rc != 0) status |= ISMPC_ST_QP_FAIL;
         forma_selfcheck(sm, C, n, eqv, viol);
         // a point that misses the stability row or a bound is not a solution, whatever the loop returned
         if (!(fabs(eqv - beq) <= 1e-7 * fmax(1.0, fabs(beq))) || !(viol <= 1e-7)) status |= ISMPC_ST_QP_FAIL;
     }
-    *iters_io = iters; *eqv_out = eqv; *viol_out = viol;
+    iters_io = iters; eqv_out = eqv; viol_out = viol;
     return status;
 }
 
@@ -722,7 +737,7 @@ __device__ __noinline__ int forma_solve_slow(const FormAShared* smp, const FormA
                                              int use_pdas, int tried_reg, const double* rg, int* iters_io, double* eqv_out,
                                              double* viol_out)
 {
-    return forma_solve_slow_body<FT>(smp, pbp, beq, cur, warm, use_pdas, tried_reg, rg, iters_io, eqv_out, viol_out);
+    return forma_solve_slow_body<FT, false>(*smp, *pbp, beq, cur, warm, use_pdas, tried_reg, rg, *iters_io, *eqv_out, *viol_out);
 }
 
 // One tick for one (instance, axis) by one warp.  Returns status bits; writes x (primal) in sm.x.
@@ -897,7 +912,7 @@ __device__ inline int forma_tick_axis(const FormAShared& sm, const ismpc_forma_m
             status |= forma_solve_slow<FT>(&smc, &pbc, beq, cur, warm, use_pdas, tried_reg, rg, &it_c, &eqv_c, &viol_c);
             iters = it_c; eqv = eqv_c; viol = viol_c;
         } else {
-            status |= forma_solve_slow_body<FT>(&sm, &pb, beq, cur, warm, use_pdas, tried_reg, rg, &iters, &eqv, &viol);
+            status |= forma_solve_slow_body<FT, true>(sm, pb, beq, cur, warm, use_pdas, tried_reg, rg, iters, eqv, viol);
         }
     }
     *iters_out = iters;
