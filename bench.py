@@ -323,13 +323,13 @@ def main():
     pdl_equal = None
     try:
         ref_out = [slots[(W + k) % n_slots]["out"].clone() for k in range(min(K, 4))]
-        h.set_option("formc_pdl", 1)
+        h.set_option("formc_pdl", 1); h.set_option("formc_variant", 2)      # (automatic would pick the throughput build under pdl)
         gp = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gp, stream=cs):
             sp = torch.cuda.current_stream().cuda_stream
             for k in range(K):
                 step(W + k, on=sp)
-        h.set_option("formc_pdl", 0)
+        h.set_option("formc_pdl", 0); h.set_option("formc_variant", 0)
         gp.replay(); barrier()
         pdl_equal = all(bool(torch.equal(ref_out[k], slots[(W + k) % n_slots]["out"])) for k in range(len(ref_out)))
         for r in range(R):
@@ -339,7 +339,7 @@ def main():
             barrier()
             pdl_ms.append(sharding.max_over_ranks(g0.elapsed_time(g1), device=dev))
     except Exception as e:
-        h.set_option("formc_pdl", 0)
+        h.set_option("formc_pdl", 0); h.set_option("formc_variant", 0)
         print("bench.py: programmatic-dependent-launch arm skipped (%s)" % e, file=sys.stderr)
     use_pdl = bool(pdl_ms) and pdl_equal
     # ---- ... and with the THROUGHPUT build of the tick kernel (formc_variant = 16: one warp per instance held to 128

@@ -205,7 +205,9 @@ void ismpc_host_free(void* p);
  *                         still run (the tick of 1,024 instances is latency-bound: median CTA 6.8 us, slowest 9.2 us).
  *                         The caller thereby DECLARES consecutive calls on that stream independent: a call must not read
  *                         device buffers the previous call writes, nor share its output buffers.  Default 0: calls
- *                         on a stream are strictly ordered (a tick may consume the previous tick's output).
+ *                         on a stream are strictly ordered (a tick may consume the previous tick's output).  With
+ *                         "formc_variant" = 0 a handle with formc_pdl = 1 runs the throughput build (16): in a stream of
+ *                         ticks two of them then overlap completely (5.9 instead of 6.8 us per 1,024-instance tick).
  *   "host_zero_copy":     ismpc_formc_solve_batch_packed with host buffers: 1 (default; ISMPC_HOST_ZERO_COPY sets the default at
  *                         creation) = the kernel reads / writes pinned host buffers itself, 0 = staging buffers and copies.
  *   "dense_dmma":         ismpc_qp_solve_batch: 1 = condensing GEMMs on the FP64 tensor cores (DMMA, default), 0 = CUDA cores.

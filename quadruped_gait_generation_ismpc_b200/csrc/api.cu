@@ -564,7 +564,8 @@ extern "C" int ismpc_formc_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc
     if (!h->formc_ready) return ISMPC_ERR_MODEL;
     const bool plan_res = plan_xyzt == nullptr;
     if (plan_res) plan_rows = h->plan_res_rows;
-    if (n < 0 || n > h->max_batch || n_ticks < 0 || !state || !walk || !inst || plan_rows <= 0)
+    const bool inst_res = inst == nullptr;      // the per-instance constants given to ismpc_formc_set_instances
+    if (n < 0 || n > h->max_batch || n_ticks < 0 || !state || !walk || (inst_res && n > h->inst_res_n) || plan_rows <= 0)
         return ISMPC_ERR_ARG;
     if (n == 0 || n_ticks == 0) return ISMPC_OK;
     CK(cudaSetDevice(h->device));
@@ -573,14 +574,15 @@ extern "C" int ismpc_formc_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc
     formc_fill_args(h, a, n);
     a.out = nullptr; a.primal = nullptr; a.active = nullptr; a.plan_rows = plan_rows;
     if (mem == ISMPC_MEM_DEVICE) {
-        a.state = state; a.walk = walk; a.inst = inst; a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt;
+        a.state = state; a.walk = walk; a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : inst;
+        a.plan = plan_res ? (const double*)h->c_plan.p : plan_xyzt;
         int rc = formc_launch_rollout(h, a, n, state, walk, push, n_ticks, traj_opt, status_opt, status_trace_opt, st);
         h->launches += 1;
         if (rc) return fail_cuda(h, (cudaError_t)rc, "formc_rollout_launch");
         return ISMPC_OK;
     }
     if (mem != ISMPC_MEM_HOST) return ISMPC_ERR_ARG;
-    if (h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
+    if (!inst_res && h->ric_S + h->ric_F == 0 && inst[0].S + inst[0].F_ds > 0 && inst[0].S >= 0 && inst[0].F_ds >= 0) {
         int prc = ismpc_formc_prepare_gait(h, inst[0].S, inst[0].F_ds);
         if (prc != ISMPC_OK) return prc;
         formc_fill_args(h, a, n);
@@ -596,11 +598,11 @@ extern "C" int ismpc_formc_rollout_ex(ismpc_handle* h, int n, int n_ticks, ismpc
     if (status_trace_opt && h->s_trace.ensure((size_t)n * n_ticks * sizeof(int32_t))) return ISMPC_ERR_ALLOC;
     CK(cudaMemcpyAsync(h->s_state.p, state, n * sizeof(ismpc_state_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_walk.p, walk, n * sizeof(ismpc_walk_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
+    if (!inst_res) CK(cudaMemcpyAsync(h->s_cinst.p, inst, n * sizeof(ismpc_formc_inst_t), cudaMemcpyHostToDevice, st));
     if (!plan_res) CK(cudaMemcpyAsync(h->s_plan.p, plan_xyzt, (size_t)plan_rows * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (push) CK(cudaMemcpyAsync(h->s_push.p, push, n * sizeof(ismpc_push_t), cudaMemcpyHostToDevice, st));
     a.state = (const ismpc_state_t*)h->s_state.p; a.walk = (const ismpc_walk_t*)h->s_walk.p;
-    a.inst = (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
+    a.inst = inst_res ? (const ismpc_formc_inst_t*)h->c_inst.p : (const ismpc_formc_inst_t*)h->s_cinst.p; a.plan = plan_res ? (const double*)h->c_plan.p : (const double*)h->s_plan.p;
     int rc = formc_launch_rollout(h, a, n, (ismpc_state_t*)h->s_state.p, (ismpc_walk_t*)h->s_walk.p,
                                   push ? (const ismpc_push_t*)h->s_push.p : nullptr, n_ticks,
                                   traj_opt ? (double*)h->s_traj.p : nullptr,

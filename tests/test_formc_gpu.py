@@ -329,6 +329,11 @@ def test_packed_tick_records_and_resident_instances(handle, variant):
         handle.formc_set_plan(plan); handle.formc_set_instances(inst)
         same(handle.formc_solve_batch_packed(tick, None, None))                      # pageable, constants and plans resident
         same(handle.formc_solve_batch(state, walk, None, None))                      # three arrays, constants resident
+        ra = handle.formc_rollout(state, walk, inst, plan, 12)                       # closed loop: constants per call ...
+        st_r, wk_r = state.copy(), walk.copy()
+        traj_r = np.zeros((len(st_r), 12, 6)); status_r = np.zeros(len(st_r), dtype=np.int32)
+        handle.formc_rollout_raw(len(st_r), 12, st_r, wk_r, None, None, 0, traj=traj_r, status=status_r, mem=abi.MEM_HOST)
+        assert np.array_equal(ra["traj"], traj_r) and ra["state"].tobytes() == st_r.tobytes()      # ... == resident
         # pinned buffers: the kernel reads the tick records and writes the result records in place
         n = len(tick)
         t_pin = torch.from_numpy(tick.view(np.uint8).reshape(-1).copy()).pin_memory()
@@ -481,11 +486,13 @@ def test_out_of_range_plan_rows_are_flagged_not_read(handle):
         assert np.array_equal(r["state"]["com_pos"][i], state["com_pos"][i])
 
 
-def test_programmatic_dependent_launch_gives_the_same_records(handle):
+@pytest.mark.parametrize("variant", [2, 16])
+def test_programmatic_dependent_launch_gives_the_same_records(handle, variant):
     """`formc_pdl` = 1: consecutive ticks on one stream are launched as programmatic dependents (a tick's CTAs start while
     the previous tick's last CTAs still run).  Twelve independent batches back to back -- a third of the instances on the
     general vertical path, whose per-CTA workspace is shared between consecutive launches of a handle and is therefore
-    fenced with griddepcontrol.wait -- give bit for bit the records of strictly ordered launches."""
+    fenced with griddepcontrol.wait -- give bit for bit the records of strictly ordered launches, for the two-warp latency
+    build and for the throughput build (the one the automatic choice takes under formc_pdl)."""
     import torch
     model = abi.formc_model()
     handle.formc_set_model(model); handle.formc_prepare_gait(35, 10)
@@ -500,7 +507,7 @@ def test_programmatic_dependent_launch_gives_the_same_records(handle):
     stream = torch.cuda.current_stream().cuda_stream
 
     def run(pdl):
-        handle.set_option("formc_pdl", pdl)
+        handle.set_option("formc_pdl", pdl); handle.set_option("formc_variant", variant)
         outs = [torch.zeros(n * abi.FORMC_OUT.itemsize, dtype=torch.uint8, device=dev) for _ in range(nb)]
         try:
             for rep in range(3):
@@ -509,7 +516,7 @@ def test_programmatic_dependent_launch_gives_the_same_records(handle):
                                                  batches[b][3].shape[0], outs[b].data_ptr(), mem=abi.MEM_DEVICE, stream=stream)
             torch.cuda.synchronize()
         finally:
-            handle.set_option("formc_pdl", 0)
+            handle.set_option("formc_pdl", 0); handle.set_option("formc_variant", 0)
         return [np.frombuffer(o.cpu().numpy().tobytes(), dtype=abi.FORMC_OUT) for o in outs]
 
     a, b = run(0), run(1)
