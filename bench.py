@@ -503,8 +503,10 @@ def main():
     hostlib.ismpc_host_pool_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     plans_c = np.ascontiguousarray(all_plans, dtype=np.float64)
     cores_per_rank = max(1, (os.cpu_count() or 1) // world)
-    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "2" if cores_per_rank >= 4 else "1"))   # host threads, one pipeline each
-    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "4" if T_HOST > 1 else "6"))           # calls in flight per thread
+    # host threads (one pipeline each) x calls in flight per thread: 3 x 3 -- on one GPU every shape from 2 x 4 to 4 x 3 gives
+    # the same 385-396 M QP/s; with 8 ranks on a 32-vCPU box 3 x 3 ran 2.11 G against 1.96 G (2 x 4), 2.03 G (4 x 2), 1.71 G (2 x 6)
+    T_HOST = int(os.environ.get("ISMPC_E2E_THREADS", "3" if cores_per_rank >= 4 else "1"))
+    D_HOST = int(os.environ.get("ISMPC_E2E_DEPTH_CPP", "3" if T_HOST > 1 else "8"))
     pool = hostlib.ismpc_host_pool_create(local, n, T_HOST, D_HOST, model.ctypes.data, 35, 10, plans_c.ctypes.data, plans_c.shape[0])
     if not pool:
         raise RuntimeError("ismpc_host_pool_create: " + hostlib.ismpc_host_last_error().decode())

@@ -269,7 +269,8 @@ typedef struct {
  * not change from tick to tick) to the handle once; afterwards ismpc_formc_solve_batch, ismpc_formc_solve_batch_packed and
  * the rollouts accept inst = NULL for calls with n <= the n given here.  n = 0 forgets them.  mem = ISMPC_MEM_HOST or
  * ISMPC_MEM_DEVICE says where `inst` lives; the call synchronises.  With host memory the gait of instance 0 is prepared
- * as ismpc_formc_prepare_gait would. */
+ * as ismpc_formc_prepare_gait would.  Like ismpc_formc_set_plan it replaces data that ticks read: call it while no work
+ * of this handle is in flight. */
 int ismpc_formc_set_instances(ismpc_handle* h, const ismpc_formc_inst_t* inst, int n, int mem);
 
 /* ismpc_formc_solve_batch with the per-tick arguments packed: tick[i] = {state, walk} of instance i (128-byte records;
