@@ -651,7 +651,12 @@ static int forma_common(ismpc_handle* h, int n, int n_ticks, bool rollout, ismpc
     a.n = n; a.model = h->am; a.timing_len = timing_len; a.plan_rows = plan_rows; a.sm_count = h->sm_count;
     FormALaunchPlan lp;
     forma_plan(h->am, h->sm_count, 2LL * n, h->a_tune, &lp, &h->a_occ);
-    if (h->a_Lwork.ensure((lp.spill_doubles + 2) * sizeof(double)) || h->a_queue.ensure(sizeof(int))) return ISMPC_ERR_ALLOC;
+    if (h->a_Lwork.ensure((lp.spill_doubles + 2) * sizeof(double))) return ISMPC_ERR_ALLOC;
+    if (!h->a_queue.p) {
+        // work-queue head + exit counter of the form-A kernels: zeroed once, every launch leaves them at zero (forma_queue_exit)
+        if (h->a_queue.ensure(2 * sizeof(int))) return ISMPC_ERR_ALLOC;
+        CK(cudaMemset(h->a_queue.p, 0, 2 * sizeof(int)));
+    }
     a.Jspill = lp.spill_doubles ? (double*)h->a_Lwork.p : nullptr;
     a.queue = (int*)h->a_queue.p;
     a.R = lp.R; a.warps_per_cta = lp.warps_per_cta;

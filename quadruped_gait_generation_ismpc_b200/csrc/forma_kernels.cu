@@ -31,6 +31,17 @@ __device__ __forceinline__ long long forma_next_item(int* queue)
     return (long long)__shfl_sync(ISMPC_FULL_MASK, v, 0);
 }
 
+// A warp that finds the queue empty leaves through here: the LAST warp of the launch to do so puts the queue head and the
+// exit counter back to zero, so that the next launch on the handle needs no memset in front of it (every other warp has made
+// its final, failing poll before it counted itself out, so nobody polls a reset head).  queue[0] = head, queue[1] = exits.
+__device__ __forceinline__ void forma_queue_exit(int* queue, int total_warps)
+{
+    if (lane_id() == 0) {
+        const int e = atomicAdd(queue + 1, 1);
+        if (e == total_warps - 1) { queue[0] = 0; queue[1] = 0; }
+    }
+}
+
 // plan rows / timing entries of an instance record inside the tables handed to the call (a step needs two timing entries)
 __device__ __forceinline__ bool forma_inst_in_range(const ismpc_forma_inst_t& in, const int32_t* fs_timing, int plan_rows,
                                                     int timing_len)
@@ -60,7 +71,7 @@ __global__ void __maxnreg__(HOT ? FORMA_MAX_REGS : 255) forma_tick_kernel(FormAA
                 a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
     for (;;) {
         const long long item = forma_next_item(a.queue);
-        if (item >= 2LL * a.n) break;
+        if (item >= 2LL * a.n) { forma_queue_exit(a.queue, (int)gridDim.x * a.warps_per_cta); break; }
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
 #ifdef ISMPC_PHASE_TIMING
         const long long t_item0 = dbg_globaltimer();
@@ -131,7 +142,7 @@ __global__ void __maxnreg__(HOT ? FORMA_MAX_REGS : 255) forma_rollout_kernel(For
                 a.Jspill ? a.Jspill + slot * forma_spill_doubles(C, F, a.R) : nullptr, sm);
     for (;;) {
         const long long item = forma_next_item(a.queue);
-        if (item >= 2LL * a.n) break;
+        if (item >= 2LL * a.n) { forma_queue_exit(a.queue, (int)gridDim.x * a.warps_per_cta); break; }
         const int inst = (int)(item >> 1), axis = (int)(item & 1);
         const ismpc_forma_inst_t in = ra.inst_io[inst];
         if (!forma_inst_in_range(in, a.fs_timing, a.plan_rows, a.timing_len)) {        // never read outside the caller's tables
@@ -272,7 +283,7 @@ int forma_tick_launch(const FormAArgs& a_in, const FormALaunchPlan& p, cudaStrea
     auto kern = p.kernel == 0 ? forma_tick_kernel<3, true> : p.kernel == 1 ? forma_tick_kernel<3, false> : forma_tick_kernel<ISMPC_MAX_FSTEPS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
-    cudaMemsetAsync(a.queue, 0, sizeof(int), st);
+    // (the work-queue head needs no reset: the previous launch on this handle left it at zero, forma_queue_exit)
     cudaMemsetAsync(a.out, 0, (size_t)a.n * sizeof(ismpc_forma_out_t), st);
     kern<<<p.grid, 32 * p.warps_per_cta, p.smem, st>>>(a);
     return (int)cudaGetLastError();
@@ -287,7 +298,6 @@ int forma_rollout_launch(const FormAArgs& a_in, const FormALaunchPlan& p, ismpc_
     auto kern = p.kernel == 0 ? forma_rollout_kernel<3, true> : p.kernel == 1 ? forma_rollout_kernel<3, false> : forma_rollout_kernel<ISMPC_MAX_FSTEPS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return (int)e;
-    cudaMemsetAsync(a.queue, 0, sizeof(int), st);
     if (status) cudaMemsetAsync(status, 0, (size_t)a.n * sizeof(int32_t), st);
     if (trace) cudaMemsetAsync(trace, 0, (size_t)a.n * n_ticks * 2 * sizeof(int32_t), st);   // skipped records write nothing
     FormARolloutArgs ra{a, inst_io, fs_plan_io, push, n_ticks, traj, pred, status, trace};
