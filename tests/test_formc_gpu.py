@@ -453,6 +453,22 @@ def test_batch_beyond_residency_grid_stride(handle):
             assert np.abs(part["out"]["zmp_in"] - big["out"]["zmp_in"][sl]).max() <= 1e-12
     finally:
         handle.set_option("formc_variant", 0)
+    # the packed builds walk the batch the same way (the tick record is re-staged for every instance a CTA takes): pinned
+    # records read in place, the automatic build and the two-warp build forced beyond its residency
+    import torch
+    tick = abi.pack_ticks(state, walk)
+    t_pin = torch.from_numpy(tick.view(np.uint8).reshape(-1).copy()).pin_memory()
+    o_pin = torch.zeros(len(tick) * abi.FORMC_OUT.itemsize, dtype=torch.uint8).pin_memory()
+    handle.formc_set_plan(plan); handle.formc_set_instances(inst)
+    try:
+        for variant in (0, 2):
+            handle.set_option("formc_variant", variant)
+            ref = handle.formc_solve_batch(state, walk, inst, plan, want_primal=False, want_active=False)["out"]
+            o_pin.zero_()
+            handle.formc_solve_batch_packed_raw(len(tick), t_pin.data_ptr(), None, None, 0, o_pin.data_ptr(), mem=abi.MEM_HOST)
+            assert o_pin.numpy().tobytes() == ref.tobytes(), "variant %d" % variant
+    finally:
+        handle.set_option("formc_variant", 0); handle.formc_set_plan(None); handle.formc_set_instances(None)
 
 
 def test_out_of_range_plan_rows_are_flagged_not_read(handle):

@@ -6,6 +6,7 @@
 tag=${1:-rX}
 o=gpurun_out
 python -m pytest tests -q -m gpu > $o/${tag}_tests.log 2>&1; tail -2 $o/${tag}_tests.log
+python __graft_entry__.py smoke > $o/${tag}_smoke.log 2>&1; tail -1 $o/${tag}_smoke.log
 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference.json 2> $o/${tag}_bench_reference.err
 python bench.py --steps 20 --warmup 5 > $o/${tag}_bench.json 2> $o/${tag}_bench.err; tail -2 $o/${tag}_bench.err
 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $o/${tag}_b_small.json 2> $o/${tag}_b_small.err && \
