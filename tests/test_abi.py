@@ -86,6 +86,20 @@ def test_plumbing_entry_points_reject_bad_arguments():
         assert L.ismpc_host_alloc(4096) is None
 
 
+def test_packed_entry_points_reject_bad_arguments_without_touching_the_device():
+    """ismpc_formc_set_instances / ismpc_formc_solve_batch_packed: a NULL handle is refused before anything else happens
+    (the same on a box without a GPU); the packed record is 128 bytes, state first, walk state at byte 72."""
+    L = binding.lib()
+    tick = np.zeros(4, dtype=abi.FORMC_TICK); out = np.zeros(4, dtype=abi.FORMC_OUT); inst = np.zeros(4, dtype=abi.FORMC_INST)
+    assert L.ismpc_formc_set_instances(None, inst.ctypes.data, 4, abi.MEM_HOST) != 0
+    assert L.ismpc_formc_solve_batch_packed(None, 4, tick.ctypes.data, None, None, 0, out.ctypes.data, None, None, abi.MEM_HOST, None) != 0
+    assert abi.FORMC_TICK.itemsize == 128 and abi.FORMC_TICK.fields["state"][1] == 0 and abi.FORMC_TICK.fields["walk"][1] == 72
+    st = np.zeros(3, dtype=abi.STATE); wk = np.zeros(3, dtype=abi.WALK)
+    st["com_pos"] = np.arange(9).reshape(3, 3); wk["mpc_iter"] = [7, 8, 9]; wk["sim_time"] = [0.5, 1.5, 2.5]
+    t = abi.pack_ticks(st, wk)
+    assert t["state"].tobytes() == st.tobytes() and t["walk"].tobytes() == wk.tobytes() and not t["reserved"].any()
+
+
 def test_host_library_uses_only_the_c_abi():
     """lib/libismpc_host.so (the C++ serving loop) links against the product library and the C++ runtime only: no CUDA
     runtime, no torch -- it is what a C++ caller of the reference's class would compile with plain g++."""
