@@ -814,7 +814,7 @@ def bench_group(torch, G, n, K, W, R, model, host_batches):
         for b in range(2):
             tk = abi.pack_ticks(np.tile(host_batches[0][0], G), np.tile(host_batches[0][1], G))
             if b:
-                tk["state"]["com_vel"] *= 0.5             # a second, different block of tick records for the same fleet
+                tk["state"]["com_vel"] *= 1.001           # a second, slightly different block of tick records for the same fleet
             tks.append(binding.PinnedBuffer(tk.nbytes, fill=tk))
         for k in range(max(W, 2)):
             g.formc_solve_batch_packed_raw(N, tks[k % 2].ptr, out_p)
