@@ -72,15 +72,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
+    def __init__(self, gpu_indices, period_ms=20):
+        self.idx = ",".join(str(i) for i in gpu_indices)
+        self.period = int(period_ms)
         self.lines = []
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -275,7 +276,11 @@ def main():
 
     # clocks / throttle reasons are sampled (nvidia-smi -lms 20) from before the warm-up until the end of the e2e loops:
     # the device-timed region alone lasts a few milliseconds, shorter than nvidia-smi's start-up
-    clocks = ClockSampler(local); clocks.start()
+    # ONE sampler for the job (rank 0 watches every GPU of it): eight nvidia-smi loops -- one per rank -- query the driver 400
+    # times a second between them and get in the way of the very loops they are meant to watch
+    clocks = ClockSampler(range(world), 20 if world == 1 else 50) if rank == 0 else None
+    if clocks:
+        clocks.start()
     for k in range(W):
         step(k)
     barrier()
@@ -583,7 +588,7 @@ def main():
         dma_runs.append(sharding.max_over_ranks(el.value, device=dev))
     e2e_dma_s = statistics.median(dma_runs)
     hostlib.ismpc_host_pool_destroy(pool)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
 
     # ---- final gather of the result records (the only collective on this path) -----------------------------
     last = np.frombuffer(slots[(W + K - 1) % n_slots]["out"].cpu().numpy().tobytes(), dtype=abi.FORMC_OUT)
@@ -770,6 +775,13 @@ def bench_group(torch, G, n, K, W, R, model, host_batches):
     import ctypes as C
     N = n * G
     L = binding.lib()
+    # rank 0 was pinned to its own slice of the CPUs for the per-rank loops; here it drives every GPU with one host thread
+    # each, so it takes the whole box (the other ranks sleep in a barrier); restored on the way out
+    aff0 = os.sched_getaffinity(0)
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
     g = binding.Group(list(range(G)), max(n, 1000), binding.GATHER_NCCL)
     res = {"devices": G, "how": "rank 0 alone drives all %d GPUs through lib/libismpc_b200_mg.so (one handle, stream and host "
                                "thread per device, contiguous shards); the other ranks wait on a CPU barrier" % G}
@@ -863,6 +875,10 @@ def bench_group(torch, G, n, K, W, R, model, host_batches):
         res["kernel_launches"] = g.kernel_launches
     finally:
         g.close()
+        try:
+            os.sched_setaffinity(0, aff0)
+        except OSError:
+            pass
     return res
 
 
