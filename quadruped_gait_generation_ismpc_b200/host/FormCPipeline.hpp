@@ -69,6 +69,8 @@ public:
         wait(s);
         return s;
     }
+    // start the round robin over at slot 0 (call with no tick in flight, e.g. after wait_all)
+    void rewind() { next_ = 0; }
     void wait(int s) { check(ismpc_wait(slots_[s].h, slots_[s].stream), slots_[s].h, "ismpc_wait"); }
     void wait_all() { for (int s = 0; s < depth(); ++s) wait(s); }
     void submit(int s) { submit_from(s, state(s), walk(s), inst(s)); }

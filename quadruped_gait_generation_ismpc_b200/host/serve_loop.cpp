@@ -147,6 +147,7 @@ struct HostPool {
         try {
             int submitted = 0;
             double t_wait = 0.0, t_submit = 0.0;
+            p.rewind();              // every run ends with wait_all: slot j % depth serves this thread's j-th step of the run
             auto now = [] { return std::chrono::steady_clock::now(); };
             for (int k = k0 + t; k < k0 + steps; k += T, ++submitted) {
                 const auto a0 = now();
