@@ -241,6 +241,7 @@ int ismpc_formc_set_plan(ismpc_handle* h, const double* plan_xyzt, int plan_rows
 /* One tick of MPCSolver::solve (MPCSolver.cpp:204-501) for n independent instances.
  * plan_xyzt: plan_rows x 4 doubles row-major (x, y, z, t) -- ftsp_and_timings (Controller.cpp:89-97); NULL = the
  *            table given to ismpc_formc_set_plan.
+ * inst:      NULL = the records given to ismpc_formc_set_instances (n must not exceed their number).
  * primal_opt (nullable): n x 3N doubles  [f(N) | u_x(N) | u_y(N)] per instance.
  * active_opt (nullable): n x 3N int8    [S_bar_z rows | x box rows | y box rows], -1 lower / 0 / +1 upper,
  *                        the convention of QProblem::getWorkingSetConstraints (qpOASES/QProblem.cpp:809-829);
