@@ -124,8 +124,9 @@ def workload_config(n):
             "launch": "GPU arm: CUDA graph of the K steps (one kernel node per step, launched as programmatic dependents: the "
                       "steps are independent batches), replayed once per timed repeat; the median of the repeats is "
                       "reported, every repeat and the strictly ordered arm beside it (`repeats`, `strictly_ordered`)",
-            "l2": "GPU arm: a 256 MB buffer is written before every timed repeat (L2 = 126 MB flushed), and the K steps "
-                  "of a repeat read K distinct device batches (1.6 MB each) that no earlier launch of the repeat touched"}
+            "l2": "GPU arm: a 256 MB buffer is written before every timed repeat (L2 = 126 MB flushed), and the steps of a "
+                  "repeat rotate over 126 distinct device batches (1.6 MB each, 199 MB > L2): a batch is never read again "
+                  "before 198 MB of other batches have gone through the cache"}
 
 
 def cpu_reference_run(steps, warmup, sample_n=None, threads=None):
