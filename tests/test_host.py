@@ -62,3 +62,22 @@ def test_synth_batches_are_deterministic_and_in_window():
     assert ((walk["sim_time"] + 200) <= inst["n_steps"] * per).all()
     ai, ft, fp = synth.forma_batch(8, seed=4, vary=True)
     assert (ai["j"] == 1).all() and fp.shape == (800, 2) and (ai["timing_first"] + ai["n_timing"] <= len(ft)).all()
+
+
+def test_bench_cpu_pinning_degrades_gracefully():
+    """bench.py pins a rank's host threads next to its GPU (sysfs + nvidia-smi); on a box without a GPU it reports the
+    error and leaves the affinity alone; whatever it does, the process keeps at least one CPU."""
+    import os
+    import bench
+    before = os.sched_getaffinity(0)
+    try:
+        r = bench.pin_to_gpu_numa_node(0, 1)
+        assert isinstance(r, dict)
+        after = os.sched_getaffinity(0)
+        assert len(after) >= 1
+        if "error" in r:
+            assert after == before
+        else:
+            assert set(r["cpus_of_this_rank"]) == after and after <= before
+    finally:
+        os.sched_setaffinity(0, before)
